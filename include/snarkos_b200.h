@@ -1,0 +1,127 @@
+/*
+ * snarkos_b200.h -- C ABI of the B200-native BLS12-377 MSM / Fr-NTT hot path.
+ *
+ * Drop-in boundary for the path snarkOS reaches through snarkVM:
+ *
+ *   snarkvm-algorithms  msm::VariableBase::msm(bases, scalars)            -> b200_msm_g1_bls12_377
+ *       [UPSTREAM algorithms/src/msm/variable_base/mod.rs; reached from snarkOS at
+ *        node/src/validator/mod.rs:383-391 (prove), node/bft/ledger-service/src/ledger.rs:341,346 (verify)]
+ *   snarkvm-algorithms  fft::EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place
+ *                                                                         -> b200_ntt_fr_bls12_377
+ *       [UPSTREAM algorithms/src/fft/domain.rs: in_order_fft_in_place / in_order_ifft_in_place /
+ *        in_order_coset_fft_in_place / in_order_coset_ifft_in_place]
+ *
+ * The hook precedent is snarkVM's own optional `cuda` feature (snarkvm-algorithms-cuda: extern "C"
+ * snarkvm_msm + NTT entry points behind a type-id / size guard); this library replaces that backend
+ * without reusing it.  A Rust -sys binding is shown in INTEGRATION.md.
+ *
+ * Data conventions (identical to snarkVM's in-memory layout, little-endian u64 limbs):
+ *   Fr element      32 B, Montgomery form (value * 2^256 mod r), fully reduced
+ *   Fq element      48 B, Montgomery form (value * 2^384 mod p), fully reduced
+ *   G1Affine        `affine_stride` bytes (104 for rustc's layout): x @0, y @48, infinity flag byte @96
+ *   scalar          32 B BigInteger256, canonical (NOT Montgomery), < r
+ *   G1Projective    144 B Jacobian (X, Y, Z) Montgomery; Z = 0 <=> infinity (returned as (1, 1, 0))
+ *
+ * Error model: every call returns b200_error_t; code == 0 is success, code > 0 is a cudaError_t,
+ * code < 0 is a library error.  msg points to a static string.  Nothing throws across the ABI.
+ * There is NO CPU fallback: without a CUDA device every compute call fails with a non-zero code.
+ *
+ * Threading: all entry points are re-entrant; concurrent callers (rayon workers, tokio blocking
+ * threads) each run on their own CUDA stream.
+ */
+#ifndef SNARKOS_B200_H
+#define SNARKOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int32_t code;
+    const char* msg;
+} b200_error_t;
+
+enum {
+    B200_OK = 0,
+    B200_ERR_INVALID_ARG = -1,
+    B200_ERR_NO_DEVICE = -2,
+    B200_ERR_TOO_LARGE = -3,
+    B200_ERR_BAD_HANDLE = -4,
+    B200_ERR_NOT_INITIALIZED = -5
+};
+
+enum { B200_NTT_FORWARD = 0, B200_NTT_INVERSE = 1 };
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+/* Bind the calling process to CUDA device `device` (one process per GPU) and build the static
+ * tables.  Idempotent.  b200_shutdown releases every cached table and registered base set. */
+b200_error_t b200_init(int device);
+void b200_shutdown(void);
+/* ABI version of this header (for the -sys crate's build-time check). */
+uint32_t b200_abi_version(void);
+
+/* ---- VariableBase::msm ------------------------------------------------------------------------
+ * out_jacobian_144B = sum_i scalars[i] * points[i].  Host buffers; copies are done internally.    */
+b200_error_t b200_msm_g1_bls12_377(void* out_jacobian_144B, const void* points, size_t npoints,
+                                   const void* scalars_32B_canonical, size_t affine_stride);
+/* Same, all pointers are DEVICE pointers; work is enqueued on `stream` (cudaStream_t, may be NULL)
+ * and the call returns without synchronising. */
+b200_error_t b200_msm_g1_bls12_377_device(void* d_out_jacobian_144B, const void* d_points, size_t npoints,
+                                          const void* d_scalars, size_t affine_stride, void* stream);
+
+/* Resident bases (the SRS `powers_of_beta_g` is fixed for the process lifetime -- KZG10::commit
+ * [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs] calls msm on a prefix of it every time). */
+b200_error_t b200_msm_register_bases(const void* points, size_t npoints, size_t affine_stride,
+                                     uint64_t* out_handle);
+b200_error_t b200_msm_register_bases_device(const void* d_points, size_t npoints, size_t affine_stride,
+                                            void* stream, uint64_t* out_handle);
+/* MSM over the first `nscalars` registered bases (nscalars <= registered count). */
+b200_error_t b200_msm_registered(void* out_jacobian_144B, uint64_t handle, const void* scalars,
+                                 size_t nscalars);
+b200_error_t b200_msm_registered_device(void* d_out_jacobian_144B, uint64_t handle, const void* d_scalars,
+                                        size_t nscalars, void* stream);
+b200_error_t b200_msm_release_bases(uint64_t handle);
+
+/* Window width the library would pick for `npoints` (0 = library default); B200_MSM_C overrides. */
+uint32_t b200_msm_window_bits(size_t npoints);
+
+/* Sum of `count` Jacobian points (144 B each): the multi-GPU partial-sum combine.  Device pointers. */
+b200_error_t b200_g1_sum_jacobian_device(void* d_out_jacobian_144B, const void* d_in, size_t count,
+                                         void* stream);
+
+/* ---- EvaluationDomain (i)FFT -------------------------------------------------------------------
+ * In-place transform of `batch` polynomials of 2^log_n Montgomery Fr elements, natural order in and
+ * out; polynomial b starts at element b * batch_stride_elems.  direction: B200_NTT_FORWARD /
+ * B200_NTT_INVERSE (inverse includes the n^-1 scaling).  coset != 0 selects coset_fft_in_place
+ * (input j scaled by 22^j first) / coset_ifft_in_place (output j scaled by 22^-j last).
+ * The caller has already zero-padded to the domain size, exactly like EvaluationDomain does. */
+b200_error_t b200_ntt_fr_bls12_377(void* inout_32B_mont, uint32_t log_n, size_t batch,
+                                   size_t batch_stride_elems, int direction, int coset);
+b200_error_t b200_ntt_fr_bls12_377_device(void* d_inout, uint32_t log_n, size_t batch,
+                                          size_t batch_stride_elems, int direction, int coset, void* stream);
+
+/* ---- synthetic inputs & diagnostics (used by bench.py / tests; not on the snarkVM call path) ---- */
+/* points[i] = k_i * G with k_i = splitmix64(seed, i), written as G1Affine images (Montgomery). */
+b200_error_t b200_g1_synthetic_bases_device(void* d_out_points, size_t npoints, size_t affine_stride,
+                                            uint64_t seed, void* stream);
+/* Element-wise device arithmetic on host buffers, for parity tests of the primitives.
+ * op: 0 fr_mul 1 fr_add 2 fr_sub 3 fq_mul 4 fq_add 5 fq_sub 6 fq_inv 7 fr_inv */
+b200_error_t b200_debug_field_op(int op, void* out, const void* a, const void* b, size_t n);
+/* Curve primitives: op 0: out[i] = a[i] + b[i] (affine inputs, XYZZ madd), 1: out[i] = 2 a[i],
+ * 2: out[i] = k[i] * a[i] with 64-bit k in b.  out = Jacobian 144 B each. */
+b200_error_t b200_debug_g1_op(int op, void* out_jacobian, const void* a_affine, const void* b,
+                              size_t n, size_t affine_stride);
+/* Throughput microbenchmarks: kind 0 IMAD, 1 IMAD.WIDE, 2 IMAD.HI, 3 Fr modmul, 4 Fq modmul, 5 XYZZ madd,
+ * 6 IADD3.  Runs `iters` dependent operations per thread on a full-chip grid and reports the
+ * elapsed milliseconds and the number of operations executed in total. */
+b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t b200_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNARKOS_B200_H */

@@ -1,0 +1,472 @@
+// api.cu -- the extern "C" boundary (include/snarkos_b200.h): lifecycle, host-buffer wrappers, resident
+// bases, synthetic inputs and the diagnostic / microbenchmark kernels.
+#include <cstring>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "msm_core.cuh"
+#include "ntt_core.cuh"
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+// ---------------------------------------------------------------------------------------------
+// process state
+// ---------------------------------------------------------------------------------------------
+struct RegisteredBases {
+    void* d_packed;
+    size_t n;
+};
+struct ApiState {
+    std::mutex mu;
+    int device = -1;
+    bool initialized = false;
+    std::unordered_map<uint64_t, RegisteredBases> bases;
+    uint64_t next_handle = 1;
+    std::vector<cudaStream_t> streams;       // every per-thread stream ever created (for shutdown)
+};
+static ApiState g_api;
+
+struct ThreadStream {
+    cudaStream_t s = nullptr;
+};
+static thread_local ThreadStream t_stream;
+
+cudaStream_t b200_thread_stream() {
+    if (!t_stream.s) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        t_stream.s = s;
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        g_api.streams.push_back(s);
+    }
+    return t_stream.s;
+}
+
+b200_error_t b200_require_device() {
+    if (g_api.initialized) {
+        // a worker thread that never touched CUDA starts on device 0: bind it to the process's device
+        int cur = -1;
+        CUDA_TRY(cudaGetDevice(&cur));
+        if (cur != g_api.device) CUDA_TRY(cudaSetDevice(g_api.device));
+        return b200_ok();
+    }
+    return b200_init(-1);
+}
+
+extern "C" uint32_t b200_abi_version(void) { return 1; }
+extern "C" uint64_t b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+extern "C" b200_error_t b200_init(int device) {
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    if (g_api.initialized && (device < 0 || device == g_api.device)) return b200_ok();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return b200_err(B200_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) return b200_err(B200_ERR_INVALID_ARG, "b200_init: device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return b200_err(B200_ERR_NO_DEVICE, "device is not sm_100 class: kernels are built for sm_100a only");
+    // keep freed scratch in the stream-ordered pool instead of returning it to the driver every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    g_api.device = device;
+    g_api.initialized = true;
+    return b200_ok();
+}
+
+extern "C" void b200_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    if (!g_api.initialized) return;
+    cudaSetDevice(g_api.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : g_api.bases) cudaFree(kv.second.d_packed);
+    g_api.bases.clear();
+    ntt_release_tables();
+    g_api.initialized = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSM entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" b200_error_t b200_msm_g1_bls12_377_device(void* d_out, const void* d_points, size_t n,
+                                                     const void* d_scalars, size_t stride, void* stream) {
+    B200_TRY(b200_require_device());
+    return msm_run_device(d_out, d_points, n, d_scalars, stride, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, size_t n, const void* scalars,
+                                              size_t stride) {
+    B200_TRY(b200_require_device());
+    if (!out) return b200_err(B200_ERR_INVALID_ARG, "msm: null output pointer");
+    if (n && (!points || !scalars)) return b200_err(B200_ERR_INVALID_ARG, "msm: null input pointer");
+    cudaStream_t s = b200_thread_stream();
+    if (!s) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
+    DevBuf d_pts, d_sc, d_out;
+    CUDA_TRY(d_pts.alloc(n * stride, s));
+    CUDA_TRY(d_sc.alloc(n * 32, s));
+    CUDA_TRY(d_out.alloc(144, s));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    }
+    B200_TRY(msm_run_device(d_out.p, d_pts.p, n, d_sc.p, stride, nullptr, s));
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, size_t n, size_t stride,
+                                                       void* stream, uint64_t* out_handle) {
+    B200_TRY(b200_require_device());
+    if (!out_handle || (n && !d_points)) return b200_err(B200_ERR_INVALID_ARG, "register_bases: null pointer");
+    void* d_packed = nullptr;
+    CUDA_TRY(cudaMalloc(&d_packed, (n ? n : 1) * sizeof(g1_packed_t)));
+    b200_error_t r = msm_pack_bases_device(d_packed, d_points, n, stride, (cudaStream_t)stream);
+    if (r.code == 0) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) r = b200_cuda_err(e);
+    }
+    if (r.code != 0) {
+        cudaFree(d_packed);
+        return r;
+    }
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    uint64_t h = g_api.next_handle++;
+    g_api.bases[h] = RegisteredBases{d_packed, n};
+    *out_handle = h;
+    return b200_ok();
+}
+
+extern "C" b200_error_t b200_msm_register_bases(const void* points, size_t n, size_t stride, uint64_t* out_handle) {
+    B200_TRY(b200_require_device());
+    if (!out_handle || (n && !points)) return b200_err(B200_ERR_INVALID_ARG, "register_bases: null pointer");
+    cudaStream_t s = b200_thread_stream();
+    DevBuf d_pts;
+    CUDA_TRY(d_pts.alloc(n * stride, s));
+    if (n) CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
+    return b200_msm_register_bases_device(d_pts.p, n, stride, s, out_handle);
+}
+
+static b200_error_t lookup_bases(uint64_t handle, RegisteredBases* out) {
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    auto it = g_api.bases.find(handle);
+    if (it == g_api.bases.end()) return b200_err(B200_ERR_BAD_HANDLE, "unknown bases handle");
+    *out = it->second;
+    return b200_ok();
+}
+
+extern "C" b200_error_t b200_msm_registered_device(void* d_out, uint64_t handle, const void* d_scalars, size_t n,
+                                                   void* stream) {
+    B200_TRY(b200_require_device());
+    RegisteredBases rb;
+    B200_TRY(lookup_bases(handle, &rb));
+    if (n > rb.n) return b200_err(B200_ERR_INVALID_ARG, "msm_registered: more scalars than registered bases");
+    return msm_run_device(d_out, nullptr, n, d_scalars, 0, rb.d_packed, (cudaStream_t)stream);
+}
+
+extern "C" b200_error_t b200_msm_registered(void* out, uint64_t handle, const void* scalars, size_t n) {
+    B200_TRY(b200_require_device());
+    if (!out || (n && !scalars)) return b200_err(B200_ERR_INVALID_ARG, "msm_registered: null pointer");
+    cudaStream_t s = b200_thread_stream();
+    DevBuf d_sc, d_out;
+    CUDA_TRY(d_sc.alloc(n * 32, s));
+    CUDA_TRY(d_out.alloc(144, s));
+    if (n) CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    B200_TRY(b200_msm_registered_device(d_out.p, handle, d_sc.p, n, s));
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+extern "C" b200_error_t b200_msm_release_bases(uint64_t handle) {
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    auto it = g_api.bases.find(handle);
+    if (it == g_api.bases.end()) return b200_err(B200_ERR_BAD_HANDLE, "unknown bases handle");
+    cudaFree(it->second.d_packed);
+    g_api.bases.erase(it);
+    return b200_ok();
+}
+
+// ---------------------------------------------------------------------------------------------
+// NTT entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" b200_error_t b200_ntt_fr_bls12_377_device(void* d_inout, uint32_t log_n, size_t batch, size_t stride,
+                                                     int direction, int coset, void* stream) {
+    B200_TRY(b200_require_device());
+    return ntt_run_device(d_inout, log_n, batch, stride, direction, coset, (cudaStream_t)stream);
+}
+
+extern "C" b200_error_t b200_ntt_fr_bls12_377(void* inout, uint32_t log_n, size_t batch, size_t stride,
+                                              int direction, int coset) {
+    B200_TRY(b200_require_device());
+    if (batch == 0) return b200_ok();
+    if (!inout) return b200_err(B200_ERR_INVALID_ARG, "ntt: null data pointer");
+    if (log_n > 28) return b200_err(B200_ERR_TOO_LARGE, "ntt: log_n > 28 is not supported");
+    const size_t n = (size_t)1 << log_n;
+    if (batch > 1 && stride < n) return b200_err(B200_ERR_INVALID_ARG, "ntt: batch stride smaller than the domain");
+    const size_t bytes = ((batch - 1) * stride + n) * 32;
+    cudaStream_t s = b200_thread_stream();
+    DevBuf d;
+    CUDA_TRY(d.alloc(bytes, s));
+    CUDA_TRY(cudaMemcpyAsync(d.p, inout, bytes, cudaMemcpyHostToDevice, s));
+    B200_TRY(ntt_run_device(d.p, log_n, batch, stride, direction, coset, s));
+    CUDA_TRY(cudaMemcpyAsync(inout, d.p, bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic bases: points[i] = splitmix64(seed, i) * G
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ void store_affine_image(uint8_t* dst, size_t stride, const g1_affine_t& a) {
+    // stride is a multiple of 8 and dst 8-byte aligned
+    unsigned long long* d64 = reinterpret_cast<unsigned long long*>(dst);
+    const bool inf = g1_affine_is_infinity(a);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        d64[k] = inf ? 0ull : ((unsigned long long)a.x.v[2 * k + 1] << 32 | a.x.v[2 * k]);
+        d64[6 + k] = inf ? 0ull : ((unsigned long long)a.y.v[2 * k + 1] << 32 | a.y.v[2 * k]);
+    }
+    for (size_t k = 12; k < stride / 8; k++) d64[k] = (k == 12 && inf) ? 1ull : 0ull;
+}
+
+__constant__ uint32_t c_gen_x[12];
+__constant__ uint32_t c_gen_y[12];
+
+__global__ void __launch_bounds__(128) synthetic_bases_kernel(uint8_t* out, size_t n, size_t stride, uint64_t seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine_t g;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { g.x.v[k] = c_gen_x[k]; g.y.v[k] = c_gen_y[k]; }
+    uint64_t k = splitmix64_at(seed, i);
+    g1_xyzz_t p = g1_mul_u64(g1_xyzz_from_affine(g), k);
+    store_affine_image(out + i * stride, stride, g1_xyzz_to_affine(p));
+}
+
+static b200_error_t upload_generator() {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaMemcpyToSymbol(c_gen_x, G1_GEN_X, sizeof(G1_GEN_X));
+        if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_gen_y, G1_GEN_Y, sizeof(G1_GEN_Y));
+    });
+    if (err != cudaSuccess) return b200_cuda_err(err);
+    return b200_ok();
+}
+
+extern "C" b200_error_t b200_g1_synthetic_bases_device(void* d_out, size_t n, size_t stride, uint64_t seed,
+                                                       void* stream) {
+    B200_TRY(b200_require_device());
+    if (n == 0) return b200_ok();
+    if (!d_out || stride < 104 || (stride & 7)) return b200_err(B200_ERR_INVALID_ARG, "synthetic_bases: bad pointer or stride");
+    B200_TRY(upload_generator());
+    synthetic_bases_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint8_t*>(d_out), n, stride, seed);
+    KERNEL_CHECK();
+    return b200_ok();
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics: element-wise field / curve ops on host buffers (parity tests of the primitives)
+// ---------------------------------------------------------------------------------------------
+template <class P> __device__ __forceinline__ Fp<P> ld_fp(const uint32_t* p) {
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; i++) r.v[i] = p[i];
+    return r;
+}
+template <class P> __device__ __forceinline__ void st_fp(uint32_t* p, const Fp<P>& a) {
+#pragma unroll
+    for (int i = 0; i < P::N; i++) p[i] = a.v[i];
+}
+
+__global__ void debug_field_kernel(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op <= 2 || op == 7) {
+        fr_t x = ld_fp<FrP>(a + 8 * i), y = b ? ld_fp<FrP>(b + 8 * i) : fp_zero<FrP>(), r;
+        if (op == 0) r = fp_mul(x, y);
+        else if (op == 1) r = fp_add(x, y);
+        else if (op == 2) r = fp_sub(x, y);
+        else r = fp_inv(x);
+        st_fp<FrP>(out + 8 * i, r);
+    } else {
+        fq_t x = ld_fp<FqP>(a + 12 * i), y = b ? ld_fp<FqP>(b + 12 * i) : fp_zero<FqP>(), r;
+        if (op == 3) r = fp_mul(x, y);
+        else if (op == 4) r = fp_add(x, y);
+        else if (op == 5) r = fp_sub(x, y);
+        else r = fp_inv(x);
+        st_fp<FqP>(out + 12 * i, r);
+    }
+}
+
+extern "C" b200_error_t b200_debug_field_op(int op, void* out, const void* a, const void* b, size_t n) {
+    B200_TRY(b200_require_device());
+    if (op < 0 || op > 7 || !out || !a) return b200_err(B200_ERR_INVALID_ARG, "debug_field_op: bad argument");
+    if (n == 0) return b200_ok();
+    const size_t esz = (op <= 2 || op == 7) ? 32 : 48;
+    cudaStream_t s = b200_thread_stream();
+    DevBuf da, db, dout;
+    CUDA_TRY(da.alloc(n * esz, s));
+    CUDA_TRY(db.alloc(n * esz, s));
+    CUDA_TRY(dout.alloc(n * esz, s));
+    CUDA_TRY(cudaMemcpyAsync(da.p, a, n * esz, cudaMemcpyHostToDevice, s));
+    if (b) CUDA_TRY(cudaMemcpyAsync(db.p, b, n * esz, cudaMemcpyHostToDevice, s));
+    debug_field_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(op, dout.as<uint32_t>(), da.as<uint32_t>(),
+                                                                    b ? db.as<uint32_t>() : nullptr, n);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, dout.p, n * esz, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+__device__ __forceinline__ g1_affine_t load_affine_image(const uint8_t* src) {
+    const unsigned long long* s64 = reinterpret_cast<const unsigned long long*>(src);
+    g1_affine_t a;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        unsigned long long x = s64[k], y = s64[6 + k];
+        a.x.v[2 * k] = (uint32_t)x; a.x.v[2 * k + 1] = (uint32_t)(x >> 32);
+        a.y.v[2 * k] = (uint32_t)y; a.y.v[2 * k + 1] = (uint32_t)(y >> 32);
+    }
+    if (src[96]) a = g1_affine_infinity();
+    return a;
+}
+
+__global__ void __launch_bounds__(64) debug_g1_kernel(int op, uint4* out, const uint8_t* a, const uint8_t* b, size_t n,
+                                                      size_t stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine_t pa = load_affine_image(a + i * stride);
+    g1_xyzz_t r = g1_xyzz_from_affine(pa);
+    if (op == 0) {
+        g1_affine_t pb = load_affine_image(b + i * stride);
+        g1_madd(r, pb);
+    } else if (op == 1) {
+        g1_dbl(r);
+    } else {
+        uint64_t k = reinterpret_cast<const unsigned long long*>(b)[i];
+        r = g1_mul_u64(r, k);
+    }
+    fq_t X, Y, Z;
+    g1_xyzz_to_jacobian(r, X, Y, Z);
+    fq_to_u4x3(X, out + 9 * i);
+    fq_to_u4x3(Y, out + 9 * i + 3);
+    fq_to_u4x3(Z, out + 9 * i + 6);
+}
+
+extern "C" b200_error_t b200_debug_g1_op(int op, void* out, const void* a, const void* b, size_t n, size_t stride) {
+    B200_TRY(b200_require_device());
+    if (op < 0 || op > 2 || !out || !a || (op != 1 && !b) || stride < 104 || (stride & 7))
+        return b200_err(B200_ERR_INVALID_ARG, "debug_g1_op: bad argument");
+    if (n == 0) return b200_ok();
+    cudaStream_t s = b200_thread_stream();
+    DevBuf da, db, dout;
+    const size_t bsz = (op == 0) ? n * stride : n * 8;
+    CUDA_TRY(da.alloc(n * stride, s));
+    CUDA_TRY(db.alloc(bsz, s));
+    CUDA_TRY(dout.alloc(n * 144, s));
+    CUDA_TRY(cudaMemcpyAsync(da.p, a, n * stride, cudaMemcpyHostToDevice, s));
+    if (op != 1) CUDA_TRY(cudaMemcpyAsync(db.p, b, bsz, cudaMemcpyHostToDevice, s));
+    debug_g1_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(op, dout.as<uint4>(), da.as<uint8_t>(), db.as<uint8_t>(), n, stride);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, dout.p, n * 144, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+// ---------------------------------------------------------------------------------------------
+// microbenchmarks (roofline denominators for the integer pipe)
+// ---------------------------------------------------------------------------------------------
+#define MB_THREADS 256
+#define MB_ILP 8
+__global__ void __launch_bounds__(MB_THREADS) microbench_kernel(int kind, uint32_t iters, uint32_t* sink, uint32_t seed) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kind <= 2 || kind == 6) {
+        uint32_t a[MB_ILP], b = seed | 1u;
+        unsigned long long w[MB_ILP];
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) { a[k] = tid * 2654435761u + k; w[k] = a[k]; }
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < MB_ILP; k++) {
+                if (kind == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
+                else if (kind == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(a[k]), "r"(b));
+                else if (kind == 2) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
+                else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
+            }
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) acc ^= a[k] ^ (uint32_t)w[k] ^ (uint32_t)(w[k] >> 32);
+        if (acc == 0x12345u) sink[0] = acc;
+    } else if (kind == 3) {
+        fr_t x = fp_one<FrP>(), y = fp_r2<FrP>();
+        x.v[0] ^= tid;
+        for (uint32_t it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
+        if (x.v[0] == 0x12345u && y.v[1] == 7u) sink[0] = x.v[1];
+    } else if (kind == 4) {
+        fq_t x = fp_one<FqP>(), y = fp_r2<FqP>();
+        x.v[0] ^= tid;
+        for (uint32_t it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
+        if (x.v[0] == 0x12345u && y.v[1] == 7u) sink[0] = x.v[1];
+    } else {
+        g1_affine_t g;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { g.x.v[k] = c_gen_x[k]; g.y.v[k] = c_gen_y[k]; }
+        g1_xyzz_t acc = g1_dbl_affine(g);
+        acc.X.v[0] ^= (tid & 1);       // keeps the branches from being resolved at compile time; value irrelevant
+        for (uint32_t it = 0; it < iters; it++) g1_madd(acc, g);
+        if (acc.X.v[0] == 0x12345u && acc.Y.v[1] == 7u) sink[0] = acc.ZZ.v[1];
+    }
+}
+
+extern "C" b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops) {
+    B200_TRY(b200_require_device());
+    if (kind < 0 || kind > 6 || !out_ms || !out_ops) return b200_err(B200_ERR_INVALID_ARG, "microbench: bad argument");
+    B200_TRY(upload_generator());
+    cudaStream_t s = b200_thread_stream();
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, g_api.device));
+    int blocks_per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, microbench_kernel, MB_THREADS, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const unsigned grid = (unsigned)(prop.multiProcessorCount * blocks_per_sm);
+    DevBuf sink;
+    CUDA_TRY(sink.alloc(64, s));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    microbench_kernel<<<grid, MB_THREADS, 0, s>>>(kind, iters / 8 + 1, sink.as<uint32_t>(), 12345u);   // warm-up
+    KERNEL_CHECK();
+    CUDA_TRY(cudaEventRecord(e0, s));
+    microbench_kernel<<<grid, MB_THREADS, 0, s>>>(kind, iters, sink.as<uint32_t>(), 12345u);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(out_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double threads = (double)grid * MB_THREADS;
+    double per_thread = (double)iters;
+    if (kind <= 2 || kind == 6) per_thread *= MB_ILP;
+    else if (kind == 3 || kind == 4) per_thread *= 2;
+    *out_ops = threads * per_thread;
+    return b200_ok();
+}

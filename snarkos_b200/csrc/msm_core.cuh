@@ -1,0 +1,121 @@
+// msm_core.cuh -- host/device-shared pieces of the Pippenger MSM over BLS12-377 G1.
+//
+// GPU counterpart of snarkVM VariableBase::msm -> batched::msm / standard::msm
+// [UPSTREAM snarkvm-algorithms 1.0.0 @ dea322b: algorithms/src/msm/variable_base/{mod,batched,standard}.rs;
+//  SURVEY.md 8a rows a1-a2].  Same group element, different schedule:
+//     snarkVM : c = ln(n) + 2 unsigned windows, rayon over windows, affine batch-add or Jacobian buckets
+//     here    : signed c-bit digits (half the buckets), counting sort of (window,bucket) -> point lists,
+//               one thread per bucket accumulating in XYZZ, segmented running-sum reduction, Horner fold.
+#pragma once
+#include "ec.cuh"
+
+#define MSM_SCALAR_BITS 253
+
+struct MsmShape {
+    uint32_t c;          // window width in bits
+    uint32_t nwin;       // floor(253 / c) + 1: always room for the last signed-digit carry
+    uint32_t nbuckets;   // per window: 2^(c-1), bucket b holds digit magnitude b + 1
+};
+B200_HOSTDEV MsmShape msm_shape(uint32_t c) {
+    MsmShape s;
+    s.c = c;
+    s.nwin = MSM_SCALAR_BITS / c + 1;
+    s.nbuckets = 1u << (c - 1);
+    return s;
+}
+
+// bits [lo, lo + c) of a 256-bit little-endian scalar held as 8 x u32 (c <= 24)
+B200_HD uint32_t msm_window_bits(const uint32_t* s, uint32_t lo, uint32_t c) {
+    uint32_t limb = lo >> 5, off = lo & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+// Signed digit of window w given the carry from window w-1.  Returns magnitude in [0, 2^(c-1)] and the
+// sign; updates carry.   sum_w digit_w * 2^(c*w) == scalar.
+B200_HD uint32_t msm_signed_digit(const uint32_t* s, uint32_t w, uint32_t c, uint32_t& carry, uint32_t& neg) {
+    uint32_t raw = msm_window_bits(s, w * c, c) + carry;
+    uint32_t half = 1u << (c - 1);
+    if (raw > half) {
+        carry = 1;
+        neg = 1;
+        return (1u << c) - raw;
+    }
+    carry = 0;
+    neg = 0;
+    return raw;
+}
+
+// 96-byte packed affine point used on the device: x | y (Montgomery), infinity = (0, 0)
+struct g1_packed_t { uint4 w[6]; };
+
+B200_HD g1_affine_t g1_unpack(const g1_packed_t& p) {
+    g1_affine_t a;
+    a.x.v[0] = p.w[0].x; a.x.v[1] = p.w[0].y; a.x.v[2] = p.w[0].z; a.x.v[3] = p.w[0].w;
+    a.x.v[4] = p.w[1].x; a.x.v[5] = p.w[1].y; a.x.v[6] = p.w[1].z; a.x.v[7] = p.w[1].w;
+    a.x.v[8] = p.w[2].x; a.x.v[9] = p.w[2].y; a.x.v[10] = p.w[2].z; a.x.v[11] = p.w[2].w;
+    a.y.v[0] = p.w[3].x; a.y.v[1] = p.w[3].y; a.y.v[2] = p.w[3].z; a.y.v[3] = p.w[3].w;
+    a.y.v[4] = p.w[4].x; a.y.v[5] = p.w[4].y; a.y.v[6] = p.w[4].z; a.y.v[7] = p.w[4].w;
+    a.y.v[8] = p.w[5].x; a.y.v[9] = p.w[5].y; a.y.v[10] = p.w[5].z; a.y.v[11] = p.w[5].w;
+    return a;
+}
+
+// XYZZ bucket image in global memory: 12 x uint4 (X | Y | ZZ | ZZZ)
+struct g1_xyzz_mem_t { uint4 w[12]; };
+
+B200_HD void fq_to_u4x3(const fq_t& a, uint4* w) {
+    w[0].x = a.v[0]; w[0].y = a.v[1]; w[0].z = a.v[2]; w[0].w = a.v[3];
+    w[1].x = a.v[4]; w[1].y = a.v[5]; w[1].z = a.v[6]; w[1].w = a.v[7];
+    w[2].x = a.v[8]; w[2].y = a.v[9]; w[2].z = a.v[10]; w[2].w = a.v[11];
+}
+B200_HD fq_t fq_from_u4x3(const uint4* w) {
+    fq_t a;
+    a.v[0] = w[0].x; a.v[1] = w[0].y; a.v[2] = w[0].z; a.v[3] = w[0].w;
+    a.v[4] = w[1].x; a.v[5] = w[1].y; a.v[6] = w[1].z; a.v[7] = w[1].w;
+    a.v[8] = w[2].x; a.v[9] = w[2].y; a.v[10] = w[2].z; a.v[11] = w[2].w;
+    return a;
+}
+B200_HD void g1_xyzz_store(g1_xyzz_mem_t* dst, const g1_xyzz_t& p) {
+    fq_to_u4x3(p.X, dst->w + 0);
+    fq_to_u4x3(p.Y, dst->w + 3);
+    fq_to_u4x3(p.ZZ, dst->w + 6);
+    fq_to_u4x3(p.ZZZ, dst->w + 9);
+}
+B200_HD g1_xyzz_t g1_xyzz_load(const g1_xyzz_mem_t* src) {
+    g1_xyzz_t p;
+    p.X = fq_from_u4x3(src->w + 0);
+    p.Y = fq_from_u4x3(src->w + 3);
+    p.ZZ = fq_from_u4x3(src->w + 6);
+    p.ZZZ = fq_from_u4x3(src->w + 9);
+    return p;
+}
+
+// Segment of the running-sum bucket reduction: buckets [s0, s0 + len) of one window carry the weights
+// s0+1 .. s0+len.  Returns  sum_i (s0 + 1 + i) * B[s0 + i]  =  (sum_i (i+1) B[s0+i])  +  s0 * (sum_i B[s0+i]).
+B200_HD g1_xyzz_t msm_reduce_segment(const g1_xyzz_mem_t* buckets, uint32_t s0, uint32_t len) {
+    g1_xyzz_t running = g1_xyzz_infinity();
+    g1_xyzz_t acc = g1_xyzz_infinity();
+    for (uint32_t i = len; i-- > 0;) {
+        g1_xyzz_t b = g1_xyzz_load(buckets + s0 + i);
+        g1_add(running, b);
+        g1_add(acc, running);
+    }
+    if (s0) {
+        g1_xyzz_t t = g1_mul_u64(running, s0);
+        g1_add(acc, t);
+    }
+    return acc;
+}
+
+// Horner fold of the per-window sums, high window first: total = sum_w 2^(c*w) * W_w
+B200_HD g1_xyzz_t msm_fold_windows(const g1_xyzz_mem_t* wsum, uint32_t nwin, uint32_t c) {
+    g1_xyzz_t total = g1_xyzz_infinity();
+    for (uint32_t w = nwin; w-- > 0;) {
+        for (uint32_t k = 0; k < c; k++) g1_dbl(total);
+        g1_xyzz_t s = g1_xyzz_load(wsum + w);
+        g1_add(total, s);
+    }
+    return total;
+}

@@ -1,0 +1,189 @@
+// ntt.cu -- kernels + launcher for EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place on B200.
+// Algorithm and index arithmetic live in ntt_core.cuh (shared with the host test shim).
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "ntt_core.cuh"
+#include "ntt_plan.h"
+
+#define NTT_MAX_LOG_N 28
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ntt_pass_kernel(const NttPassParams p) {
+    extern __shared__ uint4 sm[];
+    const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    ntt_phase_load(p, sm, tile, batch, tid, nt);
+    __syncthreads();
+    if (p.coset_pre) {
+        ntt_phase_coset_pre(p, sm, tile, tid, nt);
+        __syncthreads();
+    }
+    const uint32_t L = p.log_len[p.pass];
+    for (uint32_t s = 0; s < L; s++) {
+        ntt_phase_stage(p, sm, s, tid, nt);
+        __syncthreads();
+    }
+    ntt_phase_store(p, sm, tile, batch, tid, nt);
+}
+
+// out[i] = (base^(2^nsq))^(i << shift)
+__global__ void ntt_pow_table_kernel(uint4* out, fr_t base, uint32_t nsq, uint32_t count, uint32_t shift) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    for (uint32_t k = 0; k < nsq; k++) base = fp_sqr(base);
+    fr_t r = fp_pow_u64(base, (uint64_t)i << shift);
+    uint4 lo, hi;
+    fr_to_u4(r, lo, hi);
+    out[2 * i] = lo;
+    out[2 * i + 1] = hi;
+}
+
+// out = (2^log_n)^-1 in Montgomery form
+__global__ void ntt_size_inv_kernel(fr_t* out, uint32_t log_n) {
+    fr_t n = fp_zero<FrP>();
+    n.v[log_n >> 5] = 1u << (log_n & 31);
+    *out = fp_inv(fp_to_mont(n));
+}
+
+// ---------------------------------------------------------------------------------------------
+// cached per-(log_n, direction) tables
+// ---------------------------------------------------------------------------------------------
+struct NttDomainTables {
+    uint4* pow_lo = nullptr;
+    uint4* pow_hi = nullptr;
+    uint4* coset_lo = nullptr;
+    uint4* coset_hi = nullptr;
+    fr_t size_inv;
+};
+struct NttState {
+    std::mutex mu;
+    uint4* tile_tw[2] = {nullptr, nullptr};
+    std::map<uint32_t, NttDomainTables> domains;     // key = log_n * 2 + direction
+    bool smem_attr_set = false;
+};
+static NttState g_ntt;
+
+static fr_t fr_const(const uint32_t* limbs) {
+    fr_t r;
+    memcpy(r.v, limbs, sizeof(r.v));
+    return r;
+}
+
+static b200_error_t build_pow_table(uint4** out, const uint32_t* base_limbs, uint32_t nsq, uint32_t count,
+                                    uint32_t shift, cudaStream_t stream) {
+    CUDA_TRY(cudaMalloc(out, (size_t)count * 32));
+    ntt_pow_table_kernel<<<(count + 127) / 128, 128, 0, stream>>>(*out, fr_const(base_limbs), nsq, count, shift);
+    KERNEL_CHECK();
+    return b200_ok();
+}
+
+static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t stream, NttDomainTables* out,
+                               const uint4** tile_tw) {
+    std::lock_guard<std::mutex> lock(g_ntt.mu);
+    if (!g_ntt.smem_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (1 << NTT_MAX_TILE_LOG) * 32));
+        g_ntt.smem_attr_set = true;
+    }
+    const uint32_t* root = direction ? FR_TWO_ADIC_ROOT_INV : FR_TWO_ADIC_ROOT;
+    if (!g_ntt.tile_tw[direction]) {
+        B200_TRY(build_pow_table(&g_ntt.tile_tw[direction], root, FR_TWO_ADICITY - NTT_TILE_TW_LOG,
+                                 1u << (NTT_TILE_TW_LOG - 1), 0, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    *tile_tw = g_ntt.tile_tw[direction];
+    uint32_t key = log_n * 2 + (uint32_t)direction;
+    auto it = g_ntt.domains.find(key);
+    if (it == g_ntt.domains.end()) {
+        NttDomainTables t;
+        uint32_t lo_count = 1u << NTT_POW_LO_LOG;
+        uint32_t hi_count = log_n > NTT_POW_LO_LOG ? (1u << (log_n - NTT_POW_LO_LOG)) : 1u;
+        B200_TRY(build_pow_table(&t.pow_lo, root, FR_TWO_ADICITY - log_n, lo_count, 0, stream));
+        B200_TRY(build_pow_table(&t.pow_hi, root, FR_TWO_ADICITY - log_n, hi_count, NTT_POW_LO_LOG, stream));
+        const uint32_t* g = direction ? FR_GENERATOR_INV : FR_GENERATOR;
+        B200_TRY(build_pow_table(&t.coset_lo, g, 0, lo_count, 0, stream));
+        B200_TRY(build_pow_table(&t.coset_hi, g, 0, hi_count, NTT_POW_LO_LOG, stream));
+        fr_t* d_inv = nullptr;
+        CUDA_TRY(cudaMalloc(&d_inv, sizeof(fr_t)));
+        ntt_size_inv_kernel<<<1, 1, 0, stream>>>(d_inv, log_n);
+        KERNEL_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(&t.size_inv, d_inv, sizeof(fr_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaFree(d_inv));
+        it = g_ntt.domains.emplace(key, t).first;
+    }
+    *out = it->second;
+    return b200_ok();
+}
+
+void ntt_release_tables() {
+    std::lock_guard<std::mutex> lock(g_ntt.mu);
+    for (int d = 0; d < 2; d++) {
+        if (g_ntt.tile_tw[d]) cudaFree(g_ntt.tile_tw[d]);
+        g_ntt.tile_tw[d] = nullptr;
+    }
+    for (auto& kv : g_ntt.domains) {
+        cudaFree(kv.second.pow_lo);
+        cudaFree(kv.second.pow_hi);
+        cudaFree(kv.second.coset_lo);
+        cudaFree(kv.second.coset_hi);
+    }
+    g_ntt.domains.clear();
+}
+
+b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction,
+                            int coset, cudaStream_t stream) {
+    if (log_n > NTT_MAX_LOG_N) return b200_err(B200_ERR_TOO_LARGE, "ntt: log_n > 28 is not supported");
+    if (direction != 0 && direction != 1) return b200_err(B200_ERR_INVALID_ARG, "ntt: direction must be 0 or 1");
+    if (batch == 0) return b200_ok();
+    if (!d_inout) return b200_err(B200_ERR_INVALID_ARG, "ntt: null data pointer");
+    const size_t n = (size_t)1 << log_n;
+    if (batch > 1 && batch_stride < n) return b200_err(B200_ERR_INVALID_ARG, "ntt: batch stride smaller than the domain");
+    if (batch > 65535) return b200_err(B200_ERR_TOO_LARGE, "ntt: batch > 65535");
+    if (log_n == 0 && !direction) return b200_ok();      // size-1 domain: identity (n^-1 = 1, g^0 = 1)
+    if (log_n == 0) return b200_ok();
+
+    NttPlan plan;
+    if (!ntt_make_plan(log_n, &plan)) return b200_err(B200_ERR_INVALID_ARG, "ntt: no valid pass plan");
+    NttDomainTables tabs;
+    const uint4* tile_tw = nullptr;
+    B200_TRY(get_tables(log_n, direction, stream, &tabs, &tile_tw));
+
+    DevBuf scratch;
+    if (plan.npasses > 1) CUDA_TRY(scratch.alloc(((batch - 1) * batch_stride + n) * 32, stream));
+
+    for (uint32_t i = 0; i < plan.npasses; i++) {
+        NttPassParams p;
+        memset(&p, 0, sizeof(p));
+        const bool first = (i == 0), last = (i + 1 == plan.npasses);
+        p.src = reinterpret_cast<const uint4*>(first ? d_inout : scratch.p);
+        p.dst = reinterpret_cast<uint4*>(last ? d_inout : scratch.p);
+        p.tile_tw = tile_tw;
+        p.pow_lo = tabs.pow_lo;
+        p.pow_hi = tabs.pow_hi;
+        p.coset_lo = tabs.coset_lo;
+        p.coset_hi = tabs.coset_hi;
+        p.size_inv = tabs.size_inv;
+        p.batch_stride = batch_stride;
+        p.log_n = log_n;
+        p.pass = i;
+        p.npasses = plan.npasses;
+        for (uint32_t k = 0; k < NTT_MAX_PASSES; k++) p.log_len[k] = plan.log_len[k];
+        p.log_cw = plan.log_cw[i];
+        p.coset_pre = (first && coset && direction == 0) ? 1 : 0;
+        p.scale_post = (last && direction == 1) ? 1 : 0;
+        p.coset_post = (last && coset && direction == 1) ? 1 : 0;
+        const uint32_t tile_log = plan.log_len[i] + plan.log_cw[i];
+        const uint32_t tile_elems = 1u << tile_log;
+        uint32_t threads = tile_elems / 2;
+        if (threads > 256) threads = 256;
+        if (threads < 32) threads = 32;
+        dim3 grid(1u << (log_n - tile_log), (unsigned)batch);
+        ntt_pass_kernel<<<grid, threads, (size_t)tile_elems * 32, stream>>>(p);
+        KERNEL_CHECK();
+    }
+    return b200_ok();
+}

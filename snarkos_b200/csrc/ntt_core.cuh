@@ -1,0 +1,236 @@
+// ntt_core.cuh -- radix-2 NTT over BLS12-377 Fr as a sequence of shared-memory passes.
+//
+// GPU counterpart of snarkVM EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place
+// [UPSTREAM snarkvm-algorithms 1.0.0 @ dea322b: algorithms/src/fft/domain.rs -- in_order_fft_in_place,
+//  in_order_ifft_in_place, in_order_coset_(i)fft_in_place, distribute_powers; SURVEY.md 8a rows a3-a6,
+//  appendix A.1].  Natural order in, natural order out, Montgomery data, result fully reduced.
+//
+// Decomposition (generalised four-step / Cooley-Tukey with k passes, N = L_0 * L_1 * ... * L_{k-1}):
+//   pass i < k-1 works on sub-problems of size M_i = N / (L_0..L_{i-1}) (contiguous, base p * M_i):
+//       for every column m < S_i = M_i / L_i:  L_i-point NTT over x[p*M_i + t*S_i + m], t -> k_i,
+//       multiply by w_{M_i}^(m * k_i), store at p*M_i + k_i*S_i + m                       (in place layout)
+//   last pass: contiguous L_{k-1}-point NTTs; element k_{k-1} of sub-problem p = (k_0,..,k_{k-2})
+//       goes to  k_0 + L_0*k_1 + ... + (N / L_{k-1}) * k_{k-1}                            (digit reversal)
+// so the output is in natural order without a separate bit-reversal pass over HBM.
+//
+// One CTA owns a tile of 2^log_len x 2^log_cw elements in shared memory ("cw" = adjacent columns for the
+// strided passes, adjacent k_0 rows for the last pass) so that every global access is a run of
+// 2^log_cw * 32 contiguous bytes.  Inside the tile: DIF butterflies (natural -> bit-reversed), the
+// bit reversal is undone for free when the tile is read back out of shared memory.
+//
+// Every phase is a B200_HD function of (params, tile, batch, tid, nthreads): the CUDA kernel calls the
+// phases with __syncthreads() in between, the host test shim (tests/host/ntt_host.cpp) calls them for all
+// tids in turn -- same code, so the index arithmetic is verified on the CPU against the oracle.
+#pragma once
+#include "field.cuh"
+
+#define NTT_MAX_PASSES 4
+#define NTT_TILE_TW_LOG 12          // tile twiddle table: w_{2^12}^e, e < 2^11
+#define NTT_POW_LO_LOG 13           // two-level power tables: x^e = LO[e & 8191] * HI[e >> 13]
+
+struct NttPassParams {
+    const uint4* src;               // element = 2 consecutive uint4 (32 B)
+    uint4* dst;
+    const uint4* tile_tw;           // w_{2^12}^e (direction-specific), e < 2^11
+    const uint4* pow_lo;            // w_N^e, e < 2^13                        (inter-pass twiddles)
+    const uint4* pow_hi;            // w_N^(e << 13)
+    const uint4* coset_lo;          // g^e (forward) or g^-e (inverse), e < 2^13
+    const uint4* coset_hi;          // g^(e << 13) / g^-(e << 13)
+    fr_t size_inv;                  // n^-1 (Montgomery)
+    unsigned long long batch_stride;   // elements between consecutive polynomials
+    uint32_t log_n;
+    uint32_t pass, npasses;
+    uint32_t log_len[NTT_MAX_PASSES];  // l_i of every pass (needed for the final digit reversal)
+    uint32_t log_cw;                // tile width of THIS pass
+    uint32_t coset_pre;             // multiply input j by g^j     (forward coset, first pass)
+    uint32_t scale_post;            // multiply output by n^-1     (inverse, last pass)
+    uint32_t coset_post;            // multiply output j by g^-j   (inverse coset, last pass)
+};
+
+// ---------------------------------------------------------------------------------------------
+// element access helpers (global / shared element = two uint4 halves)
+// ---------------------------------------------------------------------------------------------
+B200_HD fr_t fr_from_u4(const uint4& lo, const uint4& hi) {
+    fr_t r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+}
+B200_HD void fr_to_u4(const fr_t& a, uint4& lo, uint4& hi) {
+    lo.x = a.v[0]; lo.y = a.v[1]; lo.z = a.v[2]; lo.w = a.v[3];
+    hi.x = a.v[4]; hi.y = a.v[5]; hi.z = a.v[6]; hi.w = a.v[7];
+}
+B200_HD fr_t fr_load(const uint4* base, unsigned long long idx) {
+    return fr_from_u4(base[2 * idx], base[2 * idx + 1]);
+}
+// shared tile: two planes of uint4 so that consecutive elements are consecutive 16-byte words
+B200_HD fr_t tile_load(const uint4* sm, uint32_t tile_elems, uint32_t e) {
+    return fr_from_u4(sm[e], sm[tile_elems + e]);
+}
+B200_HD void tile_store(uint4* sm, uint32_t tile_elems, uint32_t e, const fr_t& a) {
+    fr_to_u4(a, sm[e], sm[tile_elems + e]);
+}
+B200_HD uint32_t bitrev32(uint32_t x, uint32_t bits) {
+#if defined(__CUDACC__)
+    return bits ? (__brev(x) >> (32 - bits)) : 0u;
+#else
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+// x^e from the two-level tables (e < 2^26)
+B200_HD fr_t pow2level(const uint4* lo, const uint4* hi, unsigned long long e) {
+    fr_t a = fr_load(lo, e & ((1u << NTT_POW_LO_LOG) - 1));
+    fr_t b = fr_load(hi, e >> NTT_POW_LO_LOG);
+    return fp_mul(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry of one pass
+// ---------------------------------------------------------------------------------------------
+struct NttGeom {
+    uint32_t log_len, log_cw, log_sub, log_stride;   // this pass: L, CW, M_i, S_i
+    uint32_t last;                                   // 1 for the final (transposing) pass
+    uint32_t tile_elems;                             // L * CW
+    uint32_t log_tiles;                              // tiles per polynomial = N / (L * CW)
+};
+B200_HD NttGeom ntt_geom(const NttPassParams& p) {
+    NttGeom g;
+    g.log_len = p.log_len[p.pass];
+    g.log_cw = p.log_cw;
+    uint32_t before = 0;
+    for (uint32_t i = 0; i < p.pass; i++) before += p.log_len[i];
+    g.log_sub = p.log_n - before;
+    g.log_stride = g.log_sub - g.log_len;
+    g.last = (p.pass + 1 == p.npasses);
+    g.tile_elems = 1u << (g.log_len + g.log_cw);
+    g.log_tiles = p.log_n - g.log_len - g.log_cw;
+    return g;
+}
+
+// Global element index (within the polynomial) of tile element (t, cw) on the INPUT side.
+//   strided pass: tile -> (sub-problem p, column base m0): idx = p*M + t*S + m0 + cw
+//   last pass   : tile -> (k0 base, rest): row p = (k0_base + cw) * (P / L_0) + rest, idx = p * L + t
+B200_HD unsigned long long ntt_in_index(const NttPassParams& p, const NttGeom& g, uint32_t tile, uint32_t t,
+                                        uint32_t cw) {
+    if (!g.last) {
+        uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
+        unsigned long long sub = tile >> log_tiles_per_sub;
+        unsigned long long m0 = (unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw;
+        return (sub << g.log_sub) + ((unsigned long long)t << g.log_stride) + m0 + cw;
+    }
+    if (p.npasses == 1) return t;                       // single pass: the whole polynomial, CW = 1
+    uint32_t log_rows = p.log_n - g.log_len;            // P = number of sub-problems
+    uint32_t l0 = p.log_len[0];
+    uint32_t log_k0_tiles = l0 - g.log_cw;
+    unsigned long long k0 = ((unsigned long long)(tile & ((1u << log_k0_tiles) - 1)) << g.log_cw) + cw;
+    unsigned long long rest = tile >> log_k0_tiles;
+    unsigned long long row = (k0 << (log_rows - l0)) + rest;
+    return (row << g.log_len) + t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1: global -> shared (coalesced), optional coset pre-scaling
+// ---------------------------------------------------------------------------------------------
+B200_HD void ntt_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
+                            uint32_t nthreads) {
+    NttGeom g = ntt_geom(p);
+    const uint4* src = p.src + 2ull * batch * p.batch_stride;
+    uint32_t total = 2u * g.tile_elems;                 // 16-byte words
+    for (uint32_t u = tid; u < total; u += nthreads) {
+        uint32_t half = u & 1u, e = u >> 1;
+        uint32_t t, cw;
+        if (!g.last) { cw = e & ((1u << g.log_cw) - 1); t = e >> g.log_cw; }      // cw fastest in memory
+        else         { t = e & ((1u << g.log_len) - 1); cw = e >> g.log_len; }    // t fastest in memory
+        unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
+        sm[half * g.tile_elems + ((t << g.log_cw) + cw)] = src[2 * idx + half];
+    }
+}
+// phase 1b (only when coset_pre): x[j] *= g^j     -- distribute_powers(coeffs, g) of coset_fft_in_place
+B200_HD void ntt_phase_coset_pre(const NttPassParams& p, uint4* sm, uint32_t tile, uint32_t tid,
+                                 uint32_t nthreads) {
+    NttGeom g = ntt_geom(p);
+    for (uint32_t e = tid; e < g.tile_elems; e += nthreads) {
+        uint32_t cw = e & ((1u << g.log_cw) - 1), t = e >> g.log_cw;
+        unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
+        fr_t x = tile_load(sm, g.tile_elems, e);
+        x = fp_mul(x, pow2level(p.coset_lo, p.coset_hi, idx));
+        tile_store(sm, g.tile_elems, e, x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2 (x log_len): one DIF stage on the tile.  Stage s pairs t and t + d, d = L >> (s + 1):
+//     a' = a + b,  b' = (a - b) * w_L^((t mod d) << s)
+// ---------------------------------------------------------------------------------------------
+B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, uint32_t s, uint32_t tid, uint32_t nthreads) {
+    NttGeom g = ntt_geom(p);
+    uint32_t log_d = g.log_len - 1 - s;
+    uint32_t nbf = g.tile_elems >> 1;                   // butterflies in the tile
+    for (uint32_t u = tid; u < nbf; u += nthreads) {
+        uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
+        uint32_t j = q & ((1u << log_d) - 1);
+        uint32_t t0 = ((q >> log_d) << (log_d + 1)) | j;
+        uint32_t e0 = (t0 << g.log_cw) + cw, e1 = e0 + (1u << (log_d + g.log_cw));
+        fr_t a = tile_load(sm, g.tile_elems, e0);
+        fr_t b = tile_load(sm, g.tile_elems, e1);
+        fr_t sum = fp_add(a, b);
+        fr_t dif = fp_sub(a, b);
+        uint32_t tw = (j << s) << (NTT_TILE_TW_LOG - g.log_len);     // exponent of w_{2^12}
+        if (tw) dif = fp_mul(dif, fr_load(p.tile_tw, tw));
+        tile_store(sm, g.tile_elems, e0, sum);
+        tile_store(sm, g.tile_elems, e1, dif);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 3: shared -> global with the bit reversal undone, inter-pass twiddle / final scaling
+// ---------------------------------------------------------------------------------------------
+B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
+                             uint32_t nthreads) {
+    NttGeom g = ntt_geom(p);
+    uint4* dst = p.dst + 2ull * batch * p.batch_stride;
+    for (uint32_t e = tid; e < g.tile_elems; e += nthreads) {
+        uint32_t cw = e & ((1u << g.log_cw) - 1), k = e >> g.log_cw;          // k = output index of this pass
+        uint32_t t = bitrev32(k, g.log_len);                                   // where DIF left it
+        fr_t x = tile_load(sm, g.tile_elems, (t << g.log_cw) + cw);
+        unsigned long long out;
+        if (!g.last) {
+            uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
+            unsigned long long sub = tile >> log_tiles_per_sub;
+            unsigned long long m = ((unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw) + cw;
+            out = (sub << g.log_sub) + ((unsigned long long)k << g.log_stride) + m;
+            // twiddle w_{M}^(m*k) = w_N^((m*k mod M) << (log_n - log_sub))
+            unsigned long long ex = ((m * k) & ((1ull << g.log_sub) - 1)) << (p.log_n - g.log_sub);
+            if (ex) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, ex));
+        } else if (p.npasses == 1) {
+            out = k;
+        } else {
+            // digit reversal of the row index: row = (k0, k1, .., k_{last-1}) -> k0 + L0*k1 + ...
+            uint32_t log_rows = p.log_n - g.log_len;
+            uint32_t l0 = p.log_len[0];
+            uint32_t log_k0_tiles = l0 - g.log_cw;
+            unsigned long long k0 = ((unsigned long long)(tile & ((1u << log_k0_tiles) - 1)) << g.log_cw) + cw;
+            unsigned long long rest = tile >> log_k0_tiles;            // digits k1 .. k_{last-1}, k1 most significant
+            unsigned long long acc = k0;
+            uint32_t shift = l0;
+            uint32_t rem_bits = log_rows - l0;
+            for (uint32_t i = 1; i + 1 < p.npasses; i++) {
+                rem_bits -= p.log_len[i];
+                unsigned long long digit = (rest >> rem_bits) & ((1ull << p.log_len[i]) - 1);
+                acc += digit << shift;
+                shift += p.log_len[i];
+            }
+            out = acc + ((unsigned long long)k << log_rows);
+        }
+        if (g.last) {
+            if (p.scale_post) x = fp_mul(x, p.size_inv);
+            if (p.coset_post) x = fp_mul(x, pow2level(p.coset_lo, p.coset_hi, out));
+        }
+        uint4 lo, hi;
+        fr_to_u4(x, lo, hi);
+        dst[2 * out] = lo;
+        dst[2 * out + 1] = hi;
+    }
+}

@@ -1,0 +1,102 @@
+// CPU-side emulation shim (TEST ONLY) for the NTT pass code in snarkos_b200/csrc/ntt_core.cuh.
+// Runs exactly the per-phase functions the CUDA kernel runs, for every (tile, batch, tid) in turn, with
+// tables built by the same field code.  Verifies the pass decomposition / index arithmetic against the
+// oracle without a GPU.  Not part of the shipped library; not a CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../snarkos_b200/csrc/ntt_core.cuh"
+#include "../../snarkos_b200/csrc/ntt_plan.h"
+
+static fr_t fr_const(const uint32_t* limbs) { fr_t r; memcpy(r.v, limbs, sizeof(r.v)); return r; }
+
+static std::vector<uint4> pow_table(const uint32_t* base_limbs, uint32_t nsq, uint32_t count, uint32_t shift) {
+    std::vector<uint4> out(2 * (size_t)count);
+    fr_t base = fr_const(base_limbs);
+    for (uint32_t k = 0; k < nsq; k++) base = fp_sqr(base);
+    // incremental: step = base^(1 << shift)
+    fr_t step = base;
+    for (uint32_t k = 0; k < shift; k++) step = fp_sqr(step);
+    fr_t cur = fp_one<FrP>();
+    for (uint32_t i = 0; i < count; i++) {
+        fr_to_u4(cur, out[2 * i], out[2 * i + 1]);
+        cur = fp_mul(cur, step);
+    }
+    return out;
+}
+
+extern "C" int host_ntt_plan(uint32_t log_n, uint32_t* npasses, uint32_t* log_len, uint32_t* log_cw) {
+    NttPlan plan;
+    if (!ntt_make_plan(log_n, &plan)) return -1;
+    *npasses = plan.npasses;
+    for (int i = 0; i < NTT_MAX_PASSES; i++) { log_len[i] = plan.log_len[i]; log_cw[i] = plan.log_cw[i]; }
+    return 0;
+}
+
+// data: batch polynomials of 2^log_n Montgomery Fr (8 x u32 each), stride in elements.  `nthreads` emulated
+// threads per CTA.  plan_len/plan_cw: explicit plan (npasses entries) or npasses = 0 to use ntt_make_plan.
+extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t stride, int direction, int coset,
+                        uint32_t npasses, const uint32_t* plan_len, const uint32_t* plan_cw, uint32_t nthreads) {
+    if (log_n == 0) return 0;
+    NttPlan plan;
+    if (npasses == 0) {
+        if (!ntt_make_plan(log_n, &plan)) return -1;
+    } else {
+        memset(&plan, 0, sizeof(plan));
+        plan.npasses = npasses;
+        for (uint32_t i = 0; i < npasses; i++) { plan.log_len[i] = plan_len[i]; plan.log_cw[i] = plan_cw[i]; }
+    }
+    const uint32_t* root = direction ? FR_TWO_ADIC_ROOT_INV : FR_TWO_ADIC_ROOT;
+    const uint32_t* g = direction ? FR_GENERATOR_INV : FR_GENERATOR;
+    uint32_t lo_count = 1u << NTT_POW_LO_LOG;
+    uint32_t hi_count = log_n > NTT_POW_LO_LOG ? (1u << (log_n - NTT_POW_LO_LOG)) : 1u;
+    auto tile_tw = pow_table(root, FR_TWO_ADICITY - NTT_TILE_TW_LOG, 1u << (NTT_TILE_TW_LOG - 1), 0);
+    auto pow_lo = pow_table(root, FR_TWO_ADICITY - log_n, lo_count, 0);
+    auto pow_hi = pow_table(root, FR_TWO_ADICITY - log_n, hi_count, NTT_POW_LO_LOG);
+    auto coset_lo = pow_table(g, 0, lo_count, 0);
+    auto coset_hi = pow_table(g, 0, hi_count, NTT_POW_LO_LOG);
+    fr_t nn = fp_zero<FrP>();
+    nn.v[log_n >> 5] = 1u << (log_n & 31);
+    fr_t size_inv = fp_inv(fp_to_mont(nn));
+
+    size_t total = ((size_t)(batch - 1) * stride + ((size_t)1 << log_n));
+    std::vector<uint4> scratch(2 * total);
+    uint4* d = reinterpret_cast<uint4*>(data);
+    for (uint32_t i = 0; i < plan.npasses; i++) {
+        NttPassParams p;
+        memset(&p, 0, sizeof(p));
+        bool first = (i == 0), last = (i + 1 == plan.npasses);
+        std::vector<uint4> dst_copy;
+        p.src = first ? d : scratch.data();
+        p.dst = last ? d : scratch.data();
+        p.tile_tw = tile_tw.data();
+        p.pow_lo = pow_lo.data(); p.pow_hi = pow_hi.data();
+        p.coset_lo = coset_lo.data(); p.coset_hi = coset_hi.data();
+        p.size_inv = size_inv;
+        p.batch_stride = stride;
+        p.log_n = log_n; p.pass = i; p.npasses = plan.npasses;
+        for (int k = 0; k < NTT_MAX_PASSES; k++) p.log_len[k] = plan.log_len[k];
+        p.log_cw = plan.log_cw[i];
+        p.coset_pre = (first && coset && direction == 0);
+        p.scale_post = (last && direction == 1);
+        p.coset_post = (last && coset && direction == 1);
+        uint32_t tile_log = plan.log_len[i] + plan.log_cw[i];
+        uint32_t tile_elems = 1u << tile_log;
+        uint32_t ntiles = 1u << (log_n - tile_log);
+        // a single-pass transform reads and writes the same buffer: like on the GPU, every tile is fully
+        // loaded into "shared memory" before it is stored, and tiles of one pass touch disjoint outputs
+        // only when src != dst or npasses == 1 (one tile).
+        std::vector<uint4> sm(2 * (size_t)tile_elems);
+        for (uint32_t b = 0; b < batch; b++)
+            for (uint32_t tile = 0; tile < ntiles; tile++) {
+                for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);
+                if (p.coset_pre)
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, nthreads);
+                for (uint32_t s = 0; s < plan.log_len[i]; s++)
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage(p, sm.data(), s, tid, nthreads);
+                for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_store(p, sm.data(), tile, b, tid, nthreads);
+            }
+    }
+    return 0;
+}

@@ -1,0 +1,111 @@
+"""GPU parity (bit-exact) of EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place through the C ABI against
+the oracle; golden vectors; size-independent properties at the BASELINE sizes (2^20 x 16, 2^24)."""
+import numpy as np
+import pytest
+
+from oracle import bls12_377 as O
+from oracle import c_oracle as C
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+KAT = H.load_kat()
+KINDS = [(0, 0), (1, 0), (0, 1), (1, 1)]
+
+
+def dom(n):
+    import snarkos_b200 as S
+    return S.EvaluationDomain(n)
+
+
+def run(d, data, direction, coset):
+    f = {(0, 0): d.fft_in_place, (1, 0): d.ifft_in_place, (0, 1): d.coset_fft_in_place, (1, 1): d.coset_ifft_in_place}
+    return f[(direction, coset)](data)
+
+
+def test_golden_vectors():
+    assert H.fr_from_mont_array(dom(4).fft_in_place(H.fr_mont_array([1, 2, 3, 4]))) == KAT["NTT_4_1234"]
+    assert H.fr_from_mont_array(dom(4).coset_fft_in_place(H.fr_mont_array([1, 2, 3, 4]))) == KAT["cosetNTT_4_1234"]
+    assert H.fr_from_mont_array(dom(8).fft_in_place(H.fr_mont_array(list(range(1, 9))))) == KAT["NTT_8_1to8"]
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13, 14, 16, 17, 19, 20])
+@pytest.mark.parametrize("direction,coset", KINDS)
+def test_matches_oracle(log_n, direction, coset):
+    n = 1 << log_n
+    rng = np.random.default_rng(1000 + log_n)
+    batch = 3 if log_n <= 16 else 1
+    data = H.random_fr_mont_np(rng, (batch, n))
+    got = run(dom(n), data, direction, coset)
+    want = np.stack([C.ntt(data[b], log_n, direction=direction, coset=coset) for b in range(batch)])
+    assert np.array_equal(got, want)
+
+
+def test_zero_padding_and_edges():
+    d = dom(100)                                   # -> size 128
+    assert d.size == 128 and d.log_size_of_group == 7
+    rng = O.SplitMix64(3)
+    x = O.random_fr(rng, 100)
+    got = H.fr_from_mont_array(d.fft_in_place(H.fr_mont_array(x)))
+    assert got == O.EvaluationDomain(100).fft(x)
+    assert H.fr_from_mont_array(d.fft_in_place(H.fr_mont_array([1]))) == [1] * 128            # delta -> ones
+    assert H.fr_from_mont_array(d.fft_in_place(H.fr_mont_array([1] * 128))) == [128] + [0] * 127
+    ext = [0, 1, O.R_MOD - 1, O.R_MOD - 2] * 32
+    assert H.fr_from_mont_array(d.coset_ifft_in_place(d.coset_fft_in_place(H.fr_mont_array(ext)))) == ext
+    with pytest.raises(ValueError):
+        d.fft_in_place(H.fr_mont_array([1] * 129))
+
+
+def test_batch_stride_and_device_resident():
+    import ctypes
+    import torch
+    import snarkos_b200 as S
+    log_n, batch, n = 12, 5, 1 << 12
+    stride = n + 64
+    rng = np.random.default_rng(5)
+    data = H.random_fr_mont_np(rng, (batch * stride,))
+    want = data.copy()
+    for b in range(batch):
+        want[b * stride:b * stride + n] = C.ntt(data[b * stride:b * stride + n], log_n, direction=0, coset=1)
+    t = torch.from_numpy(data.view(np.int64)).cuda()
+    S._lib.check(S.lib().b200_ntt_fr_bls12_377_device(ctypes.c_void_p(t.data_ptr()), log_n, batch, stride, 0, 1,
+                                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), want)       # gaps between polynomials untouched
+    # EvaluationDomain on a CUDA tensor, in place
+    x = H.random_fr_mont_np(rng, (4, n))
+    t = torch.from_numpy(x.view(np.int64)).cuda()
+    r = S.EvaluationDomain(n).ifft_in_place(t)
+    assert r.data_ptr() == t.data_ptr()
+    torch.cuda.synchronize()
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), np.stack([C.ntt(x[b], log_n, direction=1) for b in range(4)]))
+
+
+@pytest.mark.parametrize("log_n,batch", [(20, 16), (24, 1)])
+def test_full_size_properties(log_n, batch):
+    """BASELINE configs: properties that need no oracle run at full size (intt(ntt(x)) = x, coset round trip,
+    linearity, ntt(delta_1) = powers of omega spot-checked), plus one polynomial checked against the oracle."""
+    import torch
+    import snarkos_b200 as S
+    n = 1 << log_n
+    d = S.EvaluationDomain(n)
+    rng = np.random.default_rng(log_n)
+    x = H.random_fr_mont_np(rng, (batch, n))
+    dx = torch.from_numpy(x.view(np.int64)).cuda()
+    orig = dx.clone()
+    d.fft_in_place(dx)
+    fwd = dx.clone()
+    assert not torch.equal(fwd, orig)
+    d.ifft_in_place(dx)
+    assert torch.equal(dx, orig)
+    d.coset_fft_in_place(dx)
+    d.coset_ifft_in_place(dx)
+    assert torch.equal(dx, orig)
+    # one polynomial against the CPU oracle (multi-threaded C restatement)
+    assert np.array_equal(fwd[0].cpu().numpy().view(np.uint64), C.ntt(x[0], log_n))
+    # delta at index 1 -> omega^k: spot check a few k against Python big-int powers
+    delta = np.zeros((n, 4), dtype=np.uint64)
+    delta[1] = H.fr_mont_array([1])[0]
+    out = d.fft_in_place(torch.from_numpy(delta.view(np.int64)).cuda()).cpu().numpy().view(np.uint64)
+    w = O.EvaluationDomain(n).group_gen
+    for k in (0, 1, 2, 12345, n // 2, n - 1):
+        assert H.fr_from_mont_array(out[k:k + 1])[0] == pow(w, k, O.R_MOD)

@@ -1,0 +1,92 @@
+"""CPU-side verification of the DEVICE NTT pass code (snarkos_b200/csrc/ntt_core.cuh + ntt_plan.h): the per-phase
+functions the CUDA kernel executes are run tile by tile on the host (tests/host/ntt_host.cpp) and compared with
+the oracle for every decomposition shape (1..4 passes, several tile widths, all four transform kinds)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import bls12_377 as O
+from oracle import c_oracle as C
+from tests import helpers as H
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    src = os.path.join(HERE, "host", "ntt_host.cpp")
+    so = os.path.join(HERE, "host", "libntt_host.so")
+    deps = [src] + [os.path.join(ROOT, "snarkos_b200", "csrc", f) for f in ("field.cuh", "ntt_core.cuh", "ntt_plan.h", "ptx_ops.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so], check=True)
+    return ctypes.CDLL(so)
+
+
+def run(lib, data, log_n, batch, stride, direction, coset, lens=(), cws=(), nthreads=8):
+    buf = np.ascontiguousarray(data, dtype=np.uint64).copy()
+    L = (ctypes.c_uint32 * 4)(*(list(lens) + [0] * (4 - len(lens))))
+    W = (ctypes.c_uint32 * 4)(*(list(cws) + [0] * (4 - len(cws))))
+    rc = lib.host_ntt(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(log_n), ctypes.c_uint32(batch),
+                      ctypes.c_uint64(stride), ctypes.c_int(direction), ctypes.c_int(coset), ctypes.c_uint32(len(lens)),
+                      L, W, ctypes.c_uint32(nthreads))
+    assert rc == 0
+    return buf
+
+
+SHAPES = [
+    (1, (1,), (0,)), (3, (3,), (0,)), (6, (6,), (0,)),
+    (6, (3, 3), (0, 0)), (6, (3, 3), (2, 2)), (6, (2, 4), (1, 2)), (7, (4, 3), (3, 1)),
+    (6, (2, 2, 2), (0, 0, 0)), (6, (2, 2, 2), (1, 2, 2)), (8, (3, 2, 3), (2, 3, 3)), (9, (3, 3, 3), (2, 1, 3)),
+    (8, (2, 2, 2, 2), (1, 2, 1, 2)), (9, (3, 2, 2, 2), (2, 1, 2, 3)),
+]
+
+
+@pytest.mark.parametrize("log_n,lens,cws", SHAPES)
+@pytest.mark.parametrize("direction,coset", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_pass_decomposition_matches_oracle(hostlib, log_n, lens, cws, direction, coset):
+    n = 1 << log_n
+    rng = O.SplitMix64(100 * log_n + 10 * len(lens) + 2 * direction + coset)
+    batch, stride = 2, n + 3
+    vals = [rng.below(O.R_MOD, 253) for _ in range(stride * (batch - 1) + n)]
+    data = H.ints_to_limbs(vals, 4)
+    got = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=5)
+    want = data.copy()
+    for b in range(batch):
+        want[b * stride:b * stride + n] = C.ntt(data[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
+    assert np.array_equal(got, want)          # includes: padding between polynomials untouched
+
+
+@pytest.mark.parametrize("log_n", [4, 10, 12, 13, 14])
+def test_default_plan(hostlib, log_n):
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    data = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    data[:, 3] &= (1 << 59) - 1                 # < 2^251 < r : valid Montgomery representatives
+    got = run(hostlib, data, log_n, 1, n, 0, 0, nthreads=64)
+    assert np.array_equal(got, C.ntt(data, log_n))
+    back = run(hostlib, got, log_n, 1, n, 1, 0, nthreads=64)
+    assert np.array_equal(back, data)
+
+
+def test_planner_invariants(hostlib):
+    for log_n in range(1, 29):
+        npasses = ctypes.c_uint32()
+        L = (ctypes.c_uint32 * 4)()
+        W = (ctypes.c_uint32 * 4)()
+        assert hostlib.host_ntt_plan(ctypes.c_uint32(log_n), ctypes.byref(npasses), L, W) == 0
+        k = npasses.value
+        assert 1 <= k <= 4 and sum(L[i] for i in range(k)) == log_n
+        before = 0
+        for i in range(k):
+            assert 1 <= L[i] <= 12 and L[i] + W[i] <= 12
+            if k == 1:
+                assert W[i] == 0
+            elif i + 1 < k:
+                assert W[i] <= log_n - before - L[i]
+            else:
+                assert W[i] <= L[0]
+            before += L[i]
