@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py -- G1 MSM Mpoints/s & Fr NTT Gelem/s @ 2^24 per B200 (BASELINE.json metric), one process per GPU.
+
+A "step" is one pass of the hot path over one batch of synthetic input: one VariableBase::msm over 2^24
+(base, scalar) pairs followed by one EvaluationDomain::fft_in_place over 2^24 Fr elements, inputs resident in HBM.
+  value        : MSM Mpoints/s, whole job (all ranks), device-resident, CUDA-event timed, max over ranks
+  ntt.value    : NTT Gelem/s, same rules
+  e2e          : the same MSM metric through the public host-buffer API (pinned host bases + scalars copied H2D and the
+                 144-byte result copied D2H inside the timed region, every step)
+  roofline     : dominant kernel of the step (msm_accumulate) against the measured HBM peak, as the contract asks;
+                 roofline_int puts the same kernel against the integer-multiply pipe (the bound that actually binds)
+  cpu_baseline : the CPU oracle (restated snarkVM algorithm, "port") on the box's host cores, bounded sample
+`--impl reference` times that CPU port alone (the reference's hot path is Rust in an un-vendored dependency and no Rust
+toolchain exists in the image, so there is no oracle/_ref to run).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "G1 MSM Mpoints/s @2^24 per GPU (BLS12-377 VariableBase::msm; Fr NTT Gelem/s @2^24 in 'ntt')"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=24, help="log2 of MSM points and NTT elements per GPU")
+    ap.add_argument("--cpu-msm-log-n", type=int, default=18, help="bounded CPU-baseline MSM sample")
+    ap.add_argument("--cpu-ntt-log-n", type=int, default=22, help="bounded CPU-baseline NTT sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                if int(r[0]) != self.gpu:
+                    continue
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port).  The ONLY place bench.py touches oracle/.
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_inputs(msm_log_n, ntt_log_n):
+    """Bounded sample built without any GPU code: 2^12 distinct oracle-generated points tiled up to 2^msm_log_n
+    (MSM cost does not depend on the point values), uniform scalars / Fr data < 2^252."""
+    import numpy as np
+    from oracle import bls12_377 as O
+    from oracle import c_oracle as C
+    rng = np.random.default_rng(2024)
+    g = np.frombuffer(O.affine_bytes(O.G1_GEN), dtype=np.uint8)
+    distinct = min(1 << 12, 1 << msm_log_n)
+    k = rng.integers(1, 1 << 62, size=distinct, dtype=np.uint64)
+    pts = C.g1_mul_u64(g, k)                                     # [distinct, 104]
+    reps = (1 << msm_log_n) // distinct
+    bases = np.tile(pts, (reps, 1)).reshape(-1)
+
+    def rnd(n):
+        s = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+        s[:, 3] &= np.uint64((1 << 59) - 1)
+        return s
+    return bases, rnd(1 << msm_log_n), rnd(1 << ntt_log_n)
+
+
+def cpu_time_once(bases, scalars, ntt_data, ntt_log_n):
+    from oracle import c_oracle as C
+    t0 = time.perf_counter()
+    C.msm(bases, scalars)
+    t1 = time.perf_counter()
+    C.ntt(ntt_data, ntt_log_n)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle as C
+    C.build()
+    cores = C.num_threads()
+    bases, scalars, ntt_data = cpu_inputs(args.cpu_msm_log_n, args.cpu_ntt_log_n)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_time_once(bases, scalars, ntt_data, args.cpu_ntt_log_n)
+    tm, tn = 0.0, 0.0
+    for _ in range(args.steps):
+        a, b = cpu_time_once(bases, scalars, ntt_data, args.cpu_ntt_log_n)
+        tm += a
+        tn += b
+    npts, nel = 1 << args.cpu_msm_log_n, 1 << args.cpu_ntt_log_n
+    value = npts * args.steps / tm / 1e6
+    sample = (f"MSM 2^{args.cpu_msm_log_n} points (2^12 distinct, tiled) + NTT 2^{args.cpu_ntt_log_n} per step; "
+              f"C restatement of snarkVM standard::msm / in-order radix-2 FFT, OpenMP {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tm + tn) / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Montgomery, 377/253-bit)",
+        "data": "synthetic",
+        "config": {"workload": f"BLS12-377 G1 MSM 2^{args.log_n} + Fr NTT 2^{args.log_n} per GPU",
+                   "reference_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample},
+        "ntt": {"value": nel * args.steps / tn / 1e9, "unit": "Gelem/s"},
+        "e2e": {"value": value, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import snarkos_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    S.init(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = 1 << args.log_n
+    K, W = args.steps, args.warmup
+
+    # ---- synthetic inputs, generated on the device --------------------------------------------------------------
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234567890 + rank)
+
+    def rand_limbs(count):          # values < 2^252 < r: canonical scalars / valid Montgomery representatives
+        t = torch.randint(-(1 << 63), (1 << 63) - 1, (count, 4), dtype=torch.int64, device=dev, generator=gen)
+        t[:, 3] &= (1 << 60) - 1
+        return t
+    bases = S.synthetic_bases(n, seed=1234567890 + rank)
+    scalars = rand_limbs(n)
+    ntt_data = rand_limbs(n)
+    dom = S.EvaluationDomain(n)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    partials = torch.empty((world, 144), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step_msm():
+        out = S.VariableBase.msm(bases, scalars)            # this rank's point range -> partial sum
+        if world > 1:                                       # 8 partial sums gathered and added (tiny)
+            dist.all_gather_into_tensor(partials.view(-1), out.contiguous())
+            out = S.sum_projective(partials)
+        return out
+
+    def step_ntt():
+        dom.fft_in_place(ntt_data)
+
+    for _ in range(W):
+        step_msm()
+        step_ntt()
+    barrier()
+
+    # ---- timed region: exactly K steps ---------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = S.kernel_launch_count()
+    sampler.start()
+    barrier()
+    with S.profile() as prof:
+        for i in range(K):
+            ev[i][0].record()
+            result = step_msm()
+            ev[i][1].record()
+            step_ntt()
+            ev[i][2].record()
+        torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = S.kernel_launch_count() - launches0
+    msm_ms = sum(ev[i][0].elapsed_time(ev[i][1]) for i in range(K))
+    ntt_ms = sum(ev[i][1].elapsed_time(ev[i][2]) for i in range(K))
+    tot_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+    t = torch.tensor([msm_ms, ntt_ms, tot_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    msm_ms, ntt_ms, tot_ms = [float(x) for x in t.cpu()]
+    stage = prof.totals()                                  # per-kernel device time summed over the K steps (this rank)
+
+    # ---- end-to-end through the host-buffer API --------------------------------------------------------------------
+    e2e = None
+    ntt_e2e = None
+    if not args.no_e2e:
+        h_bases = bases.cpu().pin_memory()
+        h_scalars = scalars.cpu().pin_memory()
+        h_ntt = ntt_data.cpu().pin_memory()
+        S.VariableBase.msm(h_bases, h_scalars)              # warm the staging pool
+        Ke = min(K, 3)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            host_result = S.VariableBase.msm(h_bases, h_scalars)     # H2D bases + scalars, compute, D2H 144 B
+        barrier()
+        t1 = time.perf_counter()
+        dom.fft_in_place(h_ntt)
+        barrier()
+        t2 = time.perf_counter()
+        for _ in range(Ke):
+            dom.fft_in_place(h_ntt)                          # H2D 2^24 * 32 B, compute, D2H 2^24 * 32 B
+        barrier()
+        t3 = time.perf_counter()
+        tt = torch.tensor([t1 - t0, t3 - t2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e_msm, e_ntt = [float(x) for x in tt.cpu()]
+        e2e = {"value": world * n * Ke / e_msm / 1e6, "unit": "Mpoints/s",
+               "h2d_bytes_per_step": int(h_bases.numel() + h_scalars.numel() * 8), "d2h_bytes_per_step": 144,
+               "steps": Ke, "api": "snarkos_b200.VariableBase.msm(pinned host bases, pinned host scalars) -> b200_msm_g1_bls12_377"}
+        ntt_e2e = {"value": world * n * Ke / e_ntt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": int(h_ntt.numel() * 8),
+                   "d2h_bytes_per_step": int(h_ntt.numel() * 8), "steps": Ke,
+                   "api": "snarkos_b200.EvaluationDomain.fft_in_place(pinned host tensor) -> b200_ntt_fr_bls12_377"}
+        del h_bases, h_scalars, h_ntt
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    hbm_peak, peak_src = measured_peaks()
+    c = int(S.lib().b200_msm_window_bits(n))
+    nwin = 253 // c + 1
+    acc_ms = stage.get("msm_accumulate", 0.0) / K
+    alg_bytes = (104 + 32) * n                                   # (104 + 32) B per point
+    roofline = {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "avg_launch_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes}
+    roofline["frac"] = roofline["achieved"] / hbm_peak if roofline["achieved"] else None
+    # integer-multiply pipe: Fq modmuls the accumulate kernel must execute vs the modmul rate of a pure fp_mul loop
+    import ctypes
+    ms_, ops_ = ctypes.c_float(), ctypes.c_double()
+    best = 0.0
+    for _ in range(3):
+        S._lib.check(S.lib().b200_debug_microbench(4, 256, ctypes.byref(ms_), ctypes.byref(ops_)))
+        best = max(best, ops_.value / (ms_.value * 1e-3))
+    modmuls = 10.0 * n * nwin                                     # one XYZZ mixed add (8M + 2S) per non-zero digit
+    roofline_int = {"bound": "int_mul_pipe", "kernel": "msm_accumulate_kernel", "unit": "G Fq-modmul/s",
+                    "achieved": modmuls / (acc_ms * 1e-3) / 1e9 if acc_ms else None, "peak": best / 1e9,
+                    "peak_source": "fp_mul<Fq> dependent-chain microbenchmark, same run, full occupancy",
+                    "modmul_per_launch": modmuls, "window_bits": c, "windows": nwin, "digits": "signed"}
+    roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"] if roofline_int["achieved"] else None
+    ntt_pass_ms = sum(v for k_, v in stage.items() if k_.startswith("ntt_pass")) / K
+    ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_transform": 64 * n, "passes": len([k_ for k_ in stage if k_.startswith("ntt_pass")])}
+    ntt_roof["frac"] = ntt_roof["achieved"] / hbm_peak if ntt_roof["achieved"] else None
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------------------
+    cpu = None
+    ntt_cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle as C
+        C.build()
+        ml, nl = args.cpu_msm_log_n, args.cpu_ntt_log_n
+        hb = bases[: (1 << ml) * 104].cpu().numpy()
+        hs = scalars[: 1 << ml].cpu().numpy().view(np.uint64)
+        hn = ntt_data[: 1 << nl].cpu().numpy().view(np.uint64)
+        tm, tn = cpu_time_once(hb, hs, hn, nl)
+        cores = C.num_threads()
+        cpu = {"value": (1 << ml) / tm / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
+               "sample": f"first 2^{ml} of the same bases/scalars, {tm:.2f} s; C restatement of snarkVM standard::msm "
+                         f"(c = ln n + 2, Jacobian buckets), OpenMP over windows; NOT snarkVM itself (no Rust toolchain)"}
+        ntt_cpu = {"value": (1 << nl) / tn / 1e9, "unit": "Gelem/s", "cores": cores, "kind": "port",
+                   "sample": f"first 2^{nl} elements as one polynomial, {tn:.2f} s; in-order radix-2 FFT with root table, OpenMP"}
+
+    line = {
+        "metric": METRIC, "value": world * n * K / msm_ms / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (Montgomery, 377-bit Fq / 253-bit Fr), integer", "data": "synthetic",
+        "config": {"workload": f"BLS12-377 G1 MSM 2^{args.log_n} + Fr NTT 2^{args.log_n} per GPU (BASELINE configs[4] shard size; "
+                               f"headline metric size)",
+                   "msm_points_per_gpu": n, "ntt_elems_per_gpu": n, "window_bits": c, "windows": nwin,
+                   "l2": "inputs larger than L2 (packed bases 1.5 GiB, scalars 0.5 GiB, NTT data 0.5 GiB vs 126 MB)",
+                   "parallelism": f"msm: point-range shard x{world} + gather/add of partial sums; ntt: independent per GPU",
+                   "bases": "k_i * G, k_i = splitmix64(seed, i), generated on the device; scalars / Fr data uniform < 2^252"},
+        "msm_ms": msm_ms / K, "clocks": clocks, "gpu_launches": int(launches),
+        "stage_ms_per_step": {k_: v / K for k_, v in stage.items()},
+        "roofline": roofline, "roofline_int": roofline_int,
+        "ntt": {"value": world * n * K / ntt_ms / 1e9, "unit": "Gelem/s", "ms": ntt_ms / K, "roofline": ntt_roof,
+                "e2e": ntt_e2e, "cpu_baseline": ntt_cpu},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -118,6 +118,10 @@ b200_error_t b200_debug_g1_op(int op, void* out_jacobian, const void* a_affine, 
  * 6 IADD3.  Runs `iters` dependent operations per thread on a full-chip grid and reports the
  * elapsed milliseconds and the number of operations executed in total. */
 b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops);
+/* Per-stage device timing of the calls the CALLING THREAD makes between begin and end (CUDA events on the
+ * launching stream).  b200_profile_end synchronises the device and writes "stage=ms;stage=ms;..." into buf. */
+void b200_profile_begin(void);
+b200_error_t b200_profile_end(char* buf, size_t buflen);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t b200_kernel_launch_count(void);
 

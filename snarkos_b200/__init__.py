@@ -6,6 +6,6 @@ through snarkVM's Varuna prover / verifier, behind snarkVM's own interface names
 
 The compute lives in snarkos_b200/libsnarkos_b200.so (CUDA, C ABI in include/snarkos_b200.h).  No CPU fallback.
 """
-from ._lib import B200Error, init, kernel_launch_count, lib  # noqa: F401
+from ._lib import B200Error, init, kernel_launch_count, lib, profile  # noqa: F401
 from .fft import EvaluationDomain  # noqa: F401
 from .msm import ResidentBases, VariableBase, sum_projective, synthetic_bases  # noqa: F401

@@ -42,6 +42,8 @@ SYMBOLS = {
     "b200_debug_field_op": (b200_error_t, [_i, _vp, _vp, _vp, _sz]),
     "b200_debug_g1_op": (b200_error_t, [_i, _vp, _vp, _vp, _sz, _sz]),
     "b200_debug_microbench": (b200_error_t, [_i, _u32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
+    "b200_profile_begin": (None, []),
+    "b200_profile_end": (b200_error_t, [ctypes.c_char_p, _sz]),
     "b200_kernel_launch_count": (_u64, []),
 }
 
@@ -71,6 +73,30 @@ def check(err: b200_error_t) -> None:
 
 def init(device: int = -1) -> None:
     check(lib().b200_init(device))
+
+
+class profile:
+    """with profile() as p: ...calls...; p.stages -> [(stage, ms), ...] measured with CUDA events on the stream."""
+
+    def __enter__(self):
+        self.stages = []
+        lib().b200_profile_begin()
+        return self
+
+    def __exit__(self, *exc):
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(lib().b200_profile_end(buf, len(buf)))
+        for item in buf.value.decode().split(";"):
+            if item:
+                k, v = item.split("=")
+                self.stages.append((k, float(v)))
+        return False
+
+    def totals(self):
+        out = {}
+        for k, v in self.stages:
+            out[k] = out.get(k, 0.0) + v
+        return out
 
 
 def kernel_launch_count() -> int:

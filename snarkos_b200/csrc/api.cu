@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary (include/snarkos_b200.h): lifecycle, host-buffer wrappers, resident
 // bases, synthetic inputs and the diagnostic / microbenchmark kernels.
+#include <cstdio>
 #include <cstring>
 #include <unordered_map>
 
@@ -92,6 +93,65 @@ extern "C" void b200_shutdown(void) {
     g_api.bases.clear();
     ntt_release_tables();
     g_api.initialized = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-stage profiling (thread-local)
+// ---------------------------------------------------------------------------------------------
+struct StageRec { const char* name; cudaEvent_t start; cudaEvent_t stop; };
+static thread_local bool t_prof_on = false;
+static thread_local std::vector<StageRec> t_prof;
+static thread_local bool t_prof_open = false;
+
+bool& StageTimer::enabled() { return t_prof_on; }
+void StageTimer::mark(const char* name, cudaStream_t stream) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    if (t_prof_open) t_prof.back().stop = e;
+    cudaEvent_t e2 = e;
+    t_prof.push_back(StageRec{name, e2, nullptr});
+    t_prof_open = true;
+}
+void StageTimer::finish(cudaStream_t stream) {
+    if (!t_prof_open) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    t_prof.back().stop = e;
+    t_prof_open = false;
+}
+
+extern "C" void b200_profile_begin(void) {
+    t_prof.clear();
+    t_prof_open = false;
+    t_prof_on = true;
+}
+// Writes "name=ms;name=ms;..." (one entry per recorded stage, in order) and stops profiling.
+extern "C" b200_error_t b200_profile_end(char* buf, size_t buflen) {
+    t_prof_on = false;
+    if (!buf || buflen == 0) return b200_err(B200_ERR_INVALID_ARG, "profile_end: null buffer");
+    CUDA_TRY(cudaDeviceSynchronize());
+    size_t pos = 0;
+    buf[0] = 0;
+    for (auto& r : t_prof) {
+        float ms = 0.f;
+        if (r.start && r.stop) cudaEventElapsedTime(&ms, r.start, r.stop);
+        int w = snprintf(buf + pos, buflen - pos, "%s=%.6f;", r.name, ms);
+        if (w < 0 || (size_t)w >= buflen - pos) break;
+        pos += (size_t)w;
+    }
+    // events are shared between consecutive stages (stop of one = start of the next): destroy each once
+    std::vector<cudaEvent_t> seen;
+    for (auto& r : t_prof)
+        for (cudaEvent_t e : {r.start, r.stop}) {
+            if (!e) continue;
+            bool dup = false;
+            for (auto s2 : seen) dup |= (s2 == e);
+            if (!dup) { seen.push_back(e); cudaEventDestroy(e); }
+        }
+    t_prof.clear();
+    return b200_ok();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -396,9 +456,11 @@ extern "C" b200_error_t b200_debug_g1_op(int op, void* out, const void* a, const
 // ---------------------------------------------------------------------------------------------
 #define MB_THREADS 256
 #define MB_ILP 8
-__global__ void __launch_bounds__(MB_THREADS) microbench_kernel(int kind, uint32_t iters, uint32_t* sink, uint32_t seed) {
+// KIND: 0 IMAD (mad.lo), 1 IMAD.WIDE, 2 IMAD.HI, 6 IADD3, 3 Fr modmul, 4 Fq modmul, 5 XYZZ mixed add
+template <int KIND>
+__global__ void __launch_bounds__(MB_THREADS) microbench_kernel(uint32_t iters, uint32_t* sink, uint32_t seed) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kind <= 2 || kind == 6) {
+    if constexpr (KIND <= 2 || KIND == 6) {
         uint32_t a[MB_ILP], b = seed | 1u;
         unsigned long long w[MB_ILP];
 #pragma unroll
@@ -406,9 +468,9 @@ __global__ void __launch_bounds__(MB_THREADS) microbench_kernel(int kind, uint32
         for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
             for (int k = 0; k < MB_ILP; k++) {
-                if (kind == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
-                else if (kind == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(a[k]), "r"(b));
-                else if (kind == 2) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
+                if constexpr (KIND == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
+                else if constexpr (KIND == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(a[k]), "r"(b));
+                else if constexpr (KIND == 2) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
                 else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
             }
         }
@@ -416,12 +478,12 @@ __global__ void __launch_bounds__(MB_THREADS) microbench_kernel(int kind, uint32
 #pragma unroll
         for (int k = 0; k < MB_ILP; k++) acc ^= a[k] ^ (uint32_t)w[k] ^ (uint32_t)(w[k] >> 32);
         if (acc == 0x12345u) sink[0] = acc;
-    } else if (kind == 3) {
+    } else if constexpr (KIND == 3) {
         fr_t x = fp_one<FrP>(), y = fp_r2<FrP>();
         x.v[0] ^= tid;
         for (uint32_t it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
         if (x.v[0] == 0x12345u && y.v[1] == 7u) sink[0] = x.v[1];
-    } else if (kind == 4) {
+    } else if constexpr (KIND == 4) {
         fq_t x = fp_one<FqP>(), y = fp_r2<FqP>();
         x.v[0] ^= tid;
         for (uint32_t it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
@@ -437,26 +499,21 @@ __global__ void __launch_bounds__(MB_THREADS) microbench_kernel(int kind, uint32
     }
 }
 
-extern "C" b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops) {
-    B200_TRY(b200_require_device());
-    if (kind < 0 || kind > 6 || !out_ms || !out_ops) return b200_err(B200_ERR_INVALID_ARG, "microbench: bad argument");
-    B200_TRY(upload_generator());
-    cudaStream_t s = b200_thread_stream();
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, g_api.device));
+template <int KIND>
+static b200_error_t run_microbench(uint32_t iters, float* out_ms, double* out_ops, cudaStream_t s, int sms) {
     int blocks_per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, microbench_kernel, MB_THREADS, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, microbench_kernel<KIND>, MB_THREADS, 0));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    const unsigned grid = (unsigned)(prop.multiProcessorCount * blocks_per_sm);
+    const unsigned grid = (unsigned)(sms * blocks_per_sm);
     DevBuf sink;
     CUDA_TRY(sink.alloc(64, s));
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    microbench_kernel<<<grid, MB_THREADS, 0, s>>>(kind, iters / 8 + 1, sink.as<uint32_t>(), 12345u);   // warm-up
+    microbench_kernel<KIND><<<grid, MB_THREADS, 0, s>>>(iters / 8 + 1, sink.as<uint32_t>(), 12345u);   // warm-up
     KERNEL_CHECK();
     CUDA_TRY(cudaEventRecord(e0, s));
-    microbench_kernel<<<grid, MB_THREADS, 0, s>>>(kind, iters, sink.as<uint32_t>(), 12345u);
+    microbench_kernel<KIND><<<grid, MB_THREADS, 0, s>>>(iters, sink.as<uint32_t>(), 12345u);
     KERNEL_CHECK();
     CUDA_TRY(cudaEventRecord(e1, s));
     CUDA_TRY(cudaEventSynchronize(e1));
@@ -465,8 +522,27 @@ extern "C" b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* o
     cudaEventDestroy(e1);
     const double threads = (double)grid * MB_THREADS;
     double per_thread = (double)iters;
-    if (kind <= 2 || kind == 6) per_thread *= MB_ILP;
-    else if (kind == 3 || kind == 4) per_thread *= 2;
+    if (KIND <= 2 || KIND == 6) per_thread *= MB_ILP;
+    else if (KIND == 3 || KIND == 4) per_thread *= 2;
     *out_ops = threads * per_thread;
     return b200_ok();
+}
+
+extern "C" b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops) {
+    B200_TRY(b200_require_device());
+    if (kind < 0 || kind > 6 || !out_ms || !out_ops) return b200_err(B200_ERR_INVALID_ARG, "microbench: bad argument");
+    B200_TRY(upload_generator());
+    cudaStream_t s = b200_thread_stream();
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, g_api.device));
+    const int sms = prop.multiProcessorCount;
+    switch (kind) {
+        case 0: return run_microbench<0>(iters, out_ms, out_ops, s, sms);
+        case 1: return run_microbench<1>(iters, out_ms, out_ops, s, sms);
+        case 2: return run_microbench<2>(iters, out_ms, out_ops, s, sms);
+        case 3: return run_microbench<3>(iters, out_ms, out_ops, s, sms);
+        case 4: return run_microbench<4>(iters, out_ms, out_ops, s, sms);
+        case 5: return run_microbench<5>(iters, out_ms, out_ops, s, sms);
+        default: return run_microbench<6>(iters, out_ms, out_ops, s, sms);
+    }
 }

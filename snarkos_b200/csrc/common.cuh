@@ -48,6 +48,16 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Optional per-stage timing (b200_profile_begin / b200_profile_end): CUDA events recorded around each stage on
+// the launching stream, by the calling thread.  Off by default; costs nothing when off.
+struct StageTimer {
+    static bool& enabled();
+    static void mark(const char* name, cudaStream_t stream);     // start of stage `name` (ends the previous one)
+    static void finish(cudaStream_t stream);                      // end of the last stage of a call
+};
+#define STAGE(name, stream) do { if (StageTimer::enabled()) StageTimer::mark(name, stream); } while (0)
+#define STAGE_END(stream) do { if (StageTimer::enabled()) StageTimer::finish(stream); } while (0)
+
 // internal entry points (device pointers, caller-provided stream)
 b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction,
                             int coset, cudaStream_t stream);

@@ -330,6 +330,7 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum;
     const g1_packed_t* pts = reinterpret_cast<const g1_packed_t*>(d_packed);
     if (!pts) {
+        STAGE("msm_pack", stream);
         CUDA_TRY(packed.alloc(n * sizeof(g1_packed_t), stream));
         B200_TRY(msm_pack_bases_device(packed.p, d_points, n, stride, stream));
         pts = packed.as<g1_packed_t>();
@@ -344,27 +345,35 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     CUDA_TRY(segs.alloc((size_t)segs_per_win * sh.nwin * sizeof(g1_xyzz_mem_t), stream));
     CUDA_TRY(wsum.alloc((size_t)sh.nwin * sizeof(g1_xyzz_mem_t), stream));
 
+    STAGE("msm_count", stream);
     CUDA_TRY(cudaMemsetAsync(counts.p, 0, (K + 1) * 4, stream));
     const unsigned nblk = (unsigned)((n + 255) / 256);
     msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh);
     KERNEL_CHECK();
+    STAGE("msm_scan", stream);
     B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
     CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+    STAGE("msm_scatter", stream);
     msm_scatter_kernel<<<nblk, 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
                                                  reinterpret_cast<const uint4*>(d_scalars), n, sh);
     KERNEL_CHECK();
+    STAGE("msm_accumulate", stream);
     msm_accumulate_kernel<<<(unsigned)((K + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
         buckets.as<g1_xyzz_mem_t>(), pts, entries.as<uint32_t>(), offsets.as<uint32_t>(), (uint32_t)K);
     KERNEL_CHECK();
+    STAGE("msm_reduce_segments", stream);
     const uint32_t nseg_threads = segs_per_win * sh.nwin;
     msm_reduce_segments_kernel<<<(nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
         segs.as<g1_xyzz_mem_t>(), buckets.as<g1_xyzz_mem_t>(), sh, seg_len, segs_per_win);
     KERNEL_CHECK();
+    STAGE("msm_window_sum", stream);
     msm_window_sum_kernel<<<sh.nwin, MSM_TREE_THREADS, 0, stream>>>(wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(),
                                                                    segs_per_win);
     KERNEL_CHECK();
+    STAGE("msm_fold", stream);
     msm_fold_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(), sh);
     KERNEL_CHECK();
+    STAGE_END(stream);
     return b200_ok();
 }
 

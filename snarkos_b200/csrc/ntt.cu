@@ -181,9 +181,12 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         uint32_t threads = tile_elems / 2;
         if (threads > 256) threads = 256;
         if (threads < 32) threads = 32;
+        static const char* const kPassName[NTT_MAX_PASSES] = {"ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"};
+        STAGE(kPassName[i], stream);
         dim3 grid(1u << (log_n - tile_log), (unsigned)batch);
         ntt_pass_kernel<<<grid, threads, (size_t)tile_elems * 32, stream>>>(p);
         KERNEL_CHECK();
     }
+    STAGE_END(stream);
     return b200_ok();
 }
