@@ -114,9 +114,10 @@ b200_error_t b200_debug_field_op(int op, void* out, const void* a, const void* b
  * 2: out[i] = k[i] * a[i] with 64-bit k in b.  out = Jacobian 144 B each. */
 b200_error_t b200_debug_g1_op(int op, void* out_jacobian, const void* a_affine, const void* b,
                               size_t n, size_t affine_stride);
-/* Throughput microbenchmarks: kind 0 IMAD, 1 IMAD.WIDE, 2 IMAD.HI, 3 Fr modmul, 4 Fq modmul, 5 XYZZ madd,
- * 6 IADD3.  Runs `iters` dependent operations per thread on a full-chip grid and reports the
- * elapsed milliseconds and the number of operations executed in total. */
+/* Throughput microbenchmarks (roofline denominators of the integer-multiply pipe).  kind: 0 IMAD, 1 IMAD.WIDE with
+ * addend (ptxas splits it), 2 IMAD.HI, 6 IADD3, 7 IMAD.WIDE without addend, 8 IMAD.WIDE.X carry chains, 11 DFMA,
+ * 14 IMAD.WIDE with addend and no chain, 3/4 Fr/Fq Montgomery product, 5 XYZZ mixed add.  Runs `iters`
+ * dependent operations per thread on a full-chip grid; reports elapsed milliseconds and operations executed. */
 b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops);
 /* Per-stage device timing of the calls the CALLING THREAD makes between begin and end (CUDA events on the
  * launching stream).  b200_profile_end synchronises the device and writes "stage=ms;stage=ms;..." into buf. */

@@ -456,20 +456,24 @@ extern "C" b200_error_t b200_debug_g1_op(int op, void* out, const void* a, const
 // ---------------------------------------------------------------------------------------------
 #define MB_THREADS 256
 #define MB_ILP 8
-// KIND: 0 IMAD (mad.lo), 1 IMAD.WIDE, 2 IMAD.HI, 6 IADD3, 3 Fr modmul, 4 Fq modmul, 5 XYZZ mixed add
+// KIND: 0 IMAD (mad.lo)            1 IMAD.WIDE with 64-bit addend      2 IMAD.HI        6 IADD3
+//       7 IMAD.WIDE, no addend     8 IMAD.WIDE.X carry chains (mad.lo.cc + madc.hi.cc pairs)   11 DFMA
+//       3 Fr modmul (default)      4 Fq modmul (default)   5 XYZZ mixed add
+// Every multiply takes an operand produced by the previous one, so nothing is loop invariant.
 template <int KIND>
 __global__ void __launch_bounds__(MB_THREADS) microbench_kernel(uint32_t iters, uint32_t* sink, uint32_t seed) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if constexpr (KIND <= 2 || KIND == 6) {
+    if constexpr (KIND <= 2 || KIND == 6 || KIND == 7) {
         uint32_t a[MB_ILP], b = seed | 1u;
         unsigned long long w[MB_ILP];
 #pragma unroll
-        for (int k = 0; k < MB_ILP; k++) { a[k] = tid * 2654435761u + k; w[k] = a[k]; }
+        for (int k = 0; k < MB_ILP; k++) { a[k] = tid * 2654435761u + k; w[k] = ((unsigned long long)a[k] << 32) | (a[k] * 7u + 1u); }
         for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
             for (int k = 0; k < MB_ILP; k++) {
                 if constexpr (KIND == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
-                else if constexpr (KIND == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(a[k]), "r"(b));
+                else if constexpr (KIND == 1) asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(w[k]) : "r"(b));
+                else if constexpr (KIND == 7) asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %0; or.b32 hi, hi, 1; mul.wide.u32 %0, lo, hi; }" : "+l"(w[k]));
                 else if constexpr (KIND == 2) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(it));
                 else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
             }
@@ -478,15 +482,75 @@ __global__ void __launch_bounds__(MB_THREADS) microbench_kernel(uint32_t iters, 
 #pragma unroll
         for (int k = 0; k < MB_ILP; k++) acc ^= a[k] ^ (uint32_t)w[k] ^ (uint32_t)(w[k] >> 32);
         if (acc == 0x12345u) sink[0] = acc;
+    } else if constexpr (KIND == 8) {
+        // two independent rows of four {mad.lo.cc, madc.hi.cc} pairs; multiplicands come from the other row
+        uint32_t X[9], Y[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) { X[k] = tid * 2654435761u + k; Y[k] = tid * 40503u + 3 * k + 1; }
+        for (uint32_t it = 0; it < iters; it++) {
+            uint32_t s = Y[0] | 1u, t = X[1] | 1u;
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                X[k] = (k == 0) ? ptx::mad_lo_cc(Y[k + 1], s, X[k]) : ptx::madc_lo_cc(Y[k + 1], s, X[k]);
+                X[k + 1] = ptx::madc_hi_cc(Y[k + 1], s, X[k + 1]);
+            }
+            X[8] = ptx::addc(X[8], 0u);
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                Y[k] = (k == 0) ? ptx::mad_lo_cc(X[k + 1], t, Y[k]) : ptx::madc_lo_cc(X[k + 1], t, Y[k]);
+                Y[k + 1] = ptx::madc_hi_cc(X[k + 1], t, Y[k + 1]);
+            }
+            Y[8] = ptx::addc(Y[8], 0u);
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) acc ^= X[k] ^ Y[k];
+        if (acc == 0x12345u) sink[0] = acc;
+    } else if constexpr (KIND == 14) {
+        // 64-bit accumulate without a carry chain: {mad.lo.cc, madc.hi} -> one IMAD.WIDE.U32 with a real addend
+        uint32_t lo[MB_ILP], hi[MB_ILP], b = seed | 1u;
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) { lo[k] = tid * 2654435761u + k; hi[k] = tid + 7u * k; }
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < MB_ILP; k++) {
+                uint32_t m = hi[k] | 1u;
+                uint32_t nl = ptx::mad_lo_cc(m, b, lo[k]);
+                hi[k] = ptx::madc_hi(m, b, hi[k]);
+                lo[k] = nl;
+            }
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) acc ^= lo[k] ^ hi[k];
+        if (acc == 0x12345u) sink[0] = acc;
+    } else if constexpr (KIND == 11) {
+        double d[MB_ILP], m = 1.0000001 + seed * 1e-12, c = 1e-9;
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) d[k] = 1.0 + tid * 1e-9 + k;
+        for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < MB_ILP; k++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[k]) : "d"(m), "d"(c));
+        }
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < MB_ILP; k++) acc += d[k];
+        if (acc == 0.12345) sink[0] = 1;
     } else if constexpr (KIND == 3) {
         fr_t x = fp_one<FrP>(), y = fp_r2<FrP>();
         x.v[0] ^= tid;
-        for (uint32_t it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
+        for (uint32_t it = 0; it < iters; it++) {
+            x = fp_mul(x, y);
+            y = fp_mul(y, x);
+        }
         if (x.v[0] == 0x12345u && y.v[1] == 7u) sink[0] = x.v[1];
     } else if constexpr (KIND == 4) {
         fq_t x = fp_one<FqP>(), y = fp_r2<FqP>();
         x.v[0] ^= tid;
-        for (uint32_t it = 0; it < iters; it++) { x = fp_mul(x, y); y = fp_mul(y, x); }
+        for (uint32_t it = 0; it < iters; it++) {
+            x = fp_mul(x, y);
+            y = fp_mul(y, x);
+        }
         if (x.v[0] == 0x12345u && y.v[1] == 7u) sink[0] = x.v[1];
     } else {
         g1_affine_t g;
@@ -522,7 +586,8 @@ static b200_error_t run_microbench(uint32_t iters, float* out_ms, double* out_op
     cudaEventDestroy(e1);
     const double threads = (double)grid * MB_THREADS;
     double per_thread = (double)iters;
-    if (KIND <= 2 || KIND == 6) per_thread *= MB_ILP;
+    if (KIND <= 2 || KIND == 6 || KIND == 7 || KIND == 11 || KIND == 14) per_thread *= MB_ILP;
+    else if (KIND == 8) per_thread *= 8;                      // 8 wide multiply-adds per iteration
     else if (KIND == 3 || KIND == 4) per_thread *= 2;
     *out_ops = threads * per_thread;
     return b200_ok();
@@ -530,7 +595,7 @@ static b200_error_t run_microbench(uint32_t iters, float* out_ms, double* out_op
 
 extern "C" b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* out_ms, double* out_ops) {
     B200_TRY(b200_require_device());
-    if (kind < 0 || kind > 6 || !out_ms || !out_ops) return b200_err(B200_ERR_INVALID_ARG, "microbench: bad argument");
+    if (kind < 0 || kind > 14 || kind == 9 || kind == 10 || kind == 12 || kind == 13 || !out_ms || !out_ops) return b200_err(B200_ERR_INVALID_ARG, "microbench: bad argument");
     B200_TRY(upload_generator());
     cudaStream_t s = b200_thread_stream();
     cudaDeviceProp prop;
@@ -543,6 +608,10 @@ extern "C" b200_error_t b200_debug_microbench(int kind, uint32_t iters, float* o
         case 3: return run_microbench<3>(iters, out_ms, out_ops, s, sms);
         case 4: return run_microbench<4>(iters, out_ms, out_ops, s, sms);
         case 5: return run_microbench<5>(iters, out_ms, out_ops, s, sms);
-        default: return run_microbench<6>(iters, out_ms, out_ops, s, sms);
+        case 6: return run_microbench<6>(iters, out_ms, out_ops, s, sms);
+        case 7: return run_microbench<7>(iters, out_ms, out_ops, s, sms);
+        case 8: return run_microbench<8>(iters, out_ms, out_ops, s, sms);
+        case 11: return run_microbench<11>(iters, out_ms, out_ops, s, sms);
+        default: return run_microbench<14>(iters, out_ms, out_ops, s, sms);
     }
 }

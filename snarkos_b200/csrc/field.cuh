@@ -28,6 +28,7 @@
 // ---------------------------------------------------------------------------------------------
 struct FrP {
     static constexpr int N = FR_LIMBS;
+    static constexpr int MODBITS = 253;
     B200_HDM static uint32_t mod(int i) {
         const uint32_t m[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu,
                                0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
@@ -47,6 +48,7 @@ struct FrP {
 
 struct FqP {
     static constexpr int N = FQ_LIMBS;
+    static constexpr int MODBITS = 377;
     B200_HDM static uint32_t mod(int i) {
         const uint32_t m[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u,
                                 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u,
@@ -198,7 +200,7 @@ B200_HD void row_mad_shift(uint32_t* acc, V v, uint32_t s) {
 
 }  // namespace detail
 
-template <class P> B200_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+template <class P> B200_HD Fp<P> fp_mul_cc(const Fp<P>& a, const Fp<P>& b) {
     constexpr int N = P::N;
     // X, Y: the two accumulators.  Exactly one of them is "even" (value at limb positions 0..N,
     // N + 1 limbs incl. carry limb) and the other "odd" (positions 1..N, N limbs) at any time.
@@ -253,7 +255,17 @@ template <class P> B200_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
-template <class P> B200_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul(a, a); }
+// Measured alternatives (profiles/r01_microbench_int_pipe.json, B200 @1965 MHz, per SM per clock):
+//   IMAD (lo) 63.5 | IMAD.HI 27.3 | IMAD.WIDE 31.5 | IMAD.WIDE + 64-bit addend 25.2 | IADD3 126 | DFMA 58.4
+// i.e. a full 32x32->64 product costs two multiplier passes however it is written, so the 2*N^2 wide
+// multiply-adds of this routine ARE the integer-multiply roofline: 288 / 31.5 = 9.14 clk per Fq product
+// (measured 9.33 = 98 %), 128 / 31.5 = 4.06 clk per Fr product (measured 4.19 = 97 %).  A carry-free
+// variant on 29-bit limbs (13 / 9 limbs, plain IMAD.WIDE into 64-bit columns) was built and measured at
+// 0.68x / 0.61x of this one (more products, and ptxas splits every accumulate into IMAD.WIDE + 2 IADD3),
+// and an FP64-pipe variant does not pay either (3 FP64 ops + 4 integer adds per 52-bit product makes it
+// issue-bound), so both were dropped.
+template <class P> B200_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul_cc(a, b); }
+template <class P> B200_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul_cc(a, a); }
 
 // canonical <-> Montgomery
 template <class P> B200_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul(a, fp_r2<P>()); }

@@ -5,7 +5,8 @@
 //   count     : signed c-bit digits of every scalar; histogram of (window, bucket)        [atomics in L2]
 //   scan      : exclusive prefix sum of the histogram -> start offset of every bucket
 //   scatter   : point index (+ sign bit) of every non-zero digit into its bucket's slot      [counting sort]
-//   accumulate: one thread per bucket, XYZZ mixed additions over its sorted point list
+//   accumulate: buckets cut into tasks of bounded length; one thread per task, XYZZ mixed additions over its
+//               slice of the sorted point list; pairwise rounds combine the partial sums of split buckets
 //   reduce    : per window, segmented running sum  sum_b (b + 1) * B_b ; block tree per window
 //   fold      : Horner over the windows with c doublings each -> Jacobian result
 // HBM layout: packed bases n * 96 B | entries n * nwin * 4 B | offsets (nwin * 2^(c-1) + 1) * 4 B |
@@ -158,17 +159,43 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket accumulation: one thread per (window, bucket); next point is fetched while the current mixed
-// addition runs (the add is ~3.3k instructions, a gather from HBM a few hundred cycles)
+// bucket accumulation, load balanced.  A bucket with more than `task_len` entries is cut into
+// ceil(cnt / task_len) equal tasks; one thread per task sums its slice of the sorted point list in XYZZ
+// (next point fetched while the current mixed addition runs: the add is ~3.3k instructions, a gather from
+// HBM a few hundred cycles).  Single-task buckets are written straight to `buckets`; the partial sums of
+// multi-task buckets are combined by log2(max tasks) pairwise rounds.  This bounds the work of any thread
+// by task_len additions whatever the scalar distribution (top window of the signed-digit split, repeated
+// scalars, tiny scalars ...), where one thread per bucket degenerates to a serial loop over n points.
 // ---------------------------------------------------------------------------------------------
+__global__ void msm_task_count_kernel(uint32_t* __restrict__ ntask, const uint32_t* __restrict__ offsets,
+                                      uint32_t nbuckets_total, uint32_t task_len) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nbuckets_total) return;
+    uint32_t cnt = k < nbuckets_total ? offsets[k + 1] - offsets[k] : 0;
+    ntask[k] = (cnt + task_len - 1) / task_len;
+}
+
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_accumulate_kernel(g1_xyzz_mem_t* __restrict__ buckets,
+                                                                        g1_xyzz_mem_t* __restrict__ partials,
+                                                                        uint32_t* __restrict__ task_bucket,
                                                                         const g1_packed_t* __restrict__ pts,
                                                                         const uint32_t* __restrict__ entries,
                                                                         const uint32_t* __restrict__ offsets,
+                                                                        const uint32_t* __restrict__ task_off,
                                                                         uint32_t nbuckets_total) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nbuckets_total) return;
-    uint32_t e = offsets[k], end = offsets[k + 1];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= task_off[nbuckets_total]) return;
+    // bucket of task t: the k with task_off[k] <= t < task_off[k + 1]
+    uint32_t lo = 0, hi = nbuckets_total;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t k = lo;
+    const uint32_t nt = task_off[k + 1] - task_off[k], j = t - task_off[k];
+    const uint32_t start = offsets[k], cnt = offsets[k + 1] - start;
+    uint32_t e = start + (uint32_t)(((unsigned long long)cnt * j) / nt);
+    const uint32_t end = start + (uint32_t)(((unsigned long long)cnt * (j + 1)) / nt);
     g1_xyzz_t acc = g1_xyzz_infinity();
     if (e < end) {
         uint32_t cur_id = entries[e];
@@ -190,7 +217,34 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_accumulate_kernel(g1_xyzz
             cur_id = nxt_id;
         }
     }
-    g1_xyzz_store(buckets + k, acc);
+    task_bucket[t] = k;
+    g1_xyzz_store(nt == 1 ? buckets + k : partials + t, acc);
+}
+
+// one pairwise round over the partial sums of multi-task buckets: P[j] += P[j + stride] for j = 0 mod 2*stride
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_round_kernel(g1_xyzz_mem_t* __restrict__ partials,
+                                                                           const uint32_t* __restrict__ task_bucket,
+                                                                           const uint32_t* __restrict__ task_off,
+                                                                           uint32_t nbuckets_total, uint32_t stride) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= task_off[nbuckets_total]) return;
+    const uint32_t k = task_bucket[t];
+    const uint32_t base = task_off[k], nt = task_off[k + 1] - base;
+    if (nt == 1) return;
+    const uint32_t j = t - base;
+    if ((j & (2 * stride - 1)) != 0 || j + stride >= nt) return;
+    g1_xyzz_t a = g1_xyzz_load(partials + t);
+    g1_xyzz_t b = g1_xyzz_load(partials + t + stride);
+    g1_add(a, b);
+    g1_xyzz_store(partials + t, a);
+}
+
+__global__ void msm_combine_final_kernel(g1_xyzz_mem_t* __restrict__ buckets, const g1_xyzz_mem_t* __restrict__ partials,
+                                         const uint32_t* __restrict__ task_off, uint32_t nbuckets_total) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbuckets_total) return;
+    const uint32_t base = task_off[k];
+    if (task_off[k + 1] - base > 1) buckets[k] = partials[base];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -327,7 +381,7 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     const size_t K = (size_t)sh.nwin * sh.nbuckets;
     if ((size_t)n * sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
 
-    DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum;
+    DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum, ntask, task_off, task_bucket, partials;
     const g1_packed_t* pts = reinterpret_cast<const g1_packed_t*>(d_packed);
     if (!pts) {
         STAGE("msm_pack", stream);
@@ -357,9 +411,40 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     msm_scatter_kernel<<<nblk, 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
                                                  reinterpret_cast<const uint4*>(d_scalars), n, sh);
     KERNEL_CHECK();
+    // ---- load-balanced accumulation ----
+    STAGE("msm_tasks", stream);
+    // task length: twice the mean bucket load, so that ordinary buckets are one task and only heavy ones split
+    size_t mean = n / sh.nbuckets;
+    uint32_t task_len = (uint32_t)(2 * mean);
+    if (const char* e = getenv("B200_MSM_TASK_LEN")) task_len = (uint32_t)atoi(e);
+    if (task_len < 32) task_len = 32;
+    // upper bound on the number of tasks: sum_k ceil(cnt_k / L) <= E / L + (non-empty buckets)
+    const size_t E = n * sh.nwin;
+    const size_t t_max = E / task_len + (K < E ? K : E) + 1;
+    CUDA_TRY(ntask.alloc((K + 1) * 4, stream));
+    CUDA_TRY(task_off.alloc((K + 2) * 4, stream));
+    CUDA_TRY(task_bucket.alloc(t_max * 4, stream));
+    CUDA_TRY(partials.alloc(t_max * sizeof(g1_xyzz_mem_t), stream));
+    msm_task_count_kernel<<<(unsigned)((K + 1 + 255) / 256), 256, 0, stream>>>(ntask.as<uint32_t>(), offsets.as<uint32_t>(),
+                                                                              (uint32_t)K, task_len);
+    KERNEL_CHECK();
+    B200_TRY(exclusive_scan(task_off.as<uint32_t>(), ntask.as<uint32_t>(), K, stream));
+    CUDA_TRY(cudaMemsetAsync(buckets.p, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
     STAGE("msm_accumulate", stream);
-    msm_accumulate_kernel<<<(unsigned)((K + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS), MSM_ACC_THREADS, 0, stream>>>(
-        buckets.as<g1_xyzz_mem_t>(), pts, entries.as<uint32_t>(), offsets.as<uint32_t>(), (uint32_t)K);
+    const unsigned tblocks = (unsigned)((t_max + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+    msm_accumulate_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
+        buckets.as<g1_xyzz_mem_t>(), partials.as<g1_xyzz_mem_t>(), task_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(),
+        offsets.as<uint32_t>(), task_off.as<uint32_t>(), (uint32_t)K);
+    KERNEL_CHECK();
+    STAGE("msm_combine", stream);
+    const size_t max_tasks_per_bucket = (n + task_len - 1) / task_len;
+    for (uint32_t stride = 1; stride < max_tasks_per_bucket; stride <<= 1) {
+        msm_combine_round_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(partials.as<g1_xyzz_mem_t>(), task_bucket.as<uint32_t>(),
+                                                                         task_off.as<uint32_t>(), (uint32_t)K, stride);
+        KERNEL_CHECK();
+    }
+    msm_combine_final_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(buckets.as<g1_xyzz_mem_t>(), partials.as<g1_xyzz_mem_t>(),
+                                                                             task_off.as<uint32_t>(), (uint32_t)K);
     KERNEL_CHECK();
     STAGE("msm_reduce_segments", stream);
     const uint32_t nseg_threads = segs_per_win * sh.nwin;

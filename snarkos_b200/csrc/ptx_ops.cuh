@@ -68,6 +68,13 @@ __device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t 
 __device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
+// carry-free 32 x 32 + 64 -> 64 (plain IMAD.WIDE.U32: full IMAD rate, unlike the .X carry variants)
+__device__ __forceinline__ unsigned long long mad_wide(uint32_t a, uint32_t b, unsigned long long c) {
+    unsigned long long r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ unsigned long long mul_wide(uint32_t a, uint32_t b) {
+    unsigned long long r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+}
 
 #else  // ---------------------------------------------------------------- host emulation
 
@@ -102,6 +109,8 @@ static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
     uint64_t t = (uint64_t)mul_hi(a, b) + c + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t;
 }
 static inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + CF; }
+static inline unsigned long long mad_wide(uint32_t a, uint32_t b, unsigned long long c) { return (unsigned long long)a * b + c; }
+static inline unsigned long long mul_wide(uint32_t a, uint32_t b) { return (unsigned long long)a * b; }
 
 #endif
 

@@ -17,6 +17,8 @@ extern "C" {
         for (size_t i = 0; i < n; i++) st<P>(out + P::N * i, FN(ld<P>(a + P::N * i), ld<P>(b + P::N * i))); \
     }
 BINOP(host_fr_mul, FrP, fp_mul<FrP>)
+BINOP(host_fr_mul_cc, FrP, fp_mul_cc<FrP>)
+BINOP(host_fq_mul_cc, FqP, fp_mul_cc<FqP>)
 BINOP(host_fr_add, FrP, fp_add<FrP>)
 BINOP(host_fr_sub, FrP, fp_sub<FrP>)
 BINOP(host_fq_mul, FqP, fp_mul<FqP>)
@@ -26,6 +28,8 @@ BINOP(host_fq_sub, FqP, fp_sub<FqP>)
     void NAME(uint32_t* out, const uint32_t* a, size_t n) {                                   \
         for (size_t i = 0; i < n; i++) st<P>(out + P::N * i, FN(ld<P>(a + P::N * i)));          \
     }
+UNOP(host_fr_sqr, FrP, fp_sqr<FrP>)
+UNOP(host_fq_sqr, FqP, fp_sqr<FqP>)
 UNOP(host_fr_neg, FrP, fp_neg<FrP>)
 UNOP(host_fq_neg, FqP, fp_neg<FqP>)
 UNOP(host_fr_inv, FrP, fp_inv<FrP>)

@@ -104,6 +104,29 @@ def test_resident_bases_and_device_path():
     assert H.jac_bytes_to_affine(tot.cpu().numpy()) == want
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "two_values", "tiny", "top_heavy"])
+def test_skewed_scalar_distributions(kind):
+    """Heavily loaded buckets (one bucket receiving most points) must go through the task split + combine rounds."""
+    import torch
+    import snarkos_b200 as S
+    n, seed = 1 << 14, 21
+    dbases = _synthetic(n, seed)
+    rng = np.random.default_rng(4)
+    if kind == "all_equal":
+        vals = [O.R_MOD - 12345] * n
+    elif kind == "two_values":
+        vals = [3 if i % 3 else (1 << 200) + 7 for i in range(n)]
+    elif kind == "tiny":
+        vals = [int(x) for x in rng.integers(0, 4, size=n)]
+    else:
+        vals = [(1 << 252) + int(x) for x in rng.integers(0, 1 << 20, size=n)]
+    sc = H.scalars_array(vals)
+    out = S.VariableBase.msm(dbases, torch.from_numpy(sc.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    k = H.splitmix64_at(seed, np.arange(n))
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+
+
 @pytest.mark.parametrize("log_n", [20, 24])
 def test_full_size_exact_identity(log_n):
     """size-independent exact check at BASELINE scale: P_i = k_i G  =>  MSM = (sum s_i k_i mod r) G"""

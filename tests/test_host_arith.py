@@ -56,7 +56,10 @@ def test_field_ops(hostlib, name, mod, bits, nl, rinv):
     e = _edge(mod)
     a = [rng.below(mod, bits) for _ in range(3000)] + [x for x in e for _ in e]
     b = [rng.below(mod, bits) for _ in range(3000)] + [y for _ in e for y in e]
-    assert _bin(hostlib, f"host_{name}_mul", a, b, nl) == [x * y * rinv % mod for x, y in zip(a, b)]
+    want = [x * y * rinv % mod for x, y in zip(a, b)]
+    assert _bin(hostlib, f"host_{name}_mul", a, b, nl) == want
+    assert _bin(hostlib, f"host_{name}_mul_cc", a, b, nl) == want          # carry-chain variant
+    assert _un(hostlib, f"host_{name}_sqr", a, nl) == [x * x * rinv % mod for x in a]
     assert _bin(hostlib, f"host_{name}_add", a, b, nl) == [(x + y) % mod for x, y in zip(a, b)]
     assert _bin(hostlib, f"host_{name}_sub", a, b, nl) == [(x - y) % mod for x, y in zip(a, b)]
     assert _un(hostlib, f"host_{name}_neg", a, nl) == [(-x) % mod for x in a]

@@ -42,8 +42,9 @@ def staged(fn, reps=3):
 
 
 if "micro" in what:
-    names = {0: "imad", 1: "imad_wide", 2: "imad_hi", 6: "iadd", 3: "fr_modmul", 4: "fq_modmul", 5: "xyzz_madd"}
-    iters = {0: 8192, 1: 8192, 2: 8192, 6: 8192, 3: 512, 4: 256, 5: 64}
+    names = {0: "imad_lo", 2: "imad_hi", 7: "imad_wide_noaddend", 1: "imad_wide+iadd3x2(ptxas split)", 14: "imad_wide_addend",
+             8: "imad_wide_x_chain", 6: "iadd3", 11: "dfma", 3: "fr_modmul", 4: "fq_modmul", 5: "xyzz_madd"}
+    iters = {0: 8192, 1: 8192, 2: 8192, 6: 8192, 7: 8192, 8: 2048, 11: 8192, 14: 8192, 3: 512, 4: 256, 5: 64}
     res["micro"] = {}
     for kind, name in names.items():
         ms, ops = ctypes.c_float(), ctypes.c_double()
@@ -52,7 +53,7 @@ if "micro" in what:
             S._lib.check(S.lib().b200_debug_microbench(kind, iters[kind], ctypes.byref(ms), ctypes.byref(ops)))
             best = max(best, ops.value / (ms.value * 1e-3))
         res["micro"][name] = best
-        print(f"micro {name:10s} {best / 1e9:10.2f} Gop/s  ({best / 148 / 1.965e9:6.2f} per SM per clk @1965MHz)", flush=True)
+        print(f"micro {name:32s} {best / 1e9:10.2f} Gop/s  ({best / 148 / 1.965e9:6.2f} per SM per clk @1965MHz)", flush=True)
 
 if "msm" in what:
     res["msm"] = {}
