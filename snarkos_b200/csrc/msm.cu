@@ -5,8 +5,8 @@
 //   count     : signed c-bit digits of every scalar; histogram of (window, bucket)        [atomics in L2]
 //   scan      : exclusive prefix sum of the histogram -> start offset of every bucket
 //   scatter   : point index (+ sign bit) of every non-zero digit into its bucket's slot      [counting sort]
-//   accumulate: buckets cut into tasks of bounded length; one thread per task, XYZZ mixed additions over its
-//               slice of the sorted point list; pairwise rounds combine the partial sums of split buckets
+//   accumulate: the sorted entry stream cut into equal chunks, one thread per chunk, XYZZ mixed additions; runs that
+//               cross a chunk boundary are stitched by pairwise combine rounds
 //   reduce    : per window, segmented running sum  sum_b (b + 1) * B_b ; block tree per window
 //   fold      : Horner over the windows with c doublings each -> Jacobian result
 // HBM layout: packed bases n * 96 B | entries n * nwin * 4 B | offsets (nwin * 2^(c-1) + 1) * 4 B |
@@ -44,35 +44,72 @@ __global__ void msm_pack_kernel(g1_packed_t* __restrict__ out, const uint8_t* __
     out[i] = p;
 }
 
+// Warp-aggregated histogram update.  Structural hot spots (the top window of the signed-digit split has only a
+// few possible digits; repeated or tiny scalars) otherwise serialise millions of atomics on one address (measured:
+// 8 ms instead of 3 ms at 2^24, c = 18).  __match_any_sync would find every group but costs ~500 cycles when the
+// 32 keys are distinct (the common case; measured +3 ms), so only two leader rounds are run: the key of the lowest
+// pending lane is broadcast, every lane holding it joins that leader's single atomicAdd and receives its rank; lanes
+// still pending after two rounds (all-distinct keys) fall back to one atomic each.  Returns the reserved slot.
+__device__ __forceinline__ uint32_t warp_aggregated_inc(uint32_t* counters, size_t key, bool active) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t pending = __ballot_sync(0xffffffffu, active);
+    uint32_t pos = 0;
+    bool mine = active;
+#pragma unroll
+    for (int round = 0; round < 2; round++) {
+        if (pending == 0) break;                                   // warp-uniform
+        const uint32_t leader = __ffs(pending) - 1;
+        const unsigned long long lkey = __shfl_sync(0xffffffffu, (unsigned long long)key, leader);
+        const uint32_t group = __ballot_sync(0xffffffffu, mine && (unsigned long long)key == lkey);
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(group));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mine && ((group >> lane) & 1u)) {
+            pos = base + __popc(group & ((1u << lane) - 1));
+            mine = false;
+        }
+        pending &= ~group;
+    }
+    if (mine) pos = atomicAdd(&counters[key], 1u);
+    return pos;
+}
+
 __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __restrict__ scalars, size_t n,
                                  MsmShape sh) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
-    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const bool valid = i < n;
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+        uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    }
     uint32_t carry = 0;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t neg;
         uint32_t d = msm_signed_digit(s, w, sh.c, carry, neg);
-        if (d) atomicAdd(&counts[(size_t)w * sh.nbuckets + (d - 1)], 1u);
+        warp_aggregated_inc(counts, (size_t)w * sh.nbuckets + (d ? d - 1 : 0), valid && d != 0);
     }
 }
 
+// scatter is launched window-major (blockIdx.y = window): at any moment the chip works on one or two windows, so
+// the live cursor slice and that window's slice of `entries` (n * 4 B) stay in L2 and the 4-byte scattered writes
+// merge there instead of each dirtying a 32-byte HBM sector (measured 8.9 -> 3.7 ms at 2^24, c = 20).  Every
+// thread re-derives the carry chain of the lower windows (a few shifts per window).
 __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __restrict__ cursor,
                                    const uint4* __restrict__ scalars, size_t n, MsmShape sh) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
-    uint32_t s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < sh.nwin; w++) {
-        uint32_t neg;
-        uint32_t d = msm_signed_digit(s, w, sh.c, carry, neg);
-        if (d) {
-            uint32_t pos = atomicAdd(&cursor[(size_t)w * sh.nbuckets + (d - 1)], 1u);
-            entries[pos] = (uint32_t)i | (neg << 31);
-        }
+    const bool valid = i < n;
+    const uint32_t w = blockIdx.y;
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+        uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
     }
+    uint32_t carry = 0, neg = 0, d = 0;
+    for (uint32_t ww = 0; ww <= w; ww++) d = msm_signed_digit(s, ww, sh.c, carry, neg);
+    const bool active = valid && d != 0;
+    uint32_t pos = warp_aggregated_inc(cursor, (size_t)w * sh.nbuckets + (d ? d - 1 : 0), active);
+    if (active) entries[pos] = (uint32_t)i | (neg << 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -159,92 +196,120 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// bucket accumulation, load balanced.  A bucket with more than `task_len` entries is cut into
-// ceil(cnt / task_len) equal tasks; one thread per task sums its slice of the sorted point list in XYZZ
-// (next point fetched while the current mixed addition runs: the add is ~3.3k instructions, a gather from
-// HBM a few hundred cycles).  Single-task buckets are written straight to `buckets`; the partial sums of
-// multi-task buckets are combined by log2(max tasks) pairwise rounds.  This bounds the work of any thread
-// by task_len additions whatever the scalar distribution (top window of the signed-digit split, repeated
-// scalars, tiny scalars ...), where one thread per bucket degenerates to a serial loop over n points.
+// bucket accumulation, equal work per lane.  The sorted entry stream is cut into chunks of `chunk` entries
+// regardless of bucket boundaries; one thread per chunk walks it with XYZZ mixed additions (the next point is
+// fetched while the current addition runs: the add is ~3.3k instructions, a gather from HBM a few hundred
+// cycles).  Every lane of a warp does the same number of additions, whatever the bucket-size distribution, so
+// the window width can grow (fewer windows = fewer additions) without losing SIMT efficiency, and no scalar
+// distribution (top window of the signed-digit split, repeated or tiny scalars) can pile n points on a thread.
+// A run of equal-bucket entries inside a chunk is flushed when the bucket ends:
+//   bucket entirely inside the chunk          -> buckets[k]
+//   run that continues a bucket begun earlier -> heads[t]   (first run of thread t)
+//   run that starts a bucket continuing later -> tails[t]   (last run of thread t)
+// and a bucket spanning threads t_a .. t_b is tails[t_a] + heads[t_a+1] + ... + heads[t_b]: the heads are summed
+// by pairwise rounds (log2 of the longest span), the tail is added last.
 // ---------------------------------------------------------------------------------------------
-__global__ void msm_task_count_kernel(uint32_t* __restrict__ ntask, const uint32_t* __restrict__ offsets,
-                                      uint32_t nbuckets_total, uint32_t task_len) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > nbuckets_total) return;
-    uint32_t cnt = k < nbuckets_total ? offsets[k + 1] - offsets[k] : 0;
-    ntask[k] = (cnt + task_len - 1) / task_len;
-}
+#define MSM_NONE 0xffffffffu
 
 __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_accumulate_kernel(g1_xyzz_mem_t* __restrict__ buckets,
-                                                                        g1_xyzz_mem_t* __restrict__ partials,
-                                                                        uint32_t* __restrict__ task_bucket,
+                                                                        g1_xyzz_mem_t* __restrict__ heads,
+                                                                        g1_xyzz_mem_t* __restrict__ tails,
+                                                                        uint32_t* __restrict__ head_bucket,
+                                                                        uint32_t* __restrict__ tail_bucket,
                                                                         const g1_packed_t* __restrict__ pts,
                                                                         const uint32_t* __restrict__ entries,
                                                                         const uint32_t* __restrict__ offsets,
-                                                                        const uint32_t* __restrict__ task_off,
-                                                                        uint32_t nbuckets_total) {
+                                                                        uint32_t* __restrict__ max_heads,
+                                                                        uint32_t nbuckets_total, uint32_t chunk) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= task_off[nbuckets_total]) return;
-    // bucket of task t: the k with task_off[k] <= t < task_off[k + 1]
+    const uint32_t total = offsets[nbuckets_total];
+    const unsigned long long e0 = (unsigned long long)t * chunk;
+    if (e0 >= total) return;
+    uint32_t e = (uint32_t)e0;
+    const uint32_t end = (e0 + chunk < total) ? (uint32_t)(e0 + chunk) : total;
+    // bucket of the first entry: the k with offsets[k] <= e < offsets[k + 1]
     uint32_t lo = 0, hi = nbuckets_total;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        if (task_off[mid] <= t) lo = mid; else hi = mid;
+        if (offsets[mid] <= e) lo = mid; else hi = mid;
     }
-    const uint32_t k = lo;
-    const uint32_t nt = task_off[k + 1] - task_off[k], j = t - task_off[k];
-    const uint32_t start = offsets[k], cnt = offsets[k + 1] - start;
-    uint32_t e = start + (uint32_t)(((unsigned long long)cnt * j) / nt);
-    const uint32_t end = start + (uint32_t)(((unsigned long long)cnt * (j + 1)) / nt);
+    uint32_t k = lo;
+    uint32_t bucket_end = offsets[k + 1];
+    bool from_start = (offsets[k] == e);
     g1_xyzz_t acc = g1_xyzz_infinity();
-    if (e < end) {
-        uint32_t cur_id = entries[e];
-        g1_packed_t cur = pts[cur_id & 0x7fffffffu];
-        for (;;) {
-            ++e;
-            uint32_t nxt_id = 0;
-            g1_packed_t nxt;
-            const bool more = e < end;
-            if (more) {
-                nxt_id = entries[e];
-                nxt = pts[nxt_id & 0x7fffffffu];
-            }
-            g1_affine_t a = g1_unpack(cur);
-            if (cur_id >> 31) a.y = fp_neg(a.y);
-            g1_madd(acc, a);
-            if (!more) break;
-            cur = nxt;
-            cur_id = nxt_id;
+    uint32_t cur_id = entries[e];
+    g1_packed_t cur = pts[cur_id & 0x7fffffffu];
+    for (;;) {
+        const uint32_t nxt_e = e + 1;
+        uint32_t nxt_id = 0;
+        g1_packed_t nxt;
+        if (nxt_e < end) {
+            nxt_id = entries[nxt_e];
+            nxt = pts[nxt_id & 0x7fffffffu];
         }
+        g1_affine_t a = g1_unpack(cur);
+        if (cur_id >> 31) a.y = fp_neg(a.y);
+        g1_madd(acc, a);
+        e = nxt_e;
+        const bool at_bucket_end = (e == bucket_end), at_chunk_end = (e == end);
+        if (at_bucket_end || at_chunk_end) {
+            if (!from_start) {
+                g1_xyzz_store(heads + t, acc);
+                head_bucket[t] = k;
+                // longest run of heads of any bucket (plain read as a filter, atomic only when it grows)
+                const uint32_t nh = (bucket_end - 1) / chunk - offsets[k] / chunk;
+                if (nh > *(volatile uint32_t*)max_heads) atomicMax(max_heads, nh);
+            } else if (at_bucket_end) {
+                g1_xyzz_store(buckets + k, acc);
+            } else {
+                g1_xyzz_store(tails + t, acc);
+                tail_bucket[t] = k;
+            }
+            if (at_chunk_end) break;
+            do { ++k; } while (offsets[k + 1] == e);          // next non-empty bucket starts exactly at e
+            bucket_end = offsets[k + 1];
+            from_start = true;
+            acc = g1_xyzz_infinity();
+        }
+        cur = nxt;
+        cur_id = nxt_id;
     }
-    task_bucket[t] = k;
-    g1_xyzz_store(nt == 1 ? buckets + k : partials + t, acc);
 }
 
-// one pairwise round over the partial sums of multi-task buckets: P[j] += P[j + stride] for j = 0 mod 2*stride
-__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_round_kernel(g1_xyzz_mem_t* __restrict__ partials,
-                                                                           const uint32_t* __restrict__ task_bucket,
-                                                                           const uint32_t* __restrict__ task_off,
-                                                                           uint32_t nbuckets_total, uint32_t stride) {
+// one pairwise round over the heads of every spanning bucket: heads[j] += heads[j + stride], j = 0 mod 2*stride
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_heads_kernel(g1_xyzz_mem_t* __restrict__ heads,
+                                                                           const uint32_t* __restrict__ head_bucket,
+                                                                           const uint32_t* __restrict__ offsets,
+                                                                           const uint32_t* __restrict__ max_heads,
+                                                                           uint32_t nthreads_total, uint32_t chunk,
+                                                                           uint32_t stride) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= task_off[nbuckets_total]) return;
-    const uint32_t k = task_bucket[t];
-    const uint32_t base = task_off[k], nt = task_off[k + 1] - base;
-    if (nt == 1) return;
-    const uint32_t j = t - base;
-    if ((j & (2 * stride - 1)) != 0 || j + stride >= nt) return;
-    g1_xyzz_t a = g1_xyzz_load(partials + t);
-    g1_xyzz_t b = g1_xyzz_load(partials + t + stride);
+    if (t >= nthreads_total || stride >= *max_heads) return;          // no bucket has that many heads: whole round is a no-op
+    const uint32_t k = head_bucket[t];
+    if (k == MSM_NONE) return;
+    const uint32_t ta = offsets[k] / chunk, tb = (offsets[k + 1] - 1) / chunk;
+    const uint32_t nh = tb - ta, j = t - (ta + 1);
+    if ((j & (2 * stride - 1)) != 0 || j + stride >= nh) return;
+    g1_xyzz_t a = g1_xyzz_load(heads + t);
+    g1_xyzz_t b = g1_xyzz_load(heads + t + stride);
     g1_add(a, b);
-    g1_xyzz_store(partials + t, a);
+    g1_xyzz_store(heads + t, a);
 }
 
-__global__ void msm_combine_final_kernel(g1_xyzz_mem_t* __restrict__ buckets, const g1_xyzz_mem_t* __restrict__ partials,
-                                         const uint32_t* __restrict__ task_off, uint32_t nbuckets_total) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nbuckets_total) return;
-    const uint32_t base = task_off[k];
-    if (task_off[k + 1] - base > 1) buckets[k] = partials[base];
+// bucket = tail of the thread where it starts + the (already summed) heads of the following threads
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_tails_kernel(g1_xyzz_mem_t* __restrict__ buckets,
+                                                                           const g1_xyzz_mem_t* __restrict__ heads,
+                                                                           const g1_xyzz_mem_t* __restrict__ tails,
+                                                                           const uint32_t* __restrict__ tail_bucket,
+                                                                           uint32_t nthreads_total) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads_total) return;
+    const uint32_t k = tail_bucket[t];
+    if (k == MSM_NONE) return;
+    g1_xyzz_t a = g1_xyzz_load(tails + t);
+    g1_xyzz_t b = g1_xyzz_load(heads + t + 1);
+    g1_add(a, b);
+    g1_xyzz_store(buckets + k, a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,9 +399,10 @@ extern "C" uint32_t b200_msm_window_bits(size_t n) {
     }
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int c = (int)lg - 4;
+    // measured sweeps (profiles/r01_msm_sweep_equal_work.json): 2^16 -> 11..13, 2^20 -> 15, 2^24 -> 20
+    int c = (int)lg - (lg >= 22 ? 4 : 5);
     if (c < 4) c = 4;
-    if (c > 21) c = 21;
+    if (c > 20) c = 20;
     return (uint32_t)c;
 }
 
@@ -381,7 +447,7 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     const size_t K = (size_t)sh.nwin * sh.nbuckets;
     if ((size_t)n * sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
 
-    DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum, ntask, task_off, task_bucket, partials;
+    DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum, heads, tails, head_bucket, tail_bucket, max_heads;
     const g1_packed_t* pts = reinterpret_cast<const g1_packed_t*>(d_packed);
     if (!pts) {
         STAGE("msm_pack", stream);
@@ -394,7 +460,11 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     CUDA_TRY(cursor.alloc((K + 1) * 4, stream));
     CUDA_TRY(entries.alloc(n * sh.nwin * 4, stream));
     CUDA_TRY(buckets.alloc(K * sizeof(g1_xyzz_mem_t), stream));
-    const uint32_t seg_len = sh.nbuckets < MSM_SEG_LEN ? sh.nbuckets : MSM_SEG_LEN;
+    // segment length of the running-sum reduction: short segments when there are few buckets (latency), long
+    // ones when there are many (each segment pays a ~c-step double-and-add for its offset)
+    uint32_t seg_len = 8;
+    while (seg_len < 64 && K / seg_len > 65536) seg_len <<= 1;
+    if (seg_len > sh.nbuckets) seg_len = sh.nbuckets;
     const uint32_t segs_per_win = (sh.nbuckets + seg_len - 1) / seg_len;
     CUDA_TRY(segs.alloc((size_t)segs_per_win * sh.nwin * sizeof(g1_xyzz_mem_t), stream));
     CUDA_TRY(wsum.alloc((size_t)sh.nwin * sizeof(g1_xyzz_mem_t), stream));
@@ -408,43 +478,39 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
     CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
     STAGE("msm_scatter", stream);
-    msm_scatter_kernel<<<nblk, 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
+    msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
                                                  reinterpret_cast<const uint4*>(d_scalars), n, sh);
     KERNEL_CHECK();
-    // ---- load-balanced accumulation ----
-    STAGE("msm_tasks", stream);
-    // task length: twice the mean bucket load, so that ordinary buckets are one task and only heavy ones split
-    size_t mean = n / sh.nbuckets;
-    uint32_t task_len = (uint32_t)(2 * mean);
-    if (const char* e = getenv("B200_MSM_TASK_LEN")) task_len = (uint32_t)atoi(e);
-    if (task_len < 32) task_len = 32;
-    // upper bound on the number of tasks: sum_k ceil(cnt_k / L) <= E / L + (non-empty buckets)
-    const size_t E = n * sh.nwin;
-    const size_t t_max = E / task_len + (K < E ? K : E) + 1;
-    CUDA_TRY(ntask.alloc((K + 1) * 4, stream));
-    CUDA_TRY(task_off.alloc((K + 2) * 4, stream));
-    CUDA_TRY(task_bucket.alloc(t_max * 4, stream));
-    CUDA_TRY(partials.alloc(t_max * sizeof(g1_xyzz_mem_t), stream));
-    msm_task_count_kernel<<<(unsigned)((K + 1 + 255) / 256), 256, 0, stream>>>(ntask.as<uint32_t>(), offsets.as<uint32_t>(),
-                                                                              (uint32_t)K, task_len);
-    KERNEL_CHECK();
-    B200_TRY(exclusive_scan(task_off.as<uint32_t>(), ntask.as<uint32_t>(), K, stream));
-    CUDA_TRY(cudaMemsetAsync(buckets.p, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
+    // ---- equal-work accumulation ----
     STAGE("msm_accumulate", stream);
+    uint32_t chunk = 128;
+    if (const char* e = getenv("B200_MSM_CHUNK")) chunk = (uint32_t)atoi(e);
+    if (chunk < 8) chunk = 8;
+    const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
+    const size_t t_max = (E + chunk - 1) / chunk;
+    CUDA_TRY(heads.alloc((t_max + 1) * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(tails.alloc(t_max * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(head_bucket.alloc((t_max + 1) * 4, stream));
+    CUDA_TRY(tail_bucket.alloc(t_max * 4, stream));
+    CUDA_TRY(max_heads.alloc(16, stream));
+    CUDA_TRY(cudaMemsetAsync(max_heads.p, 0, 16, stream));
+    CUDA_TRY(cudaMemsetAsync(head_bucket.p, 0xff, (t_max + 1) * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(tail_bucket.p, 0xff, t_max * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(buckets.p, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
     const unsigned tblocks = (unsigned)((t_max + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
     msm_accumulate_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
-        buckets.as<g1_xyzz_mem_t>(), partials.as<g1_xyzz_mem_t>(), task_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(),
-        offsets.as<uint32_t>(), task_off.as<uint32_t>(), (uint32_t)K);
+        buckets.as<g1_xyzz_mem_t>(), heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
+        tail_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(), offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)K, chunk);
     KERNEL_CHECK();
     STAGE("msm_combine", stream);
-    const size_t max_tasks_per_bucket = (n + task_len - 1) / task_len;
-    for (uint32_t stride = 1; stride < max_tasks_per_bucket; stride <<= 1) {
-        msm_combine_round_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(partials.as<g1_xyzz_mem_t>(), task_bucket.as<uint32_t>(),
-                                                                         task_off.as<uint32_t>(), (uint32_t)K, stride);
+    const size_t max_span = (n + chunk - 1) / chunk + 1;            // a bucket holds at most n entries
+    for (uint32_t stride = 1; stride < max_span; stride <<= 1) {
+        msm_combine_heads_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(heads.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
+                                                                         offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride);
         KERNEL_CHECK();
     }
-    msm_combine_final_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(buckets.as<g1_xyzz_mem_t>(), partials.as<g1_xyzz_mem_t>(),
-                                                                             task_off.as<uint32_t>(), (uint32_t)K);
+    msm_combine_tails_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(buckets.as<g1_xyzz_mem_t>(), heads.as<g1_xyzz_mem_t>(),
+                                                                     tails.as<g1_xyzz_mem_t>(), tail_bucket.as<uint32_t>(), (uint32_t)t_max);
     KERNEL_CHECK();
     STAGE("msm_reduce_segments", stream);
     const uint32_t nseg_threads = segs_per_win * sh.nwin;

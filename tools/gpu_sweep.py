@@ -57,17 +57,21 @@ if "micro" in what:
 
 if "msm" in what:
     res["msm"] = {}
-    for log_n, cs in ((16, (10, 11, 12, 13)), (20, (14, 15, 16, 17)), (24, (16, 17, 18, 19, 20, 21))):
+    chunks = [int(x) for x in os.environ.get("SWEEP_CHUNKS", "64").split(",")]
+    for log_n, cs in ((16, (10, 11, 12, 13, 14)), (20, (14, 15, 16, 17, 18)), (24, (17, 18, 19, 20, 21))):
         n = 1 << log_n
         bases = S.synthetic_bases(n, seed=5)
         sc = rand_limbs(n, 1)
         rb = S.ResidentBases(bases)
         for c in cs:
-            os.environ["B200_MSM_C"] = str(c)
-            tot, st = staged(lambda: rb.msm(sc), reps=2)
-            res["msm"][f"2^{log_n} c={c}"] = {"total_ms": tot, **st}
-            print(f"msm 2^{log_n} c={c}: total {tot:8.3f} ms  " + " ".join(f"{k[4:]}={v:.3f}" for k, v in st.items()), flush=True)
+            for ch in chunks:
+                os.environ["B200_MSM_C"] = str(c)
+                os.environ["B200_MSM_CHUNK"] = str(ch)
+                tot, st = staged(lambda: rb.msm(sc), reps=2)
+                res["msm"][f"2^{log_n} c={c} chunk={ch}"] = {"total_ms": tot, **st}
+                print(f"msm 2^{log_n} c={c} chunk={ch}: total {tot:8.3f} ms  " + " ".join(f"{k[4:]}={v:.3f}" for k, v in st.items()), flush=True)
         os.environ.pop("B200_MSM_C", None)
+        os.environ.pop("B200_MSM_CHUNK", None)
         rb.release()
         del bases, sc
 
