@@ -214,14 +214,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    partials = torch.empty((world, 144), dtype=torch.uint8, device=dev) if world > 1 else None
+    from snarkos_b200 import dist as D
 
     def step_msm():
-        out = S.VariableBase.msm(bases, scalars)            # this rank's point range -> partial sum
-        if world > 1:                                       # 8 partial sums gathered and added (tiny)
-            dist.all_gather_into_tensor(partials.view(-1), out.contiguous())
-            out = S.sum_projective(partials)
-        return out
+        # this rank's point range -> partial sum; for N > 1 the partial sums are all-gathered (144 B each) and added
+        return D.msm_sharded(bases, scalars)
 
     def step_ntt():
         dom.fft_in_place(ntt_data)

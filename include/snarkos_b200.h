@@ -103,6 +103,14 @@ b200_error_t b200_ntt_fr_bls12_377(void* inout_32B_mont, uint32_t log_n, size_t 
 b200_error_t b200_ntt_fr_bls12_377_device(void* d_inout, uint32_t log_n, size_t batch,
                                           size_t batch_stride_elems, int direction, int coset, void* stream);
 
+/* Multi-GPU four-step building block: scales a block of a distributed polynomial of total size 2^log_n.
+ * kind 0: element (r, c) of the row-major [rows x cols] block times w_N^((row_base + r) * (col_base + c)) -- the
+ * twiddle between the two transform axes; kind 1: element i times 22^(row_base + i) (direction 0) or
+ * 22^-(row_base + i) (direction 1) -- the coset shift.  w_N is the inverse root for direction 1. */
+b200_error_t b200_fr_mul_powers_device(void* d_data, uint32_t log_n, int direction, int kind,
+                                       unsigned long long rows, unsigned long long cols,
+                                       unsigned long long row_base, unsigned long long col_base, void* stream);
+
 /* ---- synthetic inputs & diagnostics (used by bench.py / tests; not on the snarkVM call path) ---- */
 /* points[i] = k_i * G with k_i = splitmix64(seed, i), written as G1Affine images (Montgomery). */
 b200_error_t b200_g1_synthetic_bases_device(void* d_out_points, size_t npoints, size_t affine_stride,

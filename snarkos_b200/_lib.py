@@ -38,6 +38,7 @@ SYMBOLS = {
     "b200_g1_sum_jacobian_device": (b200_error_t, [_vp, _vp, _sz, _vp]),
     "b200_ntt_fr_bls12_377": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i]),
     "b200_ntt_fr_bls12_377_device": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i, _vp]),
+    "b200_fr_mul_powers_device": (b200_error_t, [_vp, _u32, _i, _i, _u64, _u64, _u64, _u64, _vp]),
     "b200_g1_synthetic_bases_device": (b200_error_t, [_vp, _sz, _sz, _u64, _vp]),
     "b200_debug_field_op": (b200_error_t, [_i, _vp, _vp, _vp, _sz]),
     "b200_debug_g1_op": (b200_error_t, [_i, _vp, _vp, _vp, _sz, _sz]),

@@ -41,6 +41,30 @@ __global__ void ntt_pow_table_kernel(uint4* out, fr_t base, uint32_t nsq, uint32
     out[2 * i + 1] = hi;
 }
 
+// Element (r, c) of a row-major [rows x cols] matrix times w_N^((row_base + r) * (col_base + c)) (kind 0: the
+// four-step twiddle between the two transform axes) or element i of a vector times g^(base + i) / g^-(base + i)
+// (kind 1: the coset shift of a block of a distributed polynomial).  Powers come from the two-level tables.
+__global__ void __launch_bounds__(256) ntt_mul_powers_kernel(uint4* __restrict__ data, const uint4* __restrict__ lo,
+                                                             const uint4* __restrict__ hi, unsigned long long rows,
+                                                             unsigned long long cols, unsigned long long row_base,
+                                                             unsigned long long col_base, uint32_t log_n, int kind) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    unsigned long long e;
+    if (kind == 0) {
+        const unsigned long long r = i / cols, c = i - r * cols;
+        e = ((row_base + r) * (col_base + c)) & ((1ull << log_n) - 1);
+    } else {
+        e = row_base + i;
+    }
+    fr_t x = fr_load(data, i);
+    if (e) x = fp_mul(x, pow2level(lo, hi, e));
+    uint4 a, b;
+    fr_to_u4(x, a, b);
+    data[2 * i] = a;
+    data[2 * i + 1] = b;
+}
+
 // out = (2^log_n)^-1 in Montgomery form
 __global__ void ntt_size_inv_kernel(fr_t* out, uint32_t log_n) {
     fr_t n = fp_zero<FrP>();
@@ -116,6 +140,29 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         it = g_ntt.domains.emplace(key, t).first;
     }
     *out = it->second;
+    return b200_ok();
+}
+
+// Multi-GPU four-step helpers (see snarkos_b200/dist.py): twiddle / coset scaling of a block of a distributed
+// polynomial of total size 2^log_n.
+extern "C" b200_error_t b200_fr_mul_powers_device(void* d_data, uint32_t log_n, int direction, int kind,
+                                                  unsigned long long rows, unsigned long long cols,
+                                                  unsigned long long row_base, unsigned long long col_base, void* stream) {
+    B200_TRY(b200_require_device());
+    if (log_n > NTT_MAX_LOG_N || (direction != 0 && direction != 1) || (kind != 0 && kind != 1))
+        return b200_err(B200_ERR_INVALID_ARG, "fr_mul_powers: bad argument");
+    if (rows == 0 || cols == 0) return b200_ok();
+    if (!d_data) return b200_err(B200_ERR_INVALID_ARG, "fr_mul_powers: null pointer");
+    if (kind == 1 && row_base + rows * cols > (1ull << log_n)) return b200_err(B200_ERR_INVALID_ARG, "fr_mul_powers: coset range exceeds the domain");
+    NttDomainTables tabs;
+    const uint4* tile_tw = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_TRY(get_tables(log_n, direction, s, &tabs, &tile_tw));
+    const unsigned long long total = rows * cols;
+    ntt_mul_powers_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<uint4*>(d_data), kind == 0 ? tabs.pow_lo : tabs.coset_lo, kind == 0 ? tabs.pow_hi : tabs.coset_hi, rows,
+        cols, row_base, col_base, log_n, kind);
+    KERNEL_CHECK();
     return b200_ok();
 }
 
