@@ -189,6 +189,10 @@ def run_b200(args):
     S.init(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if "B200_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["B200_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)          # NCCL_DEBUG=VERSION/WARN prints a banner on stdout; keep it to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = 1 << args.log_n
