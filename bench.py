@@ -280,13 +280,25 @@ def run_b200(args):
             dom.fft_in_place(h_ntt)                          # H2D 2^24 * 32 B, compute, D2H 2^24 * 32 B
         barrier()
         t3 = time.perf_counter()
-        tt = torch.tensor([t1 - t0, t3 - t2], dtype=torch.float64, device=dev)
+        # KZG-style call: bases resident (registered once, like an SRS), only the scalars cross PCIe each step
+        rb = S.ResidentBases(bases)
+        rb.msm(h_scalars)
+        barrier()
+        t4 = time.perf_counter()
+        for _ in range(Ke):
+            rb.msm(h_scalars)
+        barrier()
+        t5 = time.perf_counter()
+        rb.release()
+        tt = torch.tensor([t1 - t0, t3 - t2, t5 - t4], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e_msm, e_ntt = [float(x) for x in tt.cpu()]
+        e_msm, e_ntt, e_res = [float(x) for x in tt.cpu()]
         e2e = {"value": world * n * Ke / e_msm / 1e6, "unit": "Mpoints/s",
                "h2d_bytes_per_step": int(h_bases.numel() + h_scalars.numel() * 8), "d2h_bytes_per_step": 144,
-               "steps": Ke, "api": "snarkos_b200.VariableBase.msm(pinned host bases, pinned host scalars) -> b200_msm_g1_bls12_377"}
+               "steps": Ke, "api": "snarkos_b200.VariableBase.msm(pinned host bases, pinned host scalars) -> b200_msm_g1_bls12_377",
+               "resident_bases": {"value": world * n * Ke / e_res / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h_scalars.numel() * 8),
+                                  "d2h_bytes_per_step": 144, "api": "snarkos_b200.ResidentBases.msm(pinned host scalars) -> b200_msm_registered"}}
         ntt_e2e = {"value": world * n * Ke / e_ntt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": int(h_ntt.numel() * 8),
                    "d2h_bytes_per_step": int(h_ntt.numel() * 8), "steps": Ke,
                    "api": "snarkos_b200.EvaluationDomain.fft_in_place(pinned host tensor) -> b200_ntt_fr_bls12_377"}

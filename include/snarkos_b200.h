@@ -85,6 +85,14 @@ b200_error_t b200_msm_registered_device(void* d_out_jacobian_144B, uint64_t hand
                                         size_t nscalars, void* stream);
 b200_error_t b200_msm_release_bases(uint64_t handle);
 
+/* KZG10::commit / commit_lagrange against resident powers [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs]:
+ * out = sum_i coeffs[i] * powers[i] for coefficients (or Lagrange evaluations) given as Montgomery Fr elements,
+ * exactly what snarkVM holds in a DensePolynomial; the to_bigint conversion runs on the device.  A hiding commitment is
+ * this call on powers_of_beta_g plus this call on powers_of_beta_times_gamma_g with the blinding polynomial, added. */
+b200_error_t b200_kzg_commit(void* out_jacobian_144B, uint64_t handle, const void* coeffs_32B_mont, size_t ncoeffs);
+b200_error_t b200_kzg_commit_device(void* d_out_jacobian_144B, uint64_t handle, const void* d_coeffs_mont,
+                                    size_t ncoeffs, void* stream);
+
 /* Window width the library would pick for `npoints` (0 = library default); B200_MSM_C overrides. */
 uint32_t b200_msm_window_bits(size_t npoints);
 

@@ -34,6 +34,8 @@ SYMBOLS = {
     "b200_msm_registered": (b200_error_t, [_vp, _u64, _vp, _sz]),
     "b200_msm_registered_device": (b200_error_t, [_vp, _u64, _vp, _sz, _vp]),
     "b200_msm_release_bases": (b200_error_t, [_u64]),
+    "b200_kzg_commit": (b200_error_t, [_vp, _u64, _vp, _sz]),
+    "b200_kzg_commit_device": (b200_error_t, [_vp, _u64, _vp, _sz, _vp]),
     "b200_msm_window_bits": (_u32, [_sz]),
     "b200_g1_sum_jacobian_device": (b200_error_t, [_vp, _vp, _sz, _vp]),
     "b200_ntt_fr_bls12_377": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i]),

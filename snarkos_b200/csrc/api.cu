@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary (include/snarkos_b200.h): lifecycle, host-buffer wrappers, resident
 // bases, synthetic inputs and the diagnostic / microbenchmark kernels.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -163,6 +164,21 @@ extern "C" b200_error_t b200_msm_g1_bls12_377_device(void* d_out, const void* d_
     return msm_run_device(d_out, d_points, n, d_scalars, stride, nullptr, (cudaStream_t)stream);
 }
 
+// Second per-thread stream: host->device copies of the next point range overlap the MSM of the current one.
+static thread_local ThreadStream t_copy_stream;
+static cudaStream_t b200_thread_copy_stream() {
+    if (!t_copy_stream.s) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        t_copy_stream.s = s;
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        g_api.streams.push_back(s);
+    }
+    return t_copy_stream.s;
+}
+
+#define MSM_HOST_CHUNK_LOG 22       // host-buffer calls with >= 2^23 points stream the inputs in 2^22-point ranges
+
 extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, size_t n, const void* scalars,
                                               size_t stride) {
     B200_TRY(b200_require_device());
@@ -170,18 +186,70 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     if (n && (!points || !scalars)) return b200_err(B200_ERR_INVALID_ARG, "msm: null input pointer");
     cudaStream_t s = b200_thread_stream();
     if (!s) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
-    DevBuf d_pts, d_sc, d_out;
-    CUDA_TRY(d_pts.alloc(n * stride, s));
-    CUDA_TRY(d_sc.alloc(n * 32, s));
-    CUDA_TRY(d_out.alloc(144, s));
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    const size_t chunk = (size_t)1 << MSM_HOST_CHUNK_LOG;
+    if (n < 2 * chunk || getenv("B200_MSM_NO_HOST_PIPELINE")) {
+        DevBuf d_pts, d_sc, d_out;
+        CUDA_TRY(d_pts.alloc(n * stride, s));
+        CUDA_TRY(d_sc.alloc(n * 32, s));
+        CUDA_TRY(d_out.alloc(144, s));
+        if (n) {
+            CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+        }
+        B200_TRY(msm_run_device(d_out.p, d_pts.p, n, d_sc.p, stride, nullptr, s));
+        CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return b200_ok();
     }
-    B200_TRY(msm_run_device(d_out.p, d_pts.p, n, d_sc.p, stride, nullptr, s));
-    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return b200_ok();
+    // Large call: the MSM is a sum over point ranges, so the ranges are pipelined -- range i+1 crosses PCIe while
+    // range i is being multiplied (double-buffered staging), and the partial sums are added at the end.
+    cudaStream_t cs = b200_thread_copy_stream();
+    if (!cs) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    DevBuf d_pts[2], d_sc[2], d_part, d_out;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(d_pts[b].alloc(chunk * stride, s));
+        CUDA_TRY(d_sc[b].alloc(chunk * 32, s));
+    }
+    CUDA_TRY(d_part.alloc(nchunks * 144, s));
+    CUDA_TRY(d_out.alloc(144, s));
+    std::vector<cudaEvent_t> copied(nchunks), computed(nchunks);
+    cudaEvent_t ready;
+    CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    for (size_t i = 0; i < nchunks; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ready, s));                 // staging buffers exist from here on in stream order
+    CUDA_TRY(cudaStreamWaitEvent(cs, ready, 0));
+    b200_error_t rc = b200_ok();
+    for (size_t i = 0; i < nchunks && rc.code == 0; i++) {
+        const int b = (int)(i & 1);
+        const size_t off = i * chunk, cnt = (n - off < chunk) ? n - off : chunk;
+        cudaError_t e = cudaSuccess;
+        if (i >= 2) e = cudaStreamWaitEvent(cs, computed[i - 2], 0);        // staging buffer b is free again
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pts[b].p, (const uint8_t*)points + off * stride, cnt * stride, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sc[b].p, (const uint8_t*)scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(copied[i], cs);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, copied[i], 0);
+        if (e != cudaSuccess) { rc = b200_cuda_err(e); break; }
+        rc = msm_run_device((uint8_t*)d_part.p + i * 144, d_pts[b].p, cnt, d_sc[b].p, stride, nullptr, s);
+        if (rc.code == 0) {
+            e = cudaEventRecord(computed[i], s);
+            if (e != cudaSuccess) rc = b200_cuda_err(e);
+        }
+    }
+    if (rc.code == 0) rc = b200_g1_sum_jacobian_device(d_out.p, d_part.p, nchunks, s);
+    if (rc.code == 0) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = b200_cuda_err(e);
+    }
+    cudaStreamSynchronize(cs);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (rc.code == 0 && e2 != cudaSuccess) rc = b200_cuda_err(e2);
+    cudaEventDestroy(ready);
+    for (size_t i = 0; i < nchunks; i++) { cudaEventDestroy(copied[i]); cudaEventDestroy(computed[i]); }
+    return rc;
 }
 
 extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, size_t n, size_t stride,
@@ -242,6 +310,55 @@ extern "C" b200_error_t b200_msm_registered(void* out, uint64_t handle, const vo
     CUDA_TRY(d_out.alloc(144, s));
     if (n) CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
     B200_TRY(b200_msm_registered_device(d_out.p, handle, d_sc.p, n, s));
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+// ---------------------------------------------------------------------------------------------
+// KZG10::commit / commit_lagrange over resident bases
+//   snarkVM: (num_leading_zeros, plain_coeffs) = skip_leading_zeros_and_convert_to_bigints(p);
+//            VariableBase::msm(&powers_of_beta_g[num_leading_zeros..], &plain_coeffs)
+//   [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs].  Here the Montgomery -> canonical conversion runs on the
+//   device and zero coefficients simply produce no bucket entries, so the result is the same group element.
+// ---------------------------------------------------------------------------------------------
+__global__ void fr_from_mont_kernel(uint4* __restrict__ out, const uint4* __restrict__ in, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t x = fr_from_u4(in[2 * i], in[2 * i + 1]);
+    x = fp_from_mont(x);
+    uint4 a, b;
+    fr_to_u4(x, a, b);
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+}
+
+extern "C" b200_error_t b200_kzg_commit_device(void* d_out, uint64_t handle, const void* d_coeffs_mont, size_t n,
+                                               void* stream) {
+    B200_TRY(b200_require_device());
+    RegisteredBases rb;
+    B200_TRY(lookup_bases(handle, &rb));
+    if (n > rb.n) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit: polynomial longer than the registered powers");
+    if (!d_out || (n && !d_coeffs_mont)) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf d_sc;
+    CUDA_TRY(d_sc.alloc(n * 32, s));
+    if (n) {
+        fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_sc.as<uint4>(), reinterpret_cast<const uint4*>(d_coeffs_mont), n);
+        KERNEL_CHECK();
+    }
+    return msm_run_device(d_out, nullptr, n, d_sc.p, 0, rb.d_packed, s);
+}
+
+extern "C" b200_error_t b200_kzg_commit(void* out, uint64_t handle, const void* coeffs_mont, size_t n) {
+    B200_TRY(b200_require_device());
+    if (!out || (n && !coeffs_mont)) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit: null pointer");
+    cudaStream_t s = b200_thread_stream();
+    DevBuf d_c, d_out;
+    CUDA_TRY(d_c.alloc(n * 32, s));
+    CUDA_TRY(d_out.alloc(144, s));
+    if (n) CUDA_TRY(cudaMemcpyAsync(d_c.p, coeffs_mont, n * 32, cudaMemcpyHostToDevice, s));
+    B200_TRY(b200_kzg_commit_device(d_out.p, handle, d_c.p, n, s));
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return b200_ok();

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 // ---------------------------------------------------------------------------------------------
 #define MSM_NONE 0xffffffffu
 
-__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_accumulate_kernel(g1_xyzz_mem_t* __restrict__ buckets,
+__global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_xyzz_mem_t* __restrict__ buckets,
                                                                         g1_xyzz_mem_t* __restrict__ heads,
                                                                         g1_xyzz_mem_t* __restrict__ tails,
                                                                         uint32_t* __restrict__ head_bucket,

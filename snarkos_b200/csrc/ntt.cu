@@ -65,6 +65,21 @@ __global__ void __launch_bounds__(256) ntt_mul_powers_kernel(uint4* __restrict__
     data[2 * i + 1] = b;
 }
 
+// boundary table of one pass: out[k * S + m] = w_M^(m * k), M = 2^log_sub, S = 2^log_stride (M entries)
+__global__ void __launch_bounds__(256) ntt_boundary_table_kernel(uint4* __restrict__ out, const uint4* __restrict__ lo,
+                                                                 const uint4* __restrict__ hi, uint32_t log_n,
+                                                                 uint32_t log_sub, uint32_t log_stride) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> log_sub) return;
+    const unsigned long long k = i >> log_stride, m = i & ((1ull << log_stride) - 1);
+    const unsigned long long ex = ((m * k) & ((1ull << log_sub) - 1)) << (log_n - log_sub);
+    fr_t w = pow2level(lo, hi, ex);
+    uint4 a, b;
+    fr_to_u4(w, a, b);
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+}
+
 // out = (2^log_n)^-1 in Montgomery form
 __global__ void ntt_size_inv_kernel(fr_t* out, uint32_t log_n) {
     fr_t n = fp_zero<FrP>();
@@ -75,7 +90,12 @@ __global__ void ntt_size_inv_kernel(fr_t* out, uint32_t log_n) {
 // ---------------------------------------------------------------------------------------------
 // cached per-(log_n, direction) tables
 // ---------------------------------------------------------------------------------------------
+#define NTT_BOUNDARY_TABLE_MAX_LOG 25          // up to 2^25 entries = 1 GiB per pass boundary; larger -> two-level powers
 struct NttDomainTables {
+    // per-pass inter-pass twiddle tables, valid for the plan recorded next to them
+    uint4* boundary[NTT_MAX_PASSES] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t boundary_plan[NTT_MAX_PASSES] = {0, 0, 0, 0};
+    uint32_t boundary_npasses = 0;
     uint4* pow_lo = nullptr;
     uint4* pow_hi = nullptr;
     uint4* coset_lo = nullptr;
@@ -105,7 +125,7 @@ static b200_error_t build_pow_table(uint4** out, const uint32_t* base_limbs, uin
 }
 
 static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t stream, NttDomainTables* out,
-                               const uint4** tile_tw) {
+                               const uint4** tile_tw, const NttPlan* plan = nullptr) {
     std::lock_guard<std::mutex> lock(g_ntt.mu);
     if (!g_ntt.smem_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -138,6 +158,32 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         CUDA_TRY(cudaStreamSynchronize(stream));
         CUDA_TRY(cudaFree(d_inv));
         it = g_ntt.domains.emplace(key, t).first;
+    }
+    if (plan && plan->npasses > 1 && !getenv("B200_NTT_NO_BOUNDARY_TABLES")) {
+        NttDomainTables& t = it->second;
+        bool same = t.boundary_npasses == plan->npasses;
+        for (uint32_t i = 0; same && i < plan->npasses; i++) same = (t.boundary_plan[i] == plan->log_len[i]);
+        if (!same) {                                  // (re)build for this plan; happens once per (size, direction, plan)
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            for (uint32_t i = 0; i < NTT_MAX_PASSES; i++) {
+                if (t.boundary[i]) CUDA_TRY(cudaFree(t.boundary[i]));
+                t.boundary[i] = nullptr;
+                t.boundary_plan[i] = i < plan->npasses ? plan->log_len[i] : 0;
+            }
+            t.boundary_npasses = plan->npasses;
+            uint32_t before = 0;
+            for (uint32_t i = 0; i + 1 < plan->npasses; i++) {
+                const uint32_t log_sub = log_n - before, log_stride = log_sub - plan->log_len[i];
+                before += plan->log_len[i];
+                if (log_sub > NTT_BOUNDARY_TABLE_MAX_LOG) continue;
+                const size_t count = (size_t)1 << log_sub;
+                CUDA_TRY(cudaMalloc(&t.boundary[i], count * 32));
+                ntt_boundary_table_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(t.boundary[i], t.pow_lo, t.pow_hi,
+                                                                                             log_n, log_sub, log_stride);
+                KERNEL_CHECK();
+            }
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
     }
     *out = it->second;
     return b200_ok();
@@ -173,6 +219,8 @@ void ntt_release_tables() {
         g_ntt.tile_tw[d] = nullptr;
     }
     for (auto& kv : g_ntt.domains) {
+        for (int i = 0; i < NTT_MAX_PASSES; i++)
+            if (kv.second.boundary[i]) cudaFree(kv.second.boundary[i]);
         cudaFree(kv.second.pow_lo);
         cudaFree(kv.second.pow_hi);
         cudaFree(kv.second.coset_lo);
@@ -197,7 +245,7 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
     if (!ntt_make_plan(log_n, &plan)) return b200_err(B200_ERR_INVALID_ARG, "ntt: no valid pass plan");
     NttDomainTables tabs;
     const uint4* tile_tw = nullptr;
-    B200_TRY(get_tables(log_n, direction, stream, &tabs, &tile_tw));
+    B200_TRY(get_tables(log_n, direction, stream, &tabs, &tile_tw, &plan));
 
     DevBuf scratch;
     if (plan.npasses > 1) CUDA_TRY(scratch.alloc(((batch - 1) * batch_stride + n) * 32, stream));
@@ -211,6 +259,7 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         p.tile_tw = tile_tw;
         p.pow_lo = tabs.pow_lo;
         p.pow_hi = tabs.pow_hi;
+        p.boundary_tw = tabs.boundary[i];
         p.coset_lo = tabs.coset_lo;
         p.coset_hi = tabs.coset_hi;
         p.size_inv = tabs.size_inv;

@@ -34,6 +34,7 @@ struct NttPassParams {
     const uint4* tile_tw;           // w_{2^12}^e (direction-specific), e < 2^11
     const uint4* pow_lo;            // w_N^e, e < 2^13                        (inter-pass twiddles)
     const uint4* pow_hi;            // w_N^(e << 13)
+    const uint4* boundary_tw;       // optional: w_M^(m*k) for this pass at index k*S + m (M entries); null -> two-level
     const uint4* coset_lo;          // g^e (forward) or g^-e (inverse), e < 2^13
     const uint4* coset_hi;          // g^(e << 13) / g^-(e << 13)
     fr_t size_inv;                  // n^-1 (Montgomery)
@@ -168,15 +169,23 @@ B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, uint32_t s, uint
     NttGeom g = ntt_geom(p);
     uint32_t log_d = g.log_len - 1 - s;
     uint32_t nbf = g.tile_elems >> 1;                   // butterflies in the tile
+    // Butterfly (block b, offset j) pairs t0 = b*2d + j with t0 + d and uses twiddle w_L^(j << s); j == 0 needs no
+    // product.  For the long-distance stages consecutive lanes take consecutive j (conflict-free shared memory);
+    // for the last stages (d <= 4) lanes are ordered j-major instead, so that whole warps have j == 0 and really
+    // skip the multiplication (1/d of the butterflies of a stage; d = 1: all of them).
+    const bool j_major = log_d <= 2;
+    const uint32_t log_blocks = g.log_len - 1 - log_d;  // blocks of 2d points
     for (uint32_t u = tid; u < nbf; u += nthreads) {
         uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
-        uint32_t j = q & ((1u << log_d) - 1);
-        uint32_t t0 = ((q >> log_d) << (log_d + 1)) | j;
+        uint32_t j, b;
+        if (j_major) { b = q & ((1u << log_blocks) - 1); j = q >> log_blocks; }
+        else         { j = q & ((1u << log_d) - 1); b = q >> log_d; }
+        uint32_t t0 = (b << (log_d + 1)) | j;
         uint32_t e0 = (t0 << g.log_cw) + cw, e1 = e0 + (1u << (log_d + g.log_cw));
         fr_t a = tile_load(sm, g.tile_elems, e0);
-        fr_t b = tile_load(sm, g.tile_elems, e1);
-        fr_t sum = fp_add(a, b);
-        fr_t dif = fp_sub(a, b);
+        fr_t bb = tile_load(sm, g.tile_elems, e1);
+        fr_t sum = fp_add(a, bb);
+        fr_t dif = fp_sub(a, bb);
         uint32_t tw = (j << s) << (NTT_TILE_TW_LOG - g.log_len);     // exponent of w_{2^12}
         if (tw) dif = fp_mul(dif, fr_load(p.tile_tw, tw));
         tile_store(sm, g.tile_elems, e0, sum);
@@ -201,9 +210,14 @@ B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t t
             unsigned long long sub = tile >> log_tiles_per_sub;
             unsigned long long m = ((unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw) + cw;
             out = (sub << g.log_sub) + ((unsigned long long)k << g.log_stride) + m;
-            // twiddle w_{M}^(m*k) = w_N^((m*k mod M) << (log_n - log_sub))
-            unsigned long long ex = ((m * k) & ((1ull << g.log_sub) - 1)) << (p.log_n - g.log_sub);
-            if (ex) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, ex));
+            // twiddle w_{M}^(m*k): one product from the per-pass table when it exists (same offset as the output
+            // inside its sub-problem), else w_N^((m*k mod M) << (log_n - log_sub)) from the two-level tables
+            if (p.boundary_tw) {
+                if (m && k) x = fp_mul(x, fr_load(p.boundary_tw, ((unsigned long long)k << g.log_stride) + m));
+            } else {
+                unsigned long long ex = ((m * k) & ((1ull << g.log_sub) - 1)) << (p.log_n - g.log_sub);
+                if (ex) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, ex));
+            }
         } else if (p.npasses == 1) {
             out = k;
         } else {

@@ -1,0 +1,70 @@
+"""Host-side mirror of the MSM-bearing part of snarkVM's `polycommit::kzg10::KZG10` [UPSTREAM
+algorithms/src/polycommit/kzg10/mod.rs; SURVEY.md 8a row a9, 8f rank 1]: `commit` / `commit_lagrange` against powers
+that stay resident in HBM.  The SRS is fixed for the lifetime of the process, so it is uploaded (and re-packed) once;
+each commit moves only the polynomial."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .msm import PROJECTIVE_BYTES, ResidentBases, _dev_out, _host_bytes, _is_cuda_tensor, _np_ptr, _stream_ptr, sum_projective
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class Powers:
+    """`Powers { powers_of_beta_g, powers_of_beta_times_gamma_g }` (or the Lagrange-basis equivalents) on the device."""
+
+    def __init__(self, powers_of_beta_g, powers_of_beta_times_gamma_g=None, stride: int = 104):
+        self.powers_of_beta_g = ResidentBases(powers_of_beta_g, stride)
+        self.powers_of_beta_times_gamma_g = (ResidentBases(powers_of_beta_times_gamma_g, stride)
+                                             if powers_of_beta_times_gamma_g is not None else None)
+
+    def release(self) -> None:
+        self.powers_of_beta_g.release()
+        if self.powers_of_beta_times_gamma_g is not None:
+            self.powers_of_beta_times_gamma_g.release()
+
+
+def _commit_one(rb: ResidentBases, coeffs):
+    L = _lib.lib()
+    if _is_cuda_tensor(coeffs):
+        c = coeffs.contiguous().view(torch.uint8).reshape(-1)
+        n = c.numel() // 32
+        out = _dev_out(c.device)
+        _lib.check(L.b200_kzg_commit_device(ctypes.c_void_p(out.data_ptr()), rb.handle, ctypes.c_void_p(c.data_ptr()), n, _stream_ptr()))
+        return out
+    c = _host_bytes(coeffs)
+    out = np.zeros(PROJECTIVE_BYTES, dtype=np.uint8)
+    _lib.check(L.b200_kzg_commit(_np_ptr(out), rb.handle, _np_ptr(c), c.size // 32))
+    return out
+
+
+class KZG10:
+    @staticmethod
+    def commit(powers: Powers, polynomial_coeffs, blinding_coeffs: Optional[object] = None):
+        """`KZG10::commit(powers, polynomial, hiding_bound, rng)`'s group arithmetic: sum_i coeffs[i] * beta^i G, plus
+        sum_i blinding[i] * gamma beta^i G when a blinding polynomial is given (the caller draws it, as snarkVM's
+        `KZGRandomness::rand` does on the CPU).  Coefficients are Montgomery Fr limbs ([n, 4] uint64 / CUDA tensors).
+        Returns the G1Projective image (numpy uint8[144] for host inputs, CUDA tensor for device inputs)."""
+        if blinding_coeffs is not None and powers.powers_of_beta_times_gamma_g is None:
+            raise ValueError("hiding commitment needs powers_of_beta_times_gamma_g")
+        c = _commit_one(powers.powers_of_beta_g, polynomial_coeffs)
+        if blinding_coeffs is None:
+            return c
+        r = _commit_one(powers.powers_of_beta_times_gamma_g, blinding_coeffs)
+        if _is_cuda_tensor(c):
+            return sum_projective(torch.stack([c, r]))
+        both = torch.from_numpy(np.stack([c, r])).cuda()
+        out = sum_projective(both)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    # commit_lagrange is the same sum against the Lagrange-basis powers with evaluations as "coefficients"
+    commit_lagrange = commit

@@ -37,7 +37,8 @@ extern "C" int host_ntt_plan(uint32_t log_n, uint32_t* npasses, uint32_t* log_le
 // data: batch polynomials of 2^log_n Montgomery Fr (8 x u32 each), stride in elements.  `nthreads` emulated
 // threads per CTA.  plan_len/plan_cw: explicit plan (npasses entries) or npasses = 0 to use ntt_make_plan.
 extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t stride, int direction, int coset,
-                        uint32_t npasses, const uint32_t* plan_len, const uint32_t* plan_cw, uint32_t nthreads) {
+                        uint32_t npasses, const uint32_t* plan_len, const uint32_t* plan_cw, uint32_t nthreads,
+                        int use_tables) {
     if (log_n == 0) return 0;
     NttPlan plan;
     if (npasses == 0) {
@@ -60,6 +61,24 @@ extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t
     nn.v[log_n >> 5] = 1u << (log_n & 31);
     fr_t size_inv = fp_inv(fp_to_mont(nn));
 
+    // per-pass boundary tables, exactly as ntt_boundary_table_kernel fills them (use_tables = 0 exercises the
+    // two-level fallback)
+    std::vector<std::vector<uint4>> boundary(NTT_MAX_PASSES);
+    if (use_tables) {
+        uint32_t before = 0;
+        for (uint32_t i = 0; i + 1 < plan.npasses; i++) {
+            uint32_t log_sub = log_n - before, log_stride = log_sub - plan.log_len[i];
+            before += plan.log_len[i];
+            size_t count = (size_t)1 << log_sub;
+            boundary[i].resize(2 * count);
+            for (size_t q = 0; q < count; q++) {
+                unsigned long long k = q >> log_stride, m = q & ((1ull << log_stride) - 1);
+                unsigned long long ex = ((m * k) & ((1ull << log_sub) - 1)) << (log_n - log_sub);
+                fr_t w = pow2level(pow_lo.data(), pow_hi.data(), ex);
+                fr_to_u4(w, boundary[i][2 * q], boundary[i][2 * q + 1]);
+            }
+        }
+    }
     size_t total = ((size_t)(batch - 1) * stride + ((size_t)1 << log_n));
     std::vector<uint4> scratch(2 * total);
     uint4* d = reinterpret_cast<uint4*>(data);
@@ -72,6 +91,7 @@ extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t
         p.dst = last ? d : scratch.data();
         p.tile_tw = tile_tw.data();
         p.pow_lo = pow_lo.data(); p.pow_hi = pow_hi.data();
+        p.boundary_tw = boundary[i].empty() ? nullptr : boundary[i].data();
         p.coset_lo = coset_lo.data(); p.coset_hi = coset_hi.data();
         p.size_inv = size_inv;
         p.batch_stride = stride;

@@ -141,3 +141,32 @@ def test_full_size_exact_identity(log_n):
     torch.cuda.synchronize()
     k = H.splitmix64_at(seed, np.arange(n))
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+
+
+def test_kzg_commit_resident_powers():
+    """KZG10::commit over resident powers: Montgomery coefficients in, conversion on the device, zero coefficients
+    (leading and interior) contribute nothing, hiding = second MSM on the gamma powers added."""
+    import torch
+    import snarkos_b200 as S
+    n = 1 << 12
+    g_powers = _synthetic(n, 31)
+    gamma_powers = _synthetic(64, 32)
+    powers = S.Powers(g_powers, gamma_powers)
+    rng = np.random.default_rng(9)
+    coeffs_mont = H.random_fr_mont_np(rng, (3000,))
+    coeffs_mont[:17] = 0                      # leading zeros (skip_leading_zeros_and_convert_to_bigints)
+    coeffs_mont[100:140] = 0
+    blind_mont = H.random_fr_mont_np(rng, (40,))
+    plain = C.fr_from_mont(coeffs_mont)
+    plain_b = C.fr_from_mont(blind_mont)
+    hb, hg = g_powers.cpu().numpy(), gamma_powers.cpu().numpy()
+    want = oracle_msm(hb[:3000 * 104], plain)
+    assert H.jac_bytes_to_affine(S.KZG10.commit(powers, coeffs_mont)) == want
+    dev = S.KZG10.commit(powers, torch.from_numpy(coeffs_mont.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    assert H.jac_bytes_to_affine(dev.cpu().numpy()) == want
+    want_h = O.g1_add(want, oracle_msm(hg[:40 * 104], plain_b))
+    assert H.jac_bytes_to_affine(S.KZG10.commit(powers, coeffs_mont, blind_mont)) == want_h
+    with pytest.raises(S.B200Error):
+        S.KZG10.commit(powers, H.random_fr_mont_np(rng, (n + 1,)))
+    powers.release()

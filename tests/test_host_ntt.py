@@ -26,13 +26,13 @@ def hostlib():
     return ctypes.CDLL(so)
 
 
-def run(lib, data, log_n, batch, stride, direction, coset, lens=(), cws=(), nthreads=8):
+def run(lib, data, log_n, batch, stride, direction, coset, lens=(), cws=(), nthreads=8, use_tables=1):
     buf = np.ascontiguousarray(data, dtype=np.uint64).copy()
     L = (ctypes.c_uint32 * 4)(*(list(lens) + [0] * (4 - len(lens))))
     W = (ctypes.c_uint32 * 4)(*(list(cws) + [0] * (4 - len(cws))))
     rc = lib.host_ntt(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(log_n), ctypes.c_uint32(batch),
                       ctypes.c_uint64(stride), ctypes.c_int(direction), ctypes.c_int(coset), ctypes.c_uint32(len(lens)),
-                      L, W, ctypes.c_uint32(nthreads))
+                      L, W, ctypes.c_uint32(nthreads), ctypes.c_int(use_tables))
     assert rc == 0
     return buf
 
@@ -54,6 +54,8 @@ def test_pass_decomposition_matches_oracle(hostlib, log_n, lens, cws, direction,
     vals = [rng.below(O.R_MOD, 253) for _ in range(stride * (batch - 1) + n)]
     data = H.ints_to_limbs(vals, 4)
     got = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=5)
+    got2 = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=7, use_tables=0)
+    assert np.array_equal(got, got2)          # per-pass twiddle tables == two-level powers
     want = data.copy()
     for b in range(batch):
         want[b * stride:b * stride + n] = C.ntt(data[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
