@@ -42,6 +42,11 @@ def parse_args():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/r01_ncu_full_selected_metrics.txt), valid for the default workload only (2^24, c = 20 / 8+8+8 passes)
+NCU_TRAFFIC_BYTES = {"msm_accumulate_kernel@2^24": 42.036437e9 + 1.545928e9, "ntt_pass_kernel@2^24": 3 * (0.537079e9 + 0.476968e9)}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -316,7 +321,10 @@ def run_b200(args):
     acc_ms = stage.get("msm_accumulate", 0.0) / K
     alg_bytes = (104 + 32) * n                                   # (104 + 32) B per point
     roofline = {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
-                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC_BYTES["msm_accumulate_kernel@2^24"] if args.log_n == 24 else None,
+                "traffic_note": "bytes per launch, ncu capture profiles/r01_ncu_full_selected_metrics.txt; the bucket method "
+                                "re-reads every 96 B packed point once per window, so traffic >> the (104+32) B/point figure",
                 "avg_launch_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes}
     roofline["frac"] = roofline["achieved"] / hbm_peak if roofline["achieved"] else None
     # integer-multiply pipe: Fq modmuls the accumulate kernel must execute vs the modmul rate of a pure fp_mul loop
@@ -334,7 +342,8 @@ def run_b200(args):
     roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"] if roofline_int["achieved"] else None
     ntt_pass_ms = sum(v for k_, v in stage.items() if k_.startswith("ntt_pass")) / K
     ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,
-                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC_BYTES["ntt_pass_kernel@2^24"] if args.log_n == 24 else None,
                 "algorithmic_bytes_per_transform": 64 * n, "passes": len([k_ for k_ in stage if k_.startswith("ntt_pass")])}
     ntt_roof["frac"] = ntt_roof["achieved"] / hbm_peak if ntt_roof["achieved"] else None
 
@@ -356,6 +365,30 @@ def run_b200(args):
         ntt_cpu = {"value": (1 << nl) / tn / 1e9, "unit": "Gelem/s", "cores": cores, "kind": "port",
                    "sample": f"first 2^{nl} elements as one polynomial, {tn:.2f} s; in-order radix-2 FFT with root table, OpenMP"}
 
+    # ---- config 4 shape: the small MSMs of 256 transactions' verification, batched into one call (rank 0, N = 1) -----
+    batch_verify = None
+    if world == 1:
+        n_tx, per = 256, 40
+        hb = bases[: n_tx * per * 104].cpu().numpy()
+        hs = scalars[: n_tx * per].cpu().numpy().view(np.uint64)
+        off = np.arange(n_tx + 1, dtype=np.uint64) * per
+        S.msm_batch(hb, hs, off)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            S.msm_batch(hb, hs, off)
+        t_gpu = (time.perf_counter() - t0) / reps
+        batch_verify = {"workload": f"{n_tx} independent MSMs x {per} points (KZG10::batch_check linear combinations of a block)",
+                        "e2e_ms": t_gpu * 1e3, "msms_per_s": n_tx / t_gpu, "api": "snarkos_b200.msm_batch -> b200_msm_batch_g1_bls12_377 (host buffers)"}
+        if not args.no_cpu_baseline:
+            from oracle import c_oracle as C
+            t0 = time.perf_counter()
+            for m in range(n_tx):
+                C.msm(hb[m * per * 104:(m + 1) * per * 104], hs[m * per:(m + 1) * per])
+            t_cpu = time.perf_counter() - t0
+            batch_verify["cpu_port_ms"] = t_cpu * 1e3
+            batch_verify["cpu_port_note"] = "the same 256 MSMs through the C oracle one after another (each parallel over its windows)"
+
     line = {
         "metric": METRIC, "value": world * n * K / (msm_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,6 +405,8 @@ def run_b200(args):
         "ntt": {"value": world * n * K / (ntt_ms * 1e-3) / 1e9, "unit": "Gelem/s", "ms": ntt_ms / K, "roofline": ntt_roof,
                 "e2e": ntt_e2e, "cpu_baseline": ntt_cpu},
     }
+    if batch_verify is not None:
+        line["batch_verify_msm"] = batch_verify
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:

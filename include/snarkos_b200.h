@@ -72,6 +72,17 @@ b200_error_t b200_msm_g1_bls12_377(void* out_jacobian_144B, const void* points, 
 b200_error_t b200_msm_g1_bls12_377_device(void* d_out_jacobian_144B, const void* d_points, size_t npoints,
                                           const void* d_scalars, size_t affine_stride, void* stream);
 
+/* Batched small MSMs: nmsm independent sums over consecutive ranges of one (points, scalars)
+ * pair, MSM m covering points [offsets[m], offsets[m + 1]) (offsets[0] = 0, non-decreasing, nmsm + 1 entries).  One
+ * launch set for all of them: the batch verifier's per-transaction linear combinations (KZG10::batch_check
+ * [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs]) aggregated across a block instead of hundreds of launch-bound
+ * calls.  out receives nmsm Jacobian points (144 B each); an empty range yields infinity. */
+b200_error_t b200_msm_batch_g1_bls12_377(void* out_jacobian, const void* points, const void* scalars,
+                                         const uint64_t* offsets, size_t nmsm, size_t affine_stride);
+b200_error_t b200_msm_batch_g1_bls12_377_device(void* d_out_jacobian, const void* d_points, const void* d_scalars,
+                                                const void* d_offsets_u64, size_t nmsm, size_t npoints,
+                                                size_t affine_stride, void* stream);
+
 /* Resident bases (the SRS `powers_of_beta_g` is fixed for the process lifetime -- KZG10::commit
  * [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs] calls msm on a prefix of it every time). */
 b200_error_t b200_msm_register_bases(const void* points, size_t npoints, size_t affine_stride,
@@ -110,6 +121,18 @@ b200_error_t b200_ntt_fr_bls12_377(void* inout_32B_mont, uint32_t log_n, size_t 
                                    size_t batch_stride_elems, int direction, int coset);
 b200_error_t b200_ntt_fr_bls12_377_device(void* d_inout, uint32_t log_n, size_t batch,
                                           size_t batch_stride_elems, int direction, int coset, void* stream);
+
+/* ---- polynomial glue between (i)FFTs, device resident (Varuna prover rounds) -------------
+ * Montgomery Fr vectors.  op 0: out = a*b  1: a+b  2: a-b  3: a*b + c  4: a*b - c; b is a vector or (b_is_scalar) one
+ * broadcast element; out may alias any input.  [UPSTREAM algorithms/src/fft/evaluations.rs: Mul/Add/Sub impls] */
+b200_error_t b200_fr_vec_op_device(int op, void* d_out, const void* d_a, const void* d_b, const void* d_c, size_t n,
+                                   int b_is_scalar, void* stream);
+/* In-place batch inversion (Montgomery's trick); zero elements stay zero like snarkVM's batch_inversion
+ * [UPSTREAM fields/src/traits/field.rs]. */
+b200_error_t b200_fr_batch_inverse_device(void* d_inout, size_t n, void* stream);
+/* evals[i] /= v_H(22 * w_K^i) for i < 2^log_k: division by the vanishing polynomial of a size-2^log_h domain on the
+ * coset of a size-2^log_k domain [UPSTREAM algorithms/src/fft/domain.rs: divide_by_vanishing_poly_on_coset_in_place]. */
+b200_error_t b200_fr_divide_by_vanishing_on_coset_device(void* d_evals, uint32_t log_k, uint32_t log_h, void* stream);
 
 /* Multi-GPU four-step building block: scales a block of a distributed polynomial of total size 2^log_n.
  * kind 0: element (r, c) of the row-major [rows x cols] block times w_N^((row_base + r) * (col_base + c)) -- the

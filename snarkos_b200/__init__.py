@@ -8,5 +8,6 @@ The compute lives in snarkos_b200/libsnarkos_b200.so (CUDA, C ABI in include/sna
 """
 from ._lib import B200Error, init, kernel_launch_count, lib, profile  # noqa: F401
 from .fft import EvaluationDomain  # noqa: F401
-from .msm import ResidentBases, VariableBase, sum_projective, synthetic_bases  # noqa: F401
+from .msm import ResidentBases, VariableBase, msm_batch, sum_projective, synthetic_bases  # noqa: F401
 from .kzg10 import KZG10, Powers  # noqa: F401
+from . import dist, poly  # noqa: F401,E402

@@ -29,6 +29,8 @@ SYMBOLS = {
     "b200_abi_version": (_u32, []),
     "b200_msm_g1_bls12_377": (b200_error_t, [_vp, _vp, _sz, _vp, _sz]),
     "b200_msm_g1_bls12_377_device": (b200_error_t, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200_msm_batch_g1_bls12_377": (b200_error_t, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "b200_msm_batch_g1_bls12_377_device": (b200_error_t, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "b200_msm_register_bases": (b200_error_t, [_vp, _sz, _sz, ctypes.POINTER(_u64)]),
     "b200_msm_register_bases_device": (b200_error_t, [_vp, _sz, _sz, _vp, ctypes.POINTER(_u64)]),
     "b200_msm_registered": (b200_error_t, [_vp, _u64, _vp, _sz]),
@@ -40,6 +42,9 @@ SYMBOLS = {
     "b200_g1_sum_jacobian_device": (b200_error_t, [_vp, _vp, _sz, _vp]),
     "b200_ntt_fr_bls12_377": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i]),
     "b200_ntt_fr_bls12_377_device": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i, _vp]),
+    "b200_fr_vec_op_device": (b200_error_t, [_i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "b200_fr_batch_inverse_device": (b200_error_t, [_vp, _sz, _vp]),
+    "b200_fr_divide_by_vanishing_on_coset_device": (b200_error_t, [_vp, _u32, _u32, _vp]),
     "b200_fr_mul_powers_device": (b200_error_t, [_vp, _u32, _i, _i, _u64, _u64, _u64, _u64, _vp]),
     "b200_g1_synthetic_bases_device": (b200_error_t, [_vp, _sz, _sz, _u64, _vp]),
     "b200_debug_field_op": (b200_error_t, [_i, _vp, _vp, _vp, _sz]),

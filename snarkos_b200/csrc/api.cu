@@ -252,6 +252,48 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched small MSMs: the verifier's per-transaction linear combinations of a whole block,
+// aggregated into one launch set instead of 256 launch-bound calls
+// ---------------------------------------------------------------------------------------------
+extern "C" b200_error_t b200_msm_batch_g1_bls12_377_device(void* d_out, const void* d_points, const void* d_scalars,
+                                                           const void* d_offsets_u64, size_t nmsm, size_t npoints,
+                                                           size_t stride, void* stream) {
+    B200_TRY(b200_require_device());
+    if (nmsm == 0) return b200_ok();
+    if (nmsm > (1u << 20)) return b200_err(B200_ERR_TOO_LARGE, "msm_batch: more than 2^20 MSMs per call");
+    if (!d_offsets_u64) return b200_err(B200_ERR_INVALID_ARG, "msm_batch: null offsets");
+    return msm_run_batch_device(d_out, d_points, npoints, d_scalars, stride, nullptr,
+                                reinterpret_cast<const unsigned long long*>(d_offsets_u64), (uint32_t)nmsm, (cudaStream_t)stream);
+}
+
+extern "C" b200_error_t b200_msm_batch_g1_bls12_377(void* out, const void* points, const void* scalars,
+                                                    const uint64_t* offsets, size_t nmsm, size_t stride) {
+    B200_TRY(b200_require_device());
+    if (nmsm == 0) return b200_ok();
+    if (!out || !offsets) return b200_err(B200_ERR_INVALID_ARG, "msm_batch: null pointer");
+    for (size_t m = 0; m < nmsm; m++)
+        if (offsets[m] > offsets[m + 1]) return b200_err(B200_ERR_INVALID_ARG, "msm_batch: offsets must be non-decreasing");
+    if (offsets[0] != 0) return b200_err(B200_ERR_INVALID_ARG, "msm_batch: offsets[0] must be 0");
+    const size_t n = (size_t)offsets[nmsm];
+    if (n && (!points || !scalars)) return b200_err(B200_ERR_INVALID_ARG, "msm_batch: null input pointer");
+    cudaStream_t s = b200_thread_stream();
+    DevBuf d_pts, d_sc, d_off, d_out;
+    CUDA_TRY(d_pts.alloc(n * stride, s));
+    CUDA_TRY(d_sc.alloc(n * 32, s));
+    CUDA_TRY(d_off.alloc((nmsm + 1) * 8, s));
+    CUDA_TRY(d_out.alloc(nmsm * 144, s));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_off.p, offsets, (nmsm + 1) * 8, cudaMemcpyHostToDevice, s));
+    B200_TRY(b200_msm_batch_g1_bls12_377_device(d_out.p, d_pts.p, d_sc.p, d_off.p, nmsm, n, stride, s));
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, nmsm * 144, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
 extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, size_t n, size_t stride,
                                                        void* stream, uint64_t* out_handle) {
     B200_TRY(b200_require_device());

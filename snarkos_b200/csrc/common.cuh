@@ -63,6 +63,9 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
                             int coset, cudaStream_t stream);
 b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                             const void* d_packed /* non-null: pre-packed 96 B bases */, cudaStream_t stream);
+b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
+                                  const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
+                                  cudaStream_t stream);
 b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t n, size_t stride,
                                    cudaStream_t stream);
 void ntt_release_tables();

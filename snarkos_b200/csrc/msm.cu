@@ -74,10 +74,24 @@ __device__ __forceinline__ uint32_t warp_aggregated_inc(uint32_t* counters, size
     return pos;
 }
 
+// Batched calls (many independent small MSMs in one launch set, e.g. the verifier's linear combinations of a whole
+// block of transactions): point i belongs to MSM m with seg_off[m] <= i < seg_off[m + 1]; its buckets live in the
+// "virtual windows" m * nwin + w, so everything after the digit kernels is unchanged.
+__device__ __forceinline__ uint32_t msm_segment_of(const unsigned long long* seg_off, uint32_t nmsm, size_t i) {
+    if (!seg_off) return 0;
+    uint32_t lo = 0, hi = nmsm;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __restrict__ scalars, size_t n,
-                                 MsmShape sh) {
+                                 MsmShape sh, const unsigned long long* __restrict__ seg_off, uint32_t nmsm) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
+    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, i) * sh.nwin : 0;
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (valid) {
         uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
@@ -87,7 +101,7 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t neg;
         uint32_t d = msm_signed_digit(s, w, sh.c, carry, neg);
-        warp_aggregated_inc(counts, (size_t)w * sh.nbuckets + (d ? d - 1 : 0), valid && d != 0);
+        warp_aggregated_inc(counts, (vbase + w) * sh.nbuckets + (d ? d - 1 : 0), valid && d != 0);
     }
 }
 
@@ -96,10 +110,12 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
 // merge there instead of each dirtying a 32-byte HBM sector (measured 8.9 -> 3.7 ms at 2^24, c = 20).  Every
 // thread re-derives the carry chain of the lower windows (a few shifts per window).
 __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __restrict__ cursor,
-                                   const uint4* __restrict__ scalars, size_t n, MsmShape sh) {
+                                   const uint4* __restrict__ scalars, size_t n, MsmShape sh,
+                                   const unsigned long long* __restrict__ seg_off, uint32_t nmsm) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t w = blockIdx.y;
+    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, i) * sh.nwin : 0;
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (valid) {
         uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
@@ -108,7 +124,7 @@ __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __r
     uint32_t carry = 0, neg = 0, d = 0;
     for (uint32_t ww = 0; ww <= w; ww++) d = msm_signed_digit(s, ww, sh.c, carry, neg);
     const bool active = valid && d != 0;
-    uint32_t pos = warp_aggregated_inc(cursor, (size_t)w * sh.nbuckets + (d ? d - 1 : 0), active);
+    uint32_t pos = warp_aggregated_inc(cursor, (vbase + w) * sh.nbuckets + (d ? d - 1 : 0), active);
     if (active) entries[pos] = (uint32_t)i | (neg << 31);
 }
 
@@ -361,15 +377,18 @@ __device__ __forceinline__ void store_jacobian(uint4* out, const g1_xyzz_t& p) {
     fq_to_u4x3(Z, out + 6);
 }
 
-__global__ void msm_fold_kernel(uint4* __restrict__ out_jac, const g1_xyzz_mem_t* __restrict__ wsum, MsmShape sh) {
-    if (blockIdx.x || threadIdx.x) return;
-    g1_xyzz_t total = msm_fold_windows(wsum, sh.nwin, sh.c);
-    store_jacobian(out_jac, total);
+__global__ void __launch_bounds__(32) msm_fold_kernel(uint4* __restrict__ out_jac, const g1_xyzz_mem_t* __restrict__ wsum,
+                                                      MsmShape sh, uint32_t nmsm) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmsm) return;
+    g1_xyzz_t total = msm_fold_windows(wsum + (size_t)m * sh.nwin, sh.nwin, sh.c);
+    store_jacobian(out_jac + 9 * (size_t)m, total);
 }
 
-__global__ void msm_write_infinity_kernel(uint4* out_jac) {
-    if (blockIdx.x || threadIdx.x) return;
-    store_jacobian(out_jac, g1_xyzz_infinity());
+__global__ void msm_write_infinity_kernel(uint4* out_jac, uint32_t count) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= count) return;
+    store_jacobian(out_jac + 9 * (size_t)m, g1_xyzz_infinity());
 }
 
 // sum of `count` Jacobian points (multi-GPU partial sums)
@@ -433,9 +452,18 @@ static b200_error_t exclusive_scan(uint32_t* d_out, const uint32_t* d_in, size_t
 
 b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                             const void* d_packed, cudaStream_t stream) {
+    return msm_run_batch_device(d_out, d_points, n, d_scalars, stride, d_packed, nullptr, 1, stream);
+}
+
+// nmsm independent MSMs over consecutive point ranges [seg_off[m], seg_off[m + 1]) of one (points, scalars) pair;
+// d_out receives nmsm Jacobian points.  d_seg_off == nullptr means a single MSM over everything.
+b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
+                                  const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
+                                  cudaStream_t stream) {
     if (!d_out) return b200_err(B200_ERR_INVALID_ARG, "msm: null output pointer");
+    if (nmsm == 0) return b200_ok();
     if (n == 0) {
-        msm_write_infinity_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<uint4*>(d_out));
+        msm_write_infinity_kernel<<<(nmsm + 63) / 64, 64, 0, stream>>>(reinterpret_cast<uint4*>(d_out), nmsm);
         KERNEL_CHECK();
         return b200_ok();
     }
@@ -443,8 +471,13 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     if (n >= ((size_t)1 << 28)) return b200_err(B200_ERR_TOO_LARGE, "msm: more than 2^28 - 1 points per call");
     if (reinterpret_cast<uintptr_t>(d_scalars) & 15) return b200_err(B200_ERR_INVALID_ARG, "msm: scalars must be 16-byte aligned on the device");
 
-    const MsmShape sh = msm_shape(b200_msm_window_bits(n));
-    const size_t K = (size_t)sh.nwin * sh.nbuckets;
+    // window width from the mean MSM size; `vsh` is the shape seen by the kernels after the digit stage, whose
+    // "windows" are the nmsm * nwin virtual windows
+    const MsmShape sh = msm_shape(b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
+    MsmShape vsh = sh;
+    vsh.nwin = sh.nwin * nmsm;
+    const size_t K = (size_t)vsh.nwin * sh.nbuckets;
+    if (K >= ((size_t)1 << 31)) return b200_err(B200_ERR_TOO_LARGE, "msm: too many buckets (batch too large)");
     if ((size_t)n * sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
 
     DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum, heads, tails, head_bucket, tail_bucket, max_heads;
@@ -466,20 +499,20 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     while (seg_len < 64 && K / seg_len > 65536) seg_len <<= 1;
     if (seg_len > sh.nbuckets) seg_len = sh.nbuckets;
     const uint32_t segs_per_win = (sh.nbuckets + seg_len - 1) / seg_len;
-    CUDA_TRY(segs.alloc((size_t)segs_per_win * sh.nwin * sizeof(g1_xyzz_mem_t), stream));
-    CUDA_TRY(wsum.alloc((size_t)sh.nwin * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(segs.alloc((size_t)segs_per_win * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(wsum.alloc((size_t)vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
 
     STAGE("msm_count", stream);
     CUDA_TRY(cudaMemsetAsync(counts.p, 0, (K + 1) * 4, stream));
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh);
+    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm);
     KERNEL_CHECK();
     STAGE("msm_scan", stream);
     B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
     CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
     STAGE("msm_scatter", stream);
     msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
-                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh);
+                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm);
     KERNEL_CHECK();
     // ---- equal-work accumulation ----
     STAGE("msm_accumulate", stream);
@@ -513,16 +546,16 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
                                                                      tails.as<g1_xyzz_mem_t>(), tail_bucket.as<uint32_t>(), (uint32_t)t_max);
     KERNEL_CHECK();
     STAGE("msm_reduce_segments", stream);
-    const uint32_t nseg_threads = segs_per_win * sh.nwin;
+    const uint32_t nseg_threads = segs_per_win * vsh.nwin;
     msm_reduce_segments_kernel<<<(nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
-        segs.as<g1_xyzz_mem_t>(), buckets.as<g1_xyzz_mem_t>(), sh, seg_len, segs_per_win);
+        segs.as<g1_xyzz_mem_t>(), buckets.as<g1_xyzz_mem_t>(), vsh, seg_len, segs_per_win);
     KERNEL_CHECK();
     STAGE("msm_window_sum", stream);
-    msm_window_sum_kernel<<<sh.nwin, MSM_TREE_THREADS, 0, stream>>>(wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(),
+    msm_window_sum_kernel<<<vsh.nwin, MSM_TREE_THREADS, 0, stream>>>(wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(),
                                                                    segs_per_win);
     KERNEL_CHECK();
     STAGE("msm_fold", stream);
-    msm_fold_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(), sh);
+    msm_fold_kernel<<<(nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(), sh, nmsm);
     KERNEL_CHECK();
     STAGE_END(stream);
     return b200_ok();

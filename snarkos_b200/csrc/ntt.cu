@@ -12,7 +12,7 @@
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ntt_pass_kernel(const NttPassParams p) {
+__global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const NttPassParams p) {
     extern __shared__ uint4 sm[];
     const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     ntt_phase_load(p, sm, tile, batch, tid, nt);
@@ -22,7 +22,12 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const NttPassParams p) {
         __syncthreads();
     }
     const uint32_t L = p.log_len[p.pass];
-    for (uint32_t s = 0; s < L; s++) {
+    uint32_t s = 0;
+    for (; p.radix4 && s + 1 < L; s += 2) {           // stage pairs on register-resident quads
+        ntt_phase_stage2(p, sm, s, tid, nt);
+        __syncthreads();
+    }
+    for (; s < L; s++) {                              // odd length (or radix-2 only): single stages
         ntt_phase_stage(p, sm, s, tid, nt);
         __syncthreads();
     }
@@ -272,6 +277,7 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         p.coset_pre = (first && coset && direction == 0) ? 1 : 0;
         p.scale_post = (last && direction == 1) ? 1 : 0;
         p.coset_post = (last && coset && direction == 1) ? 1 : 0;
+        p.radix4 = getenv("B200_NTT_RADIX2") ? 0 : 1;
         const uint32_t tile_log = plan.log_len[i] + plan.log_cw[i];
         const uint32_t tile_elems = 1u << tile_log;
         uint32_t threads = tile_elems / 2;

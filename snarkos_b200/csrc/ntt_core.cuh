@@ -46,6 +46,7 @@ struct NttPassParams {
     uint32_t coset_pre;             // multiply input j by g^j     (forward coset, first pass)
     uint32_t scale_post;            // multiply output by n^-1     (inverse, last pass)
     uint32_t coset_post;            // multiply output j by g^-j   (inverse coset, last pass)
+    uint32_t radix4;                // 1: process stage pairs on register quads (default), 0: radix-2 stages only
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -190,6 +191,55 @@ B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, uint32_t s, uint
         if (tw) dif = fp_mul(dif, fr_load(p.tile_tw, tw));
         tile_store(sm, g.tile_elems, e0, sum);
         tile_store(sm, g.tile_elems, e1, dif);
+    }
+}
+
+// Two consecutive DIF stages (s, s + 1) on register-resident quads: half the shared-memory traffic, half the
+// barriers and half the index arithmetic of two radix-2 stages; same number of products.  With d1 = L >> (s + 1),
+// d2 = d1 / 2, a quad is {p, p + d2, p + d1, p + d1 + d2} with p = b * 2 * d1 + j (j < d2):
+//   stage s    : (x0, x2) twiddle w_L^(j << s)          (x1, x3) twiddle w_L^((j + d2) << s)
+//   stage s + 1: (x0', x1') and (x2', x3'), both twiddle w_L^(j << (s + 1))
+// For the short-distance quads (d2 <= 4) lanes are ordered j-major so that the j == 0 quads, whose two twiddles are 1,
+// fill whole warps and really skip their products.
+B200_HD void ntt_phase_stage2(const NttPassParams& p, uint4* sm, uint32_t s, uint32_t tid, uint32_t nthreads) {
+    NttGeom g = ntt_geom(p);
+    const uint32_t log_d1 = g.log_len - 1 - s, log_d2 = log_d1 - 1;
+    const uint32_t nquads = g.tile_elems >> 2;
+    const bool j_major = log_d2 <= 2;
+    const uint32_t log_blocks = g.log_len - 1 - log_d1;      // blocks of 2 * d1 points
+    const uint32_t tw_shift = NTT_TILE_TW_LOG - g.log_len;
+    for (uint32_t u = tid; u < nquads; u += nthreads) {
+        const uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
+        uint32_t j, b;
+        if (j_major) { b = q & ((1u << log_blocks) - 1); j = q >> log_blocks; }
+        else         { j = q & ((1u << log_d2) - 1); b = q >> log_d2; }
+        const uint32_t t0 = (b << (log_d1 + 1)) | j;
+        const uint32_t e0 = (t0 << g.log_cw) + cw;
+        const uint32_t o2 = 1u << (log_d2 + g.log_cw), o1 = o2 << 1;
+        fr_t x0 = tile_load(sm, g.tile_elems, e0);
+        fr_t x1 = tile_load(sm, g.tile_elems, e0 + o2);
+        fr_t x2 = tile_load(sm, g.tile_elems, e0 + o1);
+        fr_t x3 = tile_load(sm, g.tile_elems, e0 + o1 + o2);
+        // stage s
+        fr_t a0 = fp_add(x0, x2), a2 = fp_sub(x0, x2);
+        fr_t a1 = fp_add(x1, x3), a3 = fp_sub(x1, x3);
+        const uint32_t twa = (j << s) << tw_shift;
+        const uint32_t twb = ((j + (1u << log_d2)) << s) << tw_shift;      // never 0
+        if (twa) a2 = fp_mul(a2, fr_load(p.tile_tw, twa));
+        a3 = fp_mul(a3, fr_load(p.tile_tw, twb));
+        // stage s + 1
+        const uint32_t tw2 = (j << (s + 1)) << tw_shift;
+        fr_t y0 = fp_add(a0, a1), y1 = fp_sub(a0, a1);
+        fr_t y2 = fp_add(a2, a3), y3 = fp_sub(a2, a3);
+        if (tw2) {
+            fr_t w2 = fr_load(p.tile_tw, tw2);
+            y1 = fp_mul(y1, w2);
+            y3 = fp_mul(y3, w2);
+        }
+        tile_store(sm, g.tile_elems, e0, y0);
+        tile_store(sm, g.tile_elems, e0 + o2, y1);
+        tile_store(sm, g.tile_elems, e0 + o1, y2);
+        tile_store(sm, g.tile_elems, e0 + o1 + o2, y3);
     }
 }
 

@@ -75,6 +75,21 @@ class VariableBase:
         return out
 
 
+def msm_batch(bases, scalars, offsets, stride: int = AFFINE_STRIDE) -> np.ndarray:
+    """Many independent small MSMs in one call: MSM m sums points [offsets[m], offsets[m + 1]).  Host buffers in,
+    numpy uint8 [nmsm, 144] out.  This is the aggregation a batch verifier needs: the per-transaction linear
+    combinations of a block's transactions (`KZG10::batch_check`) as ONE launch set."""
+    b = _host_bytes(bases)
+    s = _host_bytes(scalars)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    nmsm = off.size - 1
+    if nmsm < 0 or (nmsm >= 0 and int(off[-1]) * stride > b.size) or int(off[-1]) * SCALAR_BYTES > s.size:
+        raise ValueError("offsets do not fit the point / scalar buffers")
+    out = np.zeros((max(nmsm, 0), PROJECTIVE_BYTES), dtype=np.uint8)
+    _lib.check(_lib.lib().b200_msm_batch_g1_bls12_377(_np_ptr(out), _np_ptr(b), _np_ptr(s), _np_ptr(off), nmsm, stride))
+    return out
+
+
 class ResidentBases:
     """Device-resident base set (e.g. the SRS powers_of_beta_g that KZG10::commit multiplies against on every
     call [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs; SURVEY.md 8f rank 1])."""

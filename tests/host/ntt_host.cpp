@@ -101,6 +101,7 @@ extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t
         p.coset_pre = (first && coset && direction == 0);
         p.scale_post = (last && direction == 1);
         p.coset_post = (last && coset && direction == 1);
+        p.radix4 = use_tables ? 1 : 0;           // the table-less run also exercises the radix-2-only path
         uint32_t tile_log = plan.log_len[i] + plan.log_cw[i];
         uint32_t tile_elems = 1u << tile_log;
         uint32_t ntiles = 1u << (log_n - tile_log);
@@ -113,7 +114,10 @@ extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);
                 if (p.coset_pre)
                     for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, nthreads);
-                for (uint32_t s = 0; s < plan.log_len[i]; s++)
+                uint32_t s = 0;
+                for (; p.radix4 && s + 1 < plan.log_len[i]; s += 2)
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage2(p, sm.data(), s, tid, nthreads);
+                for (; s < plan.log_len[i]; s++)
                     for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage(p, sm.data(), s, tid, nthreads);
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_store(p, sm.data(), tile, b, tid, nthreads);
             }

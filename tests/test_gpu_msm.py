@@ -170,3 +170,33 @@ def test_kzg_commit_resident_powers():
     with pytest.raises(S.B200Error):
         S.KZG10.commit(powers, H.random_fr_mont_np(rng, (n + 1,)))
     powers.release()
+
+
+def test_batched_small_msms():
+    """config 4 shape: many independent small MSMs (tens of points each) in one call == each one on its own"""
+    import snarkos_b200 as S
+    rng = O.SplitMix64(77)
+    sizes = [0, 1, 7, 33, 64, 2, 0, 51, 100, 18] * 3
+    pts, sc, off = [], [], [0]
+    for k in sizes:
+        pts += O.random_points(rng, k) if k else []
+        sc += O.random_fr(rng, k)
+        off.append(off[-1] + k)
+    if len(pts) > 5:
+        pts[3] = None
+        sc[4] = 0
+    bases, scal = H.bases_array(pts), H.scalars_array(sc)
+    out = S.msm_batch(bases, scal, off)
+    assert out.shape == (len(sizes), 144)
+    for m, k in enumerate(sizes):
+        lo, hi = off[m], off[m + 1]
+        assert H.jac_bytes_to_affine(out[m]) == O.msm_naive(pts[lo:hi], sc[lo:hi]), m
+    # 256 transactions x 40 points against per-call results
+    n_tx, per = 256, 40
+    dev = _synthetic(n_tx * per, 55).cpu().numpy()
+    sc2 = H.random_scalars_np(np.random.default_rng(8), n_tx * per)
+    off2 = np.arange(n_tx + 1, dtype=np.uint64) * per
+    out2 = S.msm_batch(dev, sc2, off2)
+    for m in (0, 1, 100, 255):
+        want = oracle_msm(dev[m * per * 104:(m + 1) * per * 104], sc2[m * per:(m + 1) * per])
+        assert H.jac_bytes_to_affine(out2[m]) == want
