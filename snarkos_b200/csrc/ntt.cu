@@ -15,20 +15,23 @@
 __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const NttPassParams p) {
     extern __shared__ uint4 sm[];
     const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t L = p.log_len[p.pass];
+    uint4* sm_tw = sm + 2 * ((size_t)1 << (L + p.log_cw));         // after the two tile planes: the pass's L/2 twiddles
+    ntt_phase_stage_twiddles(p, sm_tw, tid, nt);
+    const NttTwiddles twd = ntt_shared_twiddles(sm_tw, L);
     ntt_phase_load(p, sm, tile, batch, tid, nt);
     __syncthreads();
     if (p.coset_pre) {
         ntt_phase_coset_pre(p, sm, tile, tid, nt);
         __syncthreads();
     }
-    const uint32_t L = p.log_len[p.pass];
     uint32_t s = 0;
     for (; p.radix4 && s + 1 < L; s += 2) {           // stage pairs on register-resident quads
-        ntt_phase_stage2(p, sm, s, tid, nt);
+        ntt_phase_stage2(p, sm, twd, s, tid, nt);
         __syncthreads();
     }
     for (; s < L; s++) {                              // odd length (or radix-2 only): single stages
-        ntt_phase_stage(p, sm, s, tid, nt);
+        ntt_phase_stage(p, sm, twd, s, tid, nt);
         __syncthreads();
     }
     ntt_phase_store(p, sm, tile, batch, tid, nt);
@@ -134,7 +137,7 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
     std::lock_guard<std::mutex> lock(g_ntt.mu);
     if (!g_ntt.smem_attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (1 << NTT_MAX_TILE_LOG) * 32));
+                                      (1 << NTT_MAX_TILE_LOG) * 32 + (1 << (NTT_MAX_TILE_LOG - 1)) * 32));
         g_ntt.smem_attr_set = true;
     }
     const uint32_t* root = direction ? FR_TWO_ADIC_ROOT_INV : FR_TWO_ADIC_ROOT;
@@ -286,7 +289,8 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         static const char* const kPassName[NTT_MAX_PASSES] = {"ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"};
         STAGE(kPassName[i], stream);
         dim3 grid(1u << (log_n - tile_log), (unsigned)batch);
-        ntt_pass_kernel<<<grid, threads, (size_t)tile_elems * 32, stream>>>(p);
+        const size_t smem = (size_t)tile_elems * 32 + ((size_t)1 << plan.log_len[i]) * 16;   // tile + L/2 twiddles
+        ntt_pass_kernel<<<grid, threads, smem, stream>>>(p);
         KERNEL_CHECK();
     }
     STAGE_END(stream);

@@ -166,7 +166,48 @@ B200_HD void ntt_phase_coset_pre(const NttPassParams& p, uint4* sm, uint32_t til
 // phase 2 (x log_len): one DIF stage on the tile.  Stage s pairs t and t + d, d = L >> (s + 1):
 //     a' = a + b,  b' = (a - b) * w_L^((t mod d) << s)
 // ---------------------------------------------------------------------------------------------
-B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, uint32_t s, uint32_t tid, uint32_t nthreads) {
+// Twiddle source of the in-tile stages: w_L^e at lo[e << shift], hi[e << shift] (two planes of 16-byte words).
+// The kernel stages the L/2 twiddles of its pass in shared memory (shift 0); the host shim reads the global
+// w_{2^12} table directly (lo = table, hi = table + 1, stride folded into the shift by the accessor below).
+struct NttTwiddles {
+    const uint4* lo;
+    const uint4* hi;
+    uint32_t shift;      // index = e << shift
+    uint32_t stride;     // distance between consecutive table entries in uint4 units (1: planar, 2: interleaved)
+};
+B200_HD fr_t ntt_twiddle(const NttTwiddles& t, uint32_t e) {
+    const uint32_t i = (e << t.shift) * t.stride;
+    return fr_from_u4(t.lo[i], t.hi[i]);
+}
+B200_HD NttTwiddles ntt_global_twiddles(const NttPassParams& p, uint32_t log_len) {
+    NttTwiddles t;
+    t.lo = p.tile_tw;
+    t.hi = p.tile_tw + 1;
+    t.shift = NTT_TILE_TW_LOG - log_len;
+    t.stride = 2;
+    return t;
+}
+// phase 0 (device): copy the L/2 twiddles of this pass into shared memory, planar
+B200_HD void ntt_phase_stage_twiddles(const NttPassParams& p, uint4* sm_tw, uint32_t tid, uint32_t nthreads) {
+    const uint32_t log_len = p.log_len[p.pass];
+    const uint32_t half = log_len ? (1u << (log_len - 1)) : 0;
+    const uint32_t shift = NTT_TILE_TW_LOG - log_len;
+    for (uint32_t u = tid; u < 2 * half; u += nthreads) {
+        const uint32_t e = u >> 1, h = u & 1;
+        sm_tw[h * half + e] = p.tile_tw[2 * ((unsigned long long)e << shift) + h];
+    }
+}
+B200_HD NttTwiddles ntt_shared_twiddles(const uint4* sm_tw, uint32_t log_len) {
+    NttTwiddles t;
+    t.lo = sm_tw;
+    t.hi = sm_tw + (log_len ? (1u << (log_len - 1)) : 0);
+    t.shift = 0;
+    t.stride = 1;
+    return t;
+}
+
+B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, const NttTwiddles& twd, uint32_t s, uint32_t tid,
+                             uint32_t nthreads) {
     NttGeom g = ntt_geom(p);
     uint32_t log_d = g.log_len - 1 - s;
     uint32_t nbf = g.tile_elems >> 1;                   // butterflies in the tile
@@ -187,8 +228,8 @@ B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, uint32_t s, uint
         fr_t bb = tile_load(sm, g.tile_elems, e1);
         fr_t sum = fp_add(a, bb);
         fr_t dif = fp_sub(a, bb);
-        uint32_t tw = (j << s) << (NTT_TILE_TW_LOG - g.log_len);     // exponent of w_{2^12}
-        if (tw) dif = fp_mul(dif, fr_load(p.tile_tw, tw));
+        uint32_t tw = j << s;                                        // exponent of w_L
+        if (tw) dif = fp_mul(dif, ntt_twiddle(twd, tw));
         tile_store(sm, g.tile_elems, e0, sum);
         tile_store(sm, g.tile_elems, e1, dif);
     }
@@ -201,13 +242,13 @@ B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, uint32_t s, uint
 //   stage s + 1: (x0', x1') and (x2', x3'), both twiddle w_L^(j << (s + 1))
 // For the short-distance quads (d2 <= 4) lanes are ordered j-major so that the j == 0 quads, whose two twiddles are 1,
 // fill whole warps and really skip their products.
-B200_HD void ntt_phase_stage2(const NttPassParams& p, uint4* sm, uint32_t s, uint32_t tid, uint32_t nthreads) {
+B200_HD void ntt_phase_stage2(const NttPassParams& p, uint4* sm, const NttTwiddles& twd, uint32_t s, uint32_t tid,
+                              uint32_t nthreads) {
     NttGeom g = ntt_geom(p);
     const uint32_t log_d1 = g.log_len - 1 - s, log_d2 = log_d1 - 1;
     const uint32_t nquads = g.tile_elems >> 2;
     const bool j_major = log_d2 <= 2;
     const uint32_t log_blocks = g.log_len - 1 - log_d1;      // blocks of 2 * d1 points
-    const uint32_t tw_shift = NTT_TILE_TW_LOG - g.log_len;
     for (uint32_t u = tid; u < nquads; u += nthreads) {
         const uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
         uint32_t j, b;
@@ -223,16 +264,16 @@ B200_HD void ntt_phase_stage2(const NttPassParams& p, uint4* sm, uint32_t s, uin
         // stage s
         fr_t a0 = fp_add(x0, x2), a2 = fp_sub(x0, x2);
         fr_t a1 = fp_add(x1, x3), a3 = fp_sub(x1, x3);
-        const uint32_t twa = (j << s) << tw_shift;
-        const uint32_t twb = ((j + (1u << log_d2)) << s) << tw_shift;      // never 0
-        if (twa) a2 = fp_mul(a2, fr_load(p.tile_tw, twa));
-        a3 = fp_mul(a3, fr_load(p.tile_tw, twb));
+        const uint32_t twa = j << s;
+        const uint32_t twb = (j + (1u << log_d2)) << s;                    // never 0
+        if (twa) a2 = fp_mul(a2, ntt_twiddle(twd, twa));
+        a3 = fp_mul(a3, ntt_twiddle(twd, twb));
         // stage s + 1
-        const uint32_t tw2 = (j << (s + 1)) << tw_shift;
+        const uint32_t tw2 = j << (s + 1);
         fr_t y0 = fp_add(a0, a1), y1 = fp_sub(a0, a1);
         fr_t y2 = fp_add(a2, a3), y3 = fp_sub(a2, a3);
         if (tw2) {
-            fr_t w2 = fr_load(p.tile_tw, tw2);
+            fr_t w2 = ntt_twiddle(twd, tw2);
             y1 = fp_mul(y1, w2);
             y3 = fp_mul(y3, w2);
         }

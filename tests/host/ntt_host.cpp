@@ -114,11 +114,16 @@ extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);
                 if (p.coset_pre)
                     for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, nthreads);
+                // odd tiles read the twiddles straight from the global table, even tiles through the staged copy, so both
+                // accessors are exercised
+                std::vector<uint4> smtw((size_t)1 << plan.log_len[i]);
+                for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage_twiddles(p, smtw.data(), tid, nthreads);
+                NttTwiddles twd = (tile & 1) ? ntt_global_twiddles(p, plan.log_len[i]) : ntt_shared_twiddles(smtw.data(), plan.log_len[i]);
                 uint32_t s = 0;
                 for (; p.radix4 && s + 1 < plan.log_len[i]; s += 2)
-                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage2(p, sm.data(), s, tid, nthreads);
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage2(p, sm.data(), twd, s, tid, nthreads);
                 for (; s < plan.log_len[i]; s++)
-                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage(p, sm.data(), s, tid, nthreads);
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage(p, sm.data(), twd, s, tid, nthreads);
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_store(p, sm.data(), tile, b, tid, nthreads);
             }
     }
