@@ -279,7 +279,166 @@ template <class P> B200_HD Fp<P> fp_mul_cc(const Fp<P>& a, const Fp<P>& b) {
 // and an FP64-pipe variant does not pay either (3 FP64 ops + 4 integer adds per 52-bit product makes it
 // issue-bound), so both were dropped.
 template <class P> B200_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul_cc(a, b); }
+
+// ---------------------------------------------------------------------------------------------
+// Separated product / reduction ("SOS"): full 2N-limb products and a stand-alone Montgomery reduction.
+// MEASURED AND NOT USED ON THE HOT PATHS (kept as tested building blocks, tests/test_host_arith.py): in isolation the
+// XYZZ mixed-add loop gains 4.7 % (2.77 -> 2.90 G adds/s), but the 2N-limb temporaries push msm_accumulate_kernel from
+// 167 to 212 registers (12 -> 8 resident warps per SM) and its time is unchanged (84.0 vs 84.1 ms at 2^24); forced
+// back to 168 registers it spills and slows to 92 ms.  fp_sqr therefore stays the interleaved product.
+// Same multiplier cost as the interleaved routine for a plain product (N^2 + N(N-1) wide multiply-adds), but it
+// makes two savings possible where the multiplier pipe is the bound (the MSM):
+//   * squaring: the off-diagonal products are computed once and doubled -> N(N+1)/2 instead of N^2 products
+//     (Fq: 78 + 132 = 210 instead of 276 multiplier slots);
+//   * a*b +- c*d with ONE reduction (the Y3 = R*(Q - X3) - Y1*PPP of every point addition): 2*144 + 132 = 420
+//     instead of 552 slots.
+// The 2N-limb values are accumulated in two arrays by the parity of the position where a {lo,hi} product pair
+// starts, so that again every pair sits on an aligned register pair and every row is one IMAD.WIDE.U32.X carry
+// chain; the carry leaving a chain lands on a limb that so far holds at most another chain's carry, so one addc
+// suffices and nothing ripples.
+// ---------------------------------------------------------------------------------------------
+namespace detail {
+
+// T[0 .. 2N) = P0 + P1
+template <int N2> B200_HD void wide_merge(uint32_t* T, const uint32_t* P0, const uint32_t* P1) {
+    T[0] = ptx::add_cc(P0[0], P1[0]);
+    B200_UNROLL
+    for (int k = 1; k < N2 - 1; k++) T[k] = ptx::addc_cc(P0[k], P1[k]);
+    T[N2 - 1] = ptx::addc(P0[N2 - 1], P1[N2 - 1]);
+}
+
+}  // namespace detail
+
+template <class P> B200_HD void fp_mul_wide(uint32_t* T, const Fp<P>& a, const Fp<P>& b) {
+    constexpr int N = P::N;
+    uint32_t P0[2 * N + 2], P1[2 * N + 2];
+    B200_UNROLL
+    for (int k = 0; k < 2 * N + 2; k++) { P0[k] = 0; P1[k] = 0; }
+    B200_UNROLL
+    for (int i = 0; i < N; i++) {
+        uint32_t* E = (i & 1) ? P1 : P0;             // pairs starting at positions of the parity of i
+        uint32_t* O = (i & 1) ? P0 : P1;
+        B200_UNROLL
+        for (int j = 0; j < N; j += 2) {
+            E[i + j] = (j == 0) ? ptx::mad_lo_cc(a.v[j], b.v[i], E[i + j]) : ptx::madc_lo_cc(a.v[j], b.v[i], E[i + j]);
+            E[i + j + 1] = ptx::madc_hi_cc(a.v[j], b.v[i], E[i + j + 1]);
+        }
+        E[i + N] = ptx::addc(E[i + N], 0u);
+        B200_UNROLL
+        for (int j = 1; j < N; j += 2) {
+            O[i + j] = (j == 1) ? ptx::mad_lo_cc(a.v[j], b.v[i], O[i + j]) : ptx::madc_lo_cc(a.v[j], b.v[i], O[i + j]);
+            O[i + j + 1] = ptx::madc_hi_cc(a.v[j], b.v[i], O[i + j + 1]);
+        }
+        O[i + N + 1] = ptx::addc(O[i + N + 1], 0u);
+    }
+    detail::wide_merge<2 * N>(T, P0, P1);
+}
+
+template <class P> B200_HD void fp_sqr_wide(uint32_t* T, const Fp<P>& a) {
+    constexpr int N = P::N;
+    uint32_t P0[2 * N + 2], P1[2 * N + 2];
+    B200_UNROLL
+    for (int k = 0; k < 2 * N + 2; k++) { P0[k] = 0; P1[k] = 0; }
+    // off-diagonal products a[i] * a[j], i < j, once
+    B200_UNROLL
+    for (int i = 0; i < N - 1; i++) {
+        B200_UNROLL
+        for (int q = 0; q < 2; q++) {
+            const int j0 = i + 1 + (((i + 1) & 1) != q ? 1 : 0);      // first j > i with j % 2 == q
+            if (j0 <= N - 1) {
+                uint32_t* A = ((i + j0) & 1) ? P1 : P0;
+                int last = j0;
+                B200_UNROLL
+                for (int j = j0; j < N; j += 2) {
+                    A[i + j] = (j == j0) ? ptx::mad_lo_cc(a.v[j], a.v[i], A[i + j]) : ptx::madc_lo_cc(a.v[j], a.v[i], A[i + j]);
+                    A[i + j + 1] = ptx::madc_hi_cc(a.v[j], a.v[i], A[i + j + 1]);
+                    last = j;
+                }
+                A[i + last + 2] = ptx::addc(A[i + last + 2], 0u);
+            }
+        }
+    }
+    uint32_t S[2 * N];
+    detail::wide_merge<2 * N>(S, P0, P1);
+    // T = 2 * S + sum_i a[i]^2 * 2^(64 i)
+    B200_UNROLL
+    for (int k = 2 * N - 1; k >= 1; k--) T[k] = (S[k] << 1) | (S[k - 1] >> 31);
+    T[0] = S[0] << 1;
+    B200_UNROLL
+    for (int i = 0; i < N; i++) {
+        T[2 * i] = (i == 0) ? ptx::mad_lo_cc(a.v[i], a.v[i], T[2 * i]) : ptx::madc_lo_cc(a.v[i], a.v[i], T[2 * i]);
+        T[2 * i + 1] = ptx::madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]);
+    }
+}
+
+// T (2N limbs) += U (2N limbs); the caller guarantees no overflow (sums of a few products of reduced values)
+template <class P> B200_HD void fp_wide_add(uint32_t* T, const uint32_t* U) {
+    constexpr int N2 = 2 * P::N;
+    T[0] = ptx::add_cc(T[0], U[0]);
+    B200_UNROLL
+    for (int k = 1; k < N2 - 1; k++) T[k] = ptx::addc_cc(T[k], U[k]);
+    T[N2 - 1] = ptx::addc(T[N2 - 1], U[N2 - 1]);
+}
+
+// Montgomery reduction T / 2^(32N) mod m of a 2N-limb value T < m * 2^(32N) (fully reduced result).
+// Word-serial like fp_mul_cc with the same even/odd accumulators; the a*b row is replaced by the division's shift,
+// which also brings in the next high limb of T.
+template <class P> B200_HD Fp<P> fp_redc_wide(const uint32_t* T) {
+    constexpr int N = P::N;
+    uint32_t X[N + 1], Y[N + 1];
+    auto M = [&](int i) { return P::mod(i); };
+    B200_UNROLL
+    for (int k = 0; k < N; k++) { X[k] = T[k]; Y[k] = 0; }
+    X[N] = 0;
+    Y[N] = 0;
+    {
+        uint32_t m = ptx::sub_cc(0u, X[0]);
+        detail::row_mad<P, 1>(Y, M, m);
+        detail::row_mad_mod_even<P>(X, m);
+        X[N] = ptx::addc(X[N], 0u);
+    }
+    B200_UNROLL
+    for (int i = 1; i < N; i++) {
+        uint32_t* E = (i & 1) ? X : Y;                // even-role array entering the row, E[0] == 0
+        uint32_t* O = (i & 1) ? Y : X;
+        O[0] = ptx::add_cc(O[0], E[1]);               // straggler limb; its carry rides the shift below
+        B200_UNROLL
+        for (int k = 0; k < N - 2; k++) E[k] = ptx::addc_cc(E[k + 2], 0u);      // divide by 2^64: E becomes odd-role
+        E[N - 2] = ptx::addc_cc(E[N], T[N + i - 1]);  // next high limb of T enters at position N-1
+        E[N - 1] = ptx::addc(0u, 0u);
+        O[N] = 0;
+        uint32_t m = ptx::sub_cc(0u, O[0]);
+        detail::row_mad<P, 1>(E, M, m);
+        detail::row_mad_mod_even<P>(O, m);
+        O[N] = ptx::addc(O[N], 0u);
+    }
+    uint32_t* Ev = ((N - 1) & 1) ? Y : X;
+    uint32_t* Od = ((N - 1) & 1) ? X : Y;
+    Fp<P> r;
+    r.v[0] = ptx::add_cc(Od[0], Ev[1]);
+    B200_UNROLL
+    for (int k = 1; k < N - 1; k++) r.v[k] = ptx::addc_cc(Od[k], Ev[k + 1]);
+    r.v[N - 1] = ptx::addc(Od[N - 1], Ev[N]);
+    r.v[N - 1] += T[2 * N - 1];                       // last high limb; the total is < 2m, so this cannot overflow
+    fp_reduce_once(r);
+    return r;
+}
+
+template <class P> B200_HD Fp<P> fp_sqr_sos(const Fp<P>& a) {
+    uint32_t T[2 * P::N];
+    fp_sqr_wide<P>(T, a);
+    return fp_redc_wide<P>(T);
+}
 template <class P> B200_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul_cc(a, a); }
+
+// a*b - c*d with a single reduction
+template <class P> B200_HD Fp<P> fp_mul_mul_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    uint32_t T[2 * P::N], U[2 * P::N];
+    fp_mul_wide<P>(T, a, b);
+    fp_mul_wide<P>(U, fp_neg(c), d);                  // (m - c) * d = -c*d (mod m), both addends non-negative
+    fp_wide_add<P>(T, U);
+    return fp_redc_wide<P>(T);
+}
 
 // canonical <-> Montgomery
 template <class P> B200_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul(a, fp_r2<P>()); }

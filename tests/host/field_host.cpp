@@ -11,6 +11,10 @@
 template <class P> static Fp<P> ld(const uint32_t* p) { Fp<P> r; memcpy(r.v, p, 4 * P::N); return r; }
 template <class P> static void st(uint32_t* p, const Fp<P>& a) { memcpy(p, a.v, 4 * P::N); }
 
+template <class P> static Fp<P> mul_via_wide(const Fp<P>& a, const Fp<P>& b) { uint32_t T[2 * P::N]; fp_mul_wide<P>(T, a, b); return fp_redc_wide<P>(T); }
+template <class P> static Fp<P> mms(const Fp<P>& a, const Fp<P>& b) { return fp_mul_mul_sub<P>(a, b, b, a); }           // a*b - b*a = 0
+template <class P> static Fp<P> mms2(const Fp<P>& a, const Fp<P>& b) { return fp_mul_mul_sub<P>(a, a, b, b); }         // a^2 - b^2
+
 extern "C" {
 #define BINOP(NAME, P, FN)                                                                    \
     void NAME(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {                \
@@ -28,8 +32,14 @@ BINOP(host_fq_sub, FqP, fp_sub<FqP>)
     void NAME(uint32_t* out, const uint32_t* a, size_t n) {                                   \
         for (size_t i = 0; i < n; i++) st<P>(out + P::N * i, FN(ld<P>(a + P::N * i)));          \
     }
-UNOP(host_fr_sqr, FrP, fp_sqr<FrP>)
-UNOP(host_fq_sqr, FqP, fp_sqr<FqP>)
+BINOP(host_fr_mul_wide, FrP, mul_via_wide<FrP>)
+BINOP(host_fq_mul_wide, FqP, mul_via_wide<FqP>)
+BINOP(host_fr_mms0, FrP, mms<FrP>)
+BINOP(host_fq_mms0, FqP, mms<FqP>)
+BINOP(host_fr_mms2, FrP, mms2<FrP>)
+BINOP(host_fq_mms2, FqP, mms2<FqP>)
+UNOP(host_fr_sqr, FrP, fp_sqr_sos<FrP>)
+UNOP(host_fq_sqr, FqP, fp_sqr_sos<FqP>)
 UNOP(host_fr_neg, FrP, fp_neg<FrP>)
 UNOP(host_fq_neg, FqP, fp_neg<FqP>)
 UNOP(host_fr_inv, FrP, fp_inv<FrP>)

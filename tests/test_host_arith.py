@@ -59,7 +59,10 @@ def test_field_ops(hostlib, name, mod, bits, nl, rinv):
     want = [x * y * rinv % mod for x, y in zip(a, b)]
     assert _bin(hostlib, f"host_{name}_mul", a, b, nl) == want
     assert _bin(hostlib, f"host_{name}_mul_cc", a, b, nl) == want          # carry-chain variant
-    assert _un(hostlib, f"host_{name}_sqr", a, nl) == [x * x * rinv % mod for x in a]
+    assert _un(hostlib, f"host_{name}_sqr", a, nl) == [x * x * rinv % mod for x in a]         # dedicated squaring
+    assert _bin(hostlib, f"host_{name}_mul_wide", a, b, nl) == want                           # wide product + stand-alone REDC
+    assert _bin(hostlib, f"host_{name}_mms0", a, b, nl) == [0] * len(a)                       # a*b - b*a, one reduction
+    assert _bin(hostlib, f"host_{name}_mms2", a, b, nl) == [(x * x - y * y) * rinv % mod for x, y in zip(a, b)]
     assert _bin(hostlib, f"host_{name}_add", a, b, nl) == [(x + y) % mod for x, y in zip(a, b)]
     assert _bin(hostlib, f"host_{name}_sub", a, b, nl) == [(x - y) % mod for x, y in zip(a, b)]
     assert _un(hostlib, f"host_{name}_neg", a, nl) == [(-x) % mod for x in a]
