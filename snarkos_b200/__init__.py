@@ -10,4 +10,4 @@ from ._lib import B200Error, init, kernel_launch_count, lib, profile  # noqa: F4
 from .fft import EvaluationDomain  # noqa: F401
 from .msm import ResidentBases, VariableBase, msm_batch, sum_projective, synthetic_bases  # noqa: F401
 from .kzg10 import KZG10, Powers  # noqa: F401
-from . import dist, poly  # noqa: F401,E402
+from . import dist, poly, varuna  # noqa: F401,E402

@@ -80,7 +80,7 @@ def test_batch_stride_and_device_resident():
     assert np.array_equal(t.cpu().numpy().view(np.uint64), np.stack([C.ntt(x[b], log_n, direction=1) for b in range(4)]))
 
 
-@pytest.mark.parametrize("log_n,batch", [(20, 16), (24, 1)])
+@pytest.mark.parametrize("log_n,batch", [(20, 16), (24, 1), (26, 1)])
 def test_full_size_properties(log_n, batch):
     """BASELINE configs: properties that need no oracle run at full size (intt(ntt(x)) = x, coset round trip,
     linearity, ntt(delta_1) = powers of omega spot-checked), plus one polynomial checked against the oracle."""
@@ -100,8 +100,9 @@ def test_full_size_properties(log_n, batch):
     d.coset_fft_in_place(dx)
     d.coset_ifft_in_place(dx)
     assert torch.equal(dx, orig)
-    # one polynomial against the CPU oracle (multi-threaded C restatement)
-    assert np.array_equal(fwd[0].cpu().numpy().view(np.uint64), C.ntt(x[0], log_n))
+    # one polynomial against the CPU oracle (multi-threaded C restatement); 2^26 relies on the properties alone
+    if log_n <= 24:
+        assert np.array_equal(fwd[0].cpu().numpy().view(np.uint64), C.ntt(x[0], log_n))
     # delta at index 1 -> omega^k: spot check a few k against Python big-int powers
     delta = np.zeros((n, 4), dtype=np.uint64)
     delta[1] = H.fr_mont_array([1])[0]
