@@ -295,15 +295,42 @@ def run_b200(args):
         barrier()
         t5 = time.perf_counter()
         rb.release()
-        tt = torch.tensor([t1 - t0, t3 - t2, t5 - t4], dtype=torch.float64, device=dev)
+        # same with the window table of the resident set in HBM (17.7 GB at 2^24): one bucket set, no fold
+        tab = None
+        try:
+            rbt = S.ResidentBases(bases, tabulate=True)
+            rbt.msm(h_scalars)
+            barrier()
+            t6 = time.perf_counter()
+            for _ in range(Ke):
+                rbt.msm(h_scalars)
+            barrier()
+            t7 = time.perf_counter()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(Ke):
+                rbt.msm(scalars)
+            ev1.record()
+            torch.cuda.synchronize()
+            tab = (t7 - t6, ev0.elapsed_time(ev1) * 1e-3)
+            rbt.release()
+        except S.B200Error:
+            tab = None
+        tt = torch.tensor([t1 - t0, t3 - t2, t5 - t4, tab[0] if tab else 0.0, tab[1] if tab else 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e_msm, e_ntt, e_res = [float(x) for x in tt.cpu()]
+        e_msm, e_ntt, e_res, e_tab, d_tab = [float(x) for x in tt.cpu()]
         e2e = {"value": world * n * Ke / e_msm / 1e6, "unit": "Mpoints/s",
                "h2d_bytes_per_step": int(h_bases.numel() + h_scalars.numel() * 8), "d2h_bytes_per_step": 144,
                "steps": Ke, "api": "snarkos_b200.VariableBase.msm(pinned host bases, pinned host scalars) -> b200_msm_g1_bls12_377",
                "resident_bases": {"value": world * n * Ke / e_res / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h_scalars.numel() * 8),
                                   "d2h_bytes_per_step": 144, "api": "snarkos_b200.ResidentBases.msm(pinned host scalars) -> b200_msm_registered"}}
+        if tab:
+            e2e["resident_bases_tabulated"] = {"value": world * n * Ke / e_tab / 1e6, "unit": "Mpoints/s",
+                                               "device_resident_value": world * n * Ke / d_tab / 1e6,
+                                               "h2d_bytes_per_step": int(h_scalars.numel() * 8), "d2h_bytes_per_step": 144,
+                                               "api": "snarkos_b200.ResidentBases(bases, tabulate=True).msm(...) -> b200_msm_registered "
+                                                      "(window multiples 2^(c*w) P_i resident in HBM)"}
         ntt_e2e = {"value": world * n * Ke / e_ntt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": int(h_ntt.numel() * 8),
                    "d2h_bytes_per_step": int(h_ntt.numel() * 8), "steps": Ke,
                    "api": "snarkos_b200.EvaluationDomain.fft_in_place(pinned host tensor) -> b200_ntt_fr_bls12_377"}

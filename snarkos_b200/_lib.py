@@ -33,6 +33,8 @@ SYMBOLS = {
     "b200_msm_batch_g1_bls12_377_device": (b200_error_t, [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _vp]),
     "b200_msm_register_bases": (b200_error_t, [_vp, _sz, _sz, ctypes.POINTER(_u64)]),
     "b200_msm_register_bases_device": (b200_error_t, [_vp, _sz, _sz, _vp, ctypes.POINTER(_u64)]),
+    "b200_msm_register_bases_tabulated": (b200_error_t, [_vp, _sz, _sz, _u32, ctypes.POINTER(_u64)]),
+    "b200_msm_register_bases_tabulated_device": (b200_error_t, [_vp, _sz, _sz, _u32, _vp, ctypes.POINTER(_u64)]),
     "b200_msm_registered": (b200_error_t, [_vp, _u64, _vp, _sz]),
     "b200_msm_registered_device": (b200_error_t, [_vp, _u64, _vp, _sz, _vp]),
     "b200_msm_release_bases": (b200_error_t, [_u64]),

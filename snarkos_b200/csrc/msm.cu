@@ -87,8 +87,11 @@ __device__ __forceinline__ uint32_t msm_segment_of(const unsigned long long* seg
     return lo;
 }
 
+// Tabulated bases (n_reg != 0): the caller holds 2^(c*w) * P_i for every window w at index w * n_reg + i, so all
+// windows share ONE set of 2^(c-1) buckets -- the key is the bucket alone and the entry points into the table.
 __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __restrict__ scalars, size_t n,
-                                 MsmShape sh, const unsigned long long* __restrict__ seg_off, uint32_t nmsm) {
+                                 MsmShape sh, const unsigned long long* __restrict__ seg_off, uint32_t nmsm,
+                                 size_t n_reg) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, i) * sh.nwin : 0;
@@ -101,7 +104,7 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t neg;
         uint32_t d = msm_signed_digit(s, w, sh.c, carry, neg);
-        warp_aggregated_inc(counts, (vbase + w) * sh.nbuckets + (d ? d - 1 : 0), valid && d != 0);
+        warp_aggregated_inc(counts, (n_reg ? 0 : (vbase + w) * sh.nbuckets) + (d ? d - 1 : 0), valid && d != 0);
     }
 }
 
@@ -111,7 +114,7 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
 // thread re-derives the carry chain of the lower windows (a few shifts per window).
 __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __restrict__ cursor,
                                    const uint4* __restrict__ scalars, size_t n, MsmShape sh,
-                                   const unsigned long long* __restrict__ seg_off, uint32_t nmsm) {
+                                   const unsigned long long* __restrict__ seg_off, uint32_t nmsm, size_t n_reg) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t w = blockIdx.y;
@@ -124,8 +127,8 @@ __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __r
     uint32_t carry = 0, neg = 0, d = 0;
     for (uint32_t ww = 0; ww <= w; ww++) d = msm_signed_digit(s, ww, sh.c, carry, neg);
     const bool active = valid && d != 0;
-    uint32_t pos = warp_aggregated_inc(cursor, (vbase + w) * sh.nbuckets + (d ? d - 1 : 0), active);
-    if (active) entries[pos] = (uint32_t)i | (neg << 31);
+    uint32_t pos = warp_aggregated_inc(cursor, (n_reg ? 0 : (vbase + w) * sh.nbuckets) + (d ? d - 1 : 0), active);
+    if (active) entries[pos] = (uint32_t)(n_reg ? (size_t)w * n_reg + i : i) | (neg << 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,15 +348,21 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_segments_kernel(g1
     g1_xyzz_store(segs + t, r);
 }
 
-// one block per window: sum of its segment results
-__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_window_sum_kernel(g1_xyzz_mem_t* __restrict__ wsum,
-                                                                         const g1_xyzz_mem_t* __restrict__ segs,
-                                                                         uint32_t segs_per_win) {
+// Sum of the segment results of every window, in up to two levels: blockIdx.x = window, blockIdx.y = slice of that
+// window's `count` inputs (each block adds its slice: strided per-thread sums, then a shared-memory tree) and writes
+// out[window * gridDim.y + blockIdx.y].  The launcher runs it once with many slices per window and once more over the
+// slice sums, so a call with few windows and millions of buckets (tabulated bases: ONE window of 2^23 buckets) does
+// not serialise a hundred thousand additions on 128 threads (measured 13.9 ms -> 0.2 ms).
+__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_window_sum_kernel(g1_xyzz_mem_t* __restrict__ out,
+                                                                         const g1_xyzz_mem_t* __restrict__ in,
+                                                                         uint32_t count, uint32_t per_block) {
     __shared__ g1_xyzz_mem_t sh[MSM_TREE_THREADS];
     const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    const uint32_t lo = blockIdx.y * per_block;
+    const uint32_t hi = lo + per_block < count ? lo + per_block : count;
     g1_xyzz_t acc = g1_xyzz_infinity();
-    for (uint32_t s = tid; s < segs_per_win; s += MSM_TREE_THREADS) {
-        g1_xyzz_t v = g1_xyzz_load(segs + (size_t)w * segs_per_win + s);
+    for (uint32_t s = lo + tid; s < hi; s += MSM_TREE_THREADS) {
+        g1_xyzz_t v = g1_xyzz_load(in + (size_t)w * count + s);
         g1_add(acc, v);
     }
     g1_xyzz_store(&sh[tid], acc);
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(MSM_TREE_THREADS) msm_window_sum_kernel(g1_xyz
         }
         __syncthreads();
     }
-    if (tid == 0) wsum[w] = sh[0];
+    if (tid == 0) out[(size_t)w * gridDim.y + blockIdx.y] = sh[0];
 }
 
 __device__ __forceinline__ void store_jacobian(uint4* out, const g1_xyzz_t& p) {
@@ -407,6 +416,54 @@ __global__ void g1_sum_jacobian_kernel(uint4* __restrict__ out_jac, const uint4*
         g1_add(total, q);
     }
     store_jacobian(out_jac, total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// window table of a resident base set: table[w * n + i] = 2^(c*w) * P_i as packed affine points.  With 180 GB of HBM a
+// 2^24-point SRS times 11 windows (17.7 GB) fits comfortably, and an MSM against the table needs no per-window bucket
+// sets, no window fold and a single bucket reduction.  One thread per point: c doublings per window in XYZZ, then ONE
+// field inversion for all windows of the point (Montgomery's trick over the ZZZ coordinates).
+// ---------------------------------------------------------------------------------------------
+#define MSM_TABLE_MAX_WINDOWS 17
+
+__global__ void __launch_bounds__(64) msm_window_table_kernel(g1_packed_t* __restrict__ table, size_t n, uint32_t c, uint32_t nwin) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_xyzz_t q[MSM_TABLE_MAX_WINDOWS];
+    fq_t pre[MSM_TABLE_MAX_WINDOWS];
+    g1_xyzz_t cur = g1_xyzz_from_affine(g1_unpack(table[i]));
+    fq_t acc = fp_one<FqP>();
+    for (uint32_t w = 1; w < nwin; w++) {
+        for (uint32_t k = 0; k < c; k++) g1_dbl(cur);
+        q[w] = cur;
+        pre[w] = acc;                                             // product of the non-zero ZZZ before w
+        if (!g1_xyzz_is_infinity(cur)) acc = fp_mul(acc, cur.ZZZ);
+    }
+    fq_t inv = fp_inv(acc);
+    for (uint32_t w = nwin; w-- > 1;) {
+        g1_packed_t out;
+        if (g1_xyzz_is_infinity(q[w])) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) out.w[k] = make_uint4(0, 0, 0, 0);
+        } else {
+            fq_t i3 = fp_mul(inv, pre[w]);                        // 1 / ZZZ_w
+            inv = fp_mul(inv, q[w].ZZZ);
+            fq_t i2 = fp_mul(fp_sqr(i3), fp_sqr(q[w].ZZ));        // 1 / ZZ_w  (ZZ^3 = ZZZ^2)
+            fq_t x = fp_mul(q[w].X, i2), y = fp_mul(q[w].Y, i3);
+            fq_to_u4x3(x, out.w);
+            fq_to_u4x3(y, out.w + 3);
+        }
+        table[(size_t)w * n + i] = out;
+    }
+}
+
+b200_error_t msm_build_window_table_device(void* d_table, size_t n, uint32_t c, cudaStream_t stream) {
+    const uint32_t nwin = msm_shape(c).nwin;
+    if (nwin > MSM_TABLE_MAX_WINDOWS) return b200_err(B200_ERR_INVALID_ARG, "msm: window table needs c >= 16");
+    if (n == 0) return b200_ok();
+    msm_window_table_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(reinterpret_cast<g1_packed_t*>(d_table), n, c, nwin);
+    KERNEL_CHECK();
+    return b200_ok();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -456,12 +513,19 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     return msm_run_batch_device(d_out, d_points, n, d_scalars, stride, d_packed, nullptr, 1, stream);
 }
 
+b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scalars, const void* d_table, size_t n_reg,
+                                      uint32_t c, cudaStream_t stream) {
+    return msm_run_batch_device(d_out, nullptr, n, d_scalars, 0, d_table, nullptr, 1, stream, n_reg, c);
+}
+
 // nmsm independent MSMs over consecutive point ranges [seg_off[m], seg_off[m + 1]) of one (points, scalars) pair;
 // d_out receives nmsm Jacobian points.  d_seg_off == nullptr means a single MSM over everything.
 b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                                   const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, size_t n_reg, uint32_t c_tab) {
     if (!d_out) return b200_err(B200_ERR_INVALID_ARG, "msm: null output pointer");
+    if (n_reg && (nmsm != 1 || !d_packed || c_tab < 2 || n > n_reg))
+        return b200_err(B200_ERR_INVALID_ARG, "msm: tabulated bases need a single MSM over a prefix of the table");
     if (nmsm == 0) return b200_ok();
     if (n == 0) {
         msm_write_infinity_kernel<<<(nmsm + 63) / 64, 64, 0, stream>>>(reinterpret_cast<uint4*>(d_out), nmsm);
@@ -474,9 +538,9 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
 
     // window width from the mean MSM size; `vsh` is the shape seen by the kernels after the digit stage, whose
     // "windows" are the nmsm * nwin virtual windows
-    const MsmShape sh = msm_shape(b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
+    const MsmShape sh = msm_shape(n_reg ? c_tab : b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
     MsmShape vsh = sh;
-    vsh.nwin = sh.nwin * nmsm;
+    vsh.nwin = n_reg ? 1 : sh.nwin * nmsm;           // tabulated: one bucket set, nothing to fold
     const size_t K = (size_t)vsh.nwin * sh.nbuckets;
     if (K >= ((size_t)1 << 31)) return b200_err(B200_ERR_TOO_LARGE, "msm: too many buckets (batch too large)");
     if ((size_t)n * sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
@@ -506,14 +570,14 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
     STAGE("msm_count", stream);
     CUDA_TRY(cudaMemsetAsync(counts.p, 0, (K + 1) * 4, stream));
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm);
+    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm, n_reg);
     KERNEL_CHECK();
     STAGE("msm_scan", stream);
     B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
     CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
     STAGE("msm_scatter", stream);
     msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
-                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm);
+                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm, n_reg);
     KERNEL_CHECK();
     // ---- equal-work accumulation ----
     STAGE("msm_accumulate", stream);
@@ -552,11 +616,27 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
         segs.as<g1_xyzz_mem_t>(), buckets.as<g1_xyzz_mem_t>(), vsh, seg_len, segs_per_win);
     KERNEL_CHECK();
     STAGE("msm_window_sum", stream);
-    msm_window_sum_kernel<<<vsh.nwin, MSM_TREE_THREADS, 0, stream>>>(wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(),
-                                                                   segs_per_win);
-    KERNEL_CHECK();
+    {
+        // level 1: slices of >= 4 * MSM_TREE_THREADS segment results per block; level 2: the slice sums of each window
+        const uint32_t per_block = 4 * MSM_TREE_THREADS;
+        const uint32_t slices = (segs_per_win + per_block - 1) / per_block;
+        if (slices > 1) {
+            DevBuf slice_sums;
+            CUDA_TRY(slice_sums.alloc((size_t)slices * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
+            msm_window_sum_kernel<<<dim3(vsh.nwin, slices), MSM_TREE_THREADS, 0, stream>>>(
+                slice_sums.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), segs_per_win, per_block);
+            KERNEL_CHECK();
+            msm_window_sum_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
+                wsum.as<g1_xyzz_mem_t>(), slice_sums.as<g1_xyzz_mem_t>(), slices, slices);
+            KERNEL_CHECK();
+        } else {
+            msm_window_sum_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
+                wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), segs_per_win, segs_per_win);
+            KERNEL_CHECK();
+        }
+    }
     STAGE("msm_fold", stream);
-    msm_fold_kernel<<<(nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(), sh, nmsm);
+    msm_fold_kernel<<<(nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(), n_reg ? vsh : sh, nmsm);
     KERNEL_CHECK();
     STAGE_END(stream);
     return b200_ok();

@@ -21,8 +21,10 @@ except Exception:  # pragma: no cover
 class Powers:
     """`Powers { powers_of_beta_g, powers_of_beta_times_gamma_g }` (or the Lagrange-basis equivalents) on the device."""
 
-    def __init__(self, powers_of_beta_g, powers_of_beta_times_gamma_g=None, stride: int = 104):
-        self.powers_of_beta_g = ResidentBases(powers_of_beta_g, stride)
+    def __init__(self, powers_of_beta_g, powers_of_beta_times_gamma_g=None, stride: int = 104, tabulate: bool = False):
+        """tabulate=True also stores the window multiples 2^(c*w) * beta^i G of the (fixed) SRS in HBM, which makes every
+        commit cheaper (one bucket set, no fold) at nwin x the memory."""
+        self.powers_of_beta_g = ResidentBases(powers_of_beta_g, stride, tabulate=tabulate)
         self.powers_of_beta_times_gamma_g = (ResidentBases(powers_of_beta_times_gamma_g, stride)
                                              if powers_of_beta_times_gamma_g is not None else None)
 

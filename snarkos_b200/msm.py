@@ -94,18 +94,27 @@ class ResidentBases:
     """Device-resident base set (e.g. the SRS powers_of_beta_g that KZG10::commit multiplies against on every
     call [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs; SURVEY.md 8f rank 1])."""
 
-    def __init__(self, bases, stride: int = AFFINE_STRIDE):
+    def __init__(self, bases, stride: int = AFFINE_STRIDE, tabulate: bool = False, window_bits: int = 0):
+        """tabulate=True additionally stores 2^(c*w) * P_i for every window (nwin x the memory, e.g. 17.7 GB for 2^24
+        points): later MSMs share one bucket set across windows and skip the fold."""
         L = _lib.lib()
         h = ctypes.c_uint64(0)
         if _is_cuda_tensor(bases):
             b = bases.contiguous().view(torch.uint8).reshape(-1)
             self.n = b.numel() // stride
-            _lib.check(L.b200_msm_register_bases_device(ctypes.c_void_p(b.data_ptr()), self.n, stride, _stream_ptr(),
-                                                        ctypes.byref(h)))
+            if tabulate:
+                _lib.check(L.b200_msm_register_bases_tabulated_device(ctypes.c_void_p(b.data_ptr()), self.n, stride, window_bits,
+                                                                      _stream_ptr(), ctypes.byref(h)))
+            else:
+                _lib.check(L.b200_msm_register_bases_device(ctypes.c_void_p(b.data_ptr()), self.n, stride, _stream_ptr(),
+                                                            ctypes.byref(h)))
         else:
             b = _host_bytes(bases)
             self.n = b.size // stride
-            _lib.check(L.b200_msm_register_bases(_np_ptr(b), self.n, stride, ctypes.byref(h)))
+            if tabulate:
+                _lib.check(L.b200_msm_register_bases_tabulated(_np_ptr(b), self.n, stride, window_bits, ctypes.byref(h)))
+            else:
+                _lib.check(L.b200_msm_register_bases(_np_ptr(b), self.n, stride, ctypes.byref(h)))
         self.handle: Optional[int] = h.value
 
     def msm(self, scalars):

@@ -200,3 +200,25 @@ def test_batched_small_msms():
     for m in (0, 1, 100, 255):
         want = oracle_msm(dev[m * per * 104:(m + 1) * per * 104], sc2[m * per:(m + 1) * per])
         assert H.jac_bytes_to_affine(out2[m]) == want
+
+
+@pytest.mark.parametrize("window_bits", [0, 16, 19])
+def test_tabulated_resident_bases(window_bits):
+    """resident bases with their window table 2^(c*w) * P_i: same group element as the plain path, for full and
+    prefix-length scalar vectors, including points at infinity and extreme scalars"""
+    import torch
+    import snarkos_b200 as S
+    n = 1 << 11
+    dbases = _synthetic(n, 91)
+    hb = dbases.cpu().numpy().copy()
+    hb[5 * 104:6 * 104] = 0
+    hb[5 * 104 + 96] = 1                                  # a point at infinity inside the set
+    sc = H.random_scalars_np(np.random.default_rng(12), n)
+    sc[:4] = H.scalars_array([0, 1, O.R_MOD - 1, O.R_MOD - 2])
+    rb = S.ResidentBases(hb, tabulate=True, window_bits=window_bits)
+    assert H.jac_bytes_to_affine(rb.msm(sc)) == oracle_msm(hb, sc)
+    assert H.jac_bytes_to_affine(rb.msm(sc[:700])) == oracle_msm(hb[:700 * 104], sc[:700])
+    out = rb.msm(torch.from_numpy(sc.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == oracle_msm(hb, sc)
+    rb.release()
