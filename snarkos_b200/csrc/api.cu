@@ -202,28 +202,33 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         CUDA_TRY(cudaStreamSynchronize(s));
         return b200_ok();
     }
-    // Large call: the MSM is a sum over point ranges, so the ranges are pipelined -- range i+1 crosses PCIe while
-    // range i is being multiplied (double-buffered staging), and the partial sums are added at the end.
+    // Large call: the MSM is a sum over point ranges, so the ranges are streamed -- range i+1 crosses PCIe while the
+    // buckets of range i are being accumulated (double-buffered staging); all ranges add into ONE bucket array, which
+    // is reduced and folded once at the end.
     cudaStream_t cs = b200_thread_copy_stream();
     if (!cs) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
     const size_t nchunks = (n + chunk - 1) / chunk;
-    DevBuf d_pts[2], d_sc[2], d_part, d_out;
+    DevBuf d_pts[2], d_sc[2], d_out;
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(d_pts[b].alloc(chunk * stride, s));
         CUDA_TRY(d_sc[b].alloc(chunk * 32, s));
     }
-    CUDA_TRY(d_part.alloc(nchunks * 144, s));
     CUDA_TRY(d_out.alloc(144, s));
+    void* session = nullptr;
+    B200_TRY(msm_stream_begin(&session, n, s));
     std::vector<cudaEvent_t> copied(nchunks), computed(nchunks);
     cudaEvent_t ready;
-    CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
     for (size_t i = 0; i < nchunks; i++) {
-        CUDA_TRY(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming);
     }
-    CUDA_TRY(cudaEventRecord(ready, s));                 // staging buffers exist from here on in stream order
-    CUDA_TRY(cudaStreamWaitEvent(cs, ready, 0));
     b200_error_t rc = b200_ok();
+    {
+        cudaError_t e = cudaEventRecord(ready, s);                 // staging buffers exist from here on in stream order
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ready, 0);
+        if (e != cudaSuccess) rc = b200_cuda_err(e);
+    }
     for (size_t i = 0; i < nchunks && rc.code == 0; i++) {
         const int b = (int)(i & 1);
         const size_t off = i * chunk, cnt = (n - off < chunk) ? n - off : chunk;
@@ -234,13 +239,14 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         if (e == cudaSuccess) e = cudaEventRecord(copied[i], cs);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s, copied[i], 0);
         if (e != cudaSuccess) { rc = b200_cuda_err(e); break; }
-        rc = msm_run_device((uint8_t*)d_part.p + i * 144, d_pts[b].p, cnt, d_sc[b].p, stride, nullptr, s);
+        rc = msm_stream_add(session, d_pts[b].p, cnt, d_sc[b].p, stride, s);
         if (rc.code == 0) {
             e = cudaEventRecord(computed[i], s);
             if (e != cudaSuccess) rc = b200_cuda_err(e);
         }
     }
-    if (rc.code == 0) rc = b200_g1_sum_jacobian_device(d_out.p, d_part.p, nchunks, s);
+    if (rc.code == 0) rc = msm_stream_finish(session, d_out.p, s);
+    else msm_stream_abort(session);
     if (rc.code == 0) {
         cudaError_t e = cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) rc = b200_cuda_err(e);

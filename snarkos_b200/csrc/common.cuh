@@ -68,6 +68,11 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
                                   cudaStream_t stream, size_t n_reg = 0, uint32_t c_tab = 0);
 b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scalars, const void* d_table, size_t n_reg,
                                       uint32_t c, cudaStream_t stream);
+b200_error_t msm_stream_begin(void** session, size_t n_total, cudaStream_t stream);
+b200_error_t msm_stream_add(void* session, const void* d_points, size_t n, const void* d_scalars, size_t stride,
+                            cudaStream_t stream);
+b200_error_t msm_stream_finish(void* session, void* d_out, cudaStream_t stream);
+void msm_stream_abort(void* session);
 b200_error_t msm_build_window_table_device(void* d_table, size_t n, uint32_t c, cudaStream_t stream);
 b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t n, size_t stride,
                                    cudaStream_t stream);

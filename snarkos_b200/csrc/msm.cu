@@ -518,6 +518,155 @@ b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scala
     return msm_run_batch_device(d_out, nullptr, n, d_scalars, 0, d_table, nullptr, 1, stream, n_reg, c);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The pipeline in two halves, so that the host-buffer path can stream point ranges: `msm_front` turns one range of
+// (points, scalars) into a full bucket array (pack .. combine), `msm_back` turns a bucket array into the result
+// (reduce .. fold); bucket arrays of several ranges computed with the same window width add up bucket by bucket.
+// ---------------------------------------------------------------------------------------------
+struct MsmPlan {
+    MsmShape sh;             // per-MSM shape (c, windows, buckets per window)
+    MsmShape vsh;            // shape seen after the digit stage: nwin = virtual windows (nmsm * nwin, or 1 when tabulated)
+    size_t K;                // total buckets
+    uint32_t nmsm;
+    size_t n_reg;            // != 0: tabulated bases, table row length
+    uint32_t seg_len, segs_per_win;
+};
+
+static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n_reg, uint32_t c_force) {
+    pl->sh = msm_shape(c_force ? c_force : b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
+    pl->vsh = pl->sh;
+    pl->vsh.nwin = n_reg ? 1 : pl->sh.nwin * nmsm;           // tabulated: one bucket set, nothing to fold
+    pl->K = (size_t)pl->vsh.nwin * pl->sh.nbuckets;
+    pl->nmsm = nmsm;
+    pl->n_reg = n_reg;
+    if (pl->K >= ((size_t)1 << 31)) return b200_err(B200_ERR_TOO_LARGE, "msm: too many buckets (batch too large)");
+    if ((size_t)n * pl->sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
+    // segment length of the running-sum reduction: short segments when there are few buckets (latency), long
+    // ones when there are many (each segment pays a ~c-step double-and-add for its offset)
+    uint32_t seg_len = 8;
+    while (seg_len < 64 && pl->K / seg_len > 65536) seg_len <<= 1;
+    if (seg_len > pl->sh.nbuckets) seg_len = pl->sh.nbuckets;
+    pl->seg_len = seg_len;
+    pl->segs_per_win = (pl->sh.nbuckets + seg_len - 1) / seg_len;
+    return b200_ok();
+}
+
+// bucket array (K x XYZZ) of one range of points; d_buckets is overwritten
+static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const void* d_points, size_t n,
+                              const void* d_scalars, size_t stride, const void* d_packed,
+                              const unsigned long long* d_seg_off, cudaStream_t stream) {
+    const MsmShape& sh = pl.sh;
+    const size_t K = pl.K;
+    DevBuf packed, counts, offsets, cursor, entries, heads, tails, head_bucket, tail_bucket, max_heads;
+    const g1_packed_t* pts = reinterpret_cast<const g1_packed_t*>(d_packed);
+    if (!pts) {
+        STAGE("msm_pack", stream);
+        CUDA_TRY(packed.alloc(n * sizeof(g1_packed_t), stream));
+        B200_TRY(msm_pack_bases_device(packed.p, d_points, n, stride, stream));
+        pts = packed.as<g1_packed_t>();
+    }
+    CUDA_TRY(counts.alloc((K + 1) * 4, stream));
+    CUDA_TRY(offsets.alloc((K + 1) * 4, stream));
+    CUDA_TRY(cursor.alloc((K + 1) * 4, stream));
+    CUDA_TRY(entries.alloc(n * sh.nwin * 4, stream));
+
+    STAGE("msm_count", stream);
+    CUDA_TRY(cudaMemsetAsync(counts.p, 0, (K + 1) * 4, stream));
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg);
+    KERNEL_CHECK();
+    STAGE("msm_scan", stream);
+    B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
+    CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+    STAGE("msm_scatter", stream);
+    msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
+                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg);
+    KERNEL_CHECK();
+    // ---- equal-work accumulation ----
+    STAGE("msm_accumulate", stream);
+    uint32_t chunk = 128;
+    if (const char* e = getenv("B200_MSM_CHUNK")) chunk = (uint32_t)atoi(e);
+    if (chunk < 8) chunk = 8;
+    const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
+    const size_t t_max = (E + chunk - 1) / chunk;
+    CUDA_TRY(heads.alloc((t_max + 1) * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(tails.alloc(t_max * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(head_bucket.alloc((t_max + 1) * 4, stream));
+    CUDA_TRY(tail_bucket.alloc(t_max * 4, stream));
+    CUDA_TRY(max_heads.alloc(16, stream));
+    CUDA_TRY(cudaMemsetAsync(max_heads.p, 0, 16, stream));
+    CUDA_TRY(cudaMemsetAsync(head_bucket.p, 0xff, (t_max + 1) * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(tail_bucket.p, 0xff, t_max * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(d_buckets, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
+    const unsigned tblocks = (unsigned)((t_max + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
+    msm_accumulate_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
+        d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
+        tail_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(), offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)K, chunk);
+    KERNEL_CHECK();
+    STAGE("msm_combine", stream);
+    const size_t max_span = (n + chunk - 1) / chunk + 1;            // a bucket holds at most n entries
+    for (uint32_t stride2 = 1; stride2 < max_span; stride2 <<= 1) {
+        msm_combine_heads_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(heads.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
+                                                                         offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride2);
+        KERNEL_CHECK();
+    }
+    msm_combine_tails_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(d_buckets, heads.as<g1_xyzz_mem_t>(),
+                                                                     tails.as<g1_xyzz_mem_t>(), tail_bucket.as<uint32_t>(), (uint32_t)t_max);
+    KERNEL_CHECK();
+    return b200_ok();
+}
+
+// total[k] += part[k] for every bucket (streamed point ranges share one bucket array)
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_merge_buckets_kernel(g1_xyzz_mem_t* __restrict__ total,
+                                                                           const g1_xyzz_mem_t* __restrict__ part, uint32_t K) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    g1_xyzz_t b = g1_xyzz_load(part + k);
+    if (g1_xyzz_is_infinity(b)) return;
+    g1_xyzz_t a = g1_xyzz_load(total + k);
+    g1_add(a, b);
+    g1_xyzz_store(total + k, a);
+}
+
+// result(s) from a bucket array: per-window running sums, window sums, fold
+static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t* d_buckets, cudaStream_t stream) {
+    const MsmShape& vsh = pl.vsh;
+    DevBuf segs, wsum;
+    CUDA_TRY(segs.alloc((size_t)pl.segs_per_win * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
+    CUDA_TRY(wsum.alloc((size_t)vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
+    STAGE("msm_reduce_segments", stream);
+    const uint32_t nseg_threads = pl.segs_per_win * vsh.nwin;
+    msm_reduce_segments_kernel<<<(nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
+        segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
+    KERNEL_CHECK();
+    STAGE("msm_window_sum", stream);
+    {
+        // level 1: slices of >= 4 * MSM_TREE_THREADS segment results per block; level 2: the slice sums of each window
+        const uint32_t per_block = 4 * MSM_TREE_THREADS;
+        const uint32_t slices = (pl.segs_per_win + per_block - 1) / per_block;
+        if (slices > 1) {
+            DevBuf slice_sums;
+            CUDA_TRY(slice_sums.alloc((size_t)slices * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
+            msm_window_sum_kernel<<<dim3(vsh.nwin, slices), MSM_TREE_THREADS, 0, stream>>>(
+                slice_sums.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), pl.segs_per_win, per_block);
+            KERNEL_CHECK();
+            msm_window_sum_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
+                wsum.as<g1_xyzz_mem_t>(), slice_sums.as<g1_xyzz_mem_t>(), slices, slices);
+            KERNEL_CHECK();
+        } else {
+            msm_window_sum_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
+                wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), pl.segs_per_win, pl.segs_per_win);
+            KERNEL_CHECK();
+        }
+    }
+    STAGE("msm_fold", stream);
+    msm_fold_kernel<<<(pl.nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(),
+                                                            pl.n_reg ? vsh : pl.sh, pl.nmsm);
+    KERNEL_CHECK();
+    STAGE_END(stream);
+    return b200_ok();
+}
+
 // nmsm independent MSMs over consecutive point ranges [seg_off[m], seg_off[m + 1]) of one (points, scalars) pair;
 // d_out receives nmsm Jacobian points.  d_seg_off == nullptr means a single MSM over everything.
 b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
@@ -535,112 +684,71 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
     if (!d_scalars || (!d_points && !d_packed)) return b200_err(B200_ERR_INVALID_ARG, "msm: null input pointer");
     if (n >= ((size_t)1 << 28)) return b200_err(B200_ERR_TOO_LARGE, "msm: more than 2^28 - 1 points per call");
     if (reinterpret_cast<uintptr_t>(d_scalars) & 15) return b200_err(B200_ERR_INVALID_ARG, "msm: scalars must be 16-byte aligned on the device");
+    MsmPlan pl;
+    B200_TRY(msm_make_plan(&pl, n, nmsm, n_reg, n_reg ? c_tab : 0));
+    DevBuf buckets;
+    CUDA_TRY(buckets.alloc(pl.K * sizeof(g1_xyzz_mem_t), stream));
+    B200_TRY(msm_front(pl, buckets.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, d_packed, d_seg_off, stream));
+    return msm_back(pl, d_out, buckets.as<g1_xyzz_mem_t>(), stream);
+}
 
-    // window width from the mean MSM size; `vsh` is the shape seen by the kernels after the digit stage, whose
-    // "windows" are the nmsm * nwin virtual windows
-    const MsmShape sh = msm_shape(n_reg ? c_tab : b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
-    MsmShape vsh = sh;
-    vsh.nwin = n_reg ? 1 : sh.nwin * nmsm;           // tabulated: one bucket set, nothing to fold
-    const size_t K = (size_t)vsh.nwin * sh.nbuckets;
-    if (K >= ((size_t)1 << 31)) return b200_err(B200_ERR_TOO_LARGE, "msm: too many buckets (batch too large)");
-    if ((size_t)n * sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
+// Streaming form for the host-buffer path: a session fixes the window width for n_total points; every range adds
+// its buckets into the session's bucket array; finish reduces once.
+struct MsmStream {
+    MsmPlan plan;
+    DevBuf total, part;
+    bool first = true;
+};
 
-    DevBuf packed, counts, offsets, cursor, entries, buckets, segs, wsum, heads, tails, head_bucket, tail_bucket, max_heads;
-    const g1_packed_t* pts = reinterpret_cast<const g1_packed_t*>(d_packed);
-    if (!pts) {
-        STAGE("msm_pack", stream);
-        CUDA_TRY(packed.alloc(n * sizeof(g1_packed_t), stream));
-        B200_TRY(msm_pack_bases_device(packed.p, d_points, n, stride, stream));
-        pts = packed.as<g1_packed_t>();
+b200_error_t msm_stream_begin(void** session, size_t n_total, cudaStream_t stream) {
+    MsmStream* st = new MsmStream();
+    // one window narrower than the single-shot choice: every range pays one group addition per touched bucket when it
+    // is merged, so fewer, fuller buckets win (2^24 in 2^22 ranges: c = 19)
+    uint32_t c = b200_msm_window_bits(n_total);
+    if (!getenv("B200_MSM_C") && c > 6) c -= 1;
+    b200_error_t r = msm_make_plan(&st->plan, n_total, 1, 0, c);
+    if (r.code == 0) {
+        cudaError_t e = st->total.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);
+        if (e == cudaSuccess) e = st->part.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);
+        if (e != cudaSuccess) r = b200_cuda_err(e);
     }
-    CUDA_TRY(counts.alloc((K + 1) * 4, stream));
-    CUDA_TRY(offsets.alloc((K + 1) * 4, stream));
-    CUDA_TRY(cursor.alloc((K + 1) * 4, stream));
-    CUDA_TRY(entries.alloc(n * sh.nwin * 4, stream));
-    CUDA_TRY(buckets.alloc(K * sizeof(g1_xyzz_mem_t), stream));
-    // segment length of the running-sum reduction: short segments when there are few buckets (latency), long
-    // ones when there are many (each segment pays a ~c-step double-and-add for its offset)
-    uint32_t seg_len = 8;
-    while (seg_len < 64 && K / seg_len > 65536) seg_len <<= 1;
-    if (seg_len > sh.nbuckets) seg_len = sh.nbuckets;
-    const uint32_t segs_per_win = (sh.nbuckets + seg_len - 1) / seg_len;
-    CUDA_TRY(segs.alloc((size_t)segs_per_win * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
-    CUDA_TRY(wsum.alloc((size_t)vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
-
-    STAGE("msm_count", stream);
-    CUDA_TRY(cudaMemsetAsync(counts.p, 0, (K + 1) * 4, stream));
-    const unsigned nblk = (unsigned)((n + 255) / 256);
-    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm, n_reg);
-    KERNEL_CHECK();
-    STAGE("msm_scan", stream);
-    B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
-    CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-    STAGE("msm_scatter", stream);
-    msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
-                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, nmsm, n_reg);
-    KERNEL_CHECK();
-    // ---- equal-work accumulation ----
-    STAGE("msm_accumulate", stream);
-    uint32_t chunk = 128;
-    if (const char* e = getenv("B200_MSM_CHUNK")) chunk = (uint32_t)atoi(e);
-    if (chunk < 8) chunk = 8;
-    const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
-    const size_t t_max = (E + chunk - 1) / chunk;
-    CUDA_TRY(heads.alloc((t_max + 1) * sizeof(g1_xyzz_mem_t), stream));
-    CUDA_TRY(tails.alloc(t_max * sizeof(g1_xyzz_mem_t), stream));
-    CUDA_TRY(head_bucket.alloc((t_max + 1) * 4, stream));
-    CUDA_TRY(tail_bucket.alloc(t_max * 4, stream));
-    CUDA_TRY(max_heads.alloc(16, stream));
-    CUDA_TRY(cudaMemsetAsync(max_heads.p, 0, 16, stream));
-    CUDA_TRY(cudaMemsetAsync(head_bucket.p, 0xff, (t_max + 1) * 4, stream));
-    CUDA_TRY(cudaMemsetAsync(tail_bucket.p, 0xff, t_max * 4, stream));
-    CUDA_TRY(cudaMemsetAsync(buckets.p, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
-    const unsigned tblocks = (unsigned)((t_max + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-    msm_accumulate_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
-        buckets.as<g1_xyzz_mem_t>(), heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-        tail_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(), offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)K, chunk);
-    KERNEL_CHECK();
-    STAGE("msm_combine", stream);
-    const size_t max_span = (n + chunk - 1) / chunk + 1;            // a bucket holds at most n entries
-    for (uint32_t stride = 1; stride < max_span; stride <<= 1) {
-        msm_combine_heads_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(heads.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-                                                                         offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride);
-        KERNEL_CHECK();
-    }
-    msm_combine_tails_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(buckets.as<g1_xyzz_mem_t>(), heads.as<g1_xyzz_mem_t>(),
-                                                                     tails.as<g1_xyzz_mem_t>(), tail_bucket.as<uint32_t>(), (uint32_t)t_max);
-    KERNEL_CHECK();
-    STAGE("msm_reduce_segments", stream);
-    const uint32_t nseg_threads = segs_per_win * vsh.nwin;
-    msm_reduce_segments_kernel<<<(nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
-        segs.as<g1_xyzz_mem_t>(), buckets.as<g1_xyzz_mem_t>(), vsh, seg_len, segs_per_win);
-    KERNEL_CHECK();
-    STAGE("msm_window_sum", stream);
-    {
-        // level 1: slices of >= 4 * MSM_TREE_THREADS segment results per block; level 2: the slice sums of each window
-        const uint32_t per_block = 4 * MSM_TREE_THREADS;
-        const uint32_t slices = (segs_per_win + per_block - 1) / per_block;
-        if (slices > 1) {
-            DevBuf slice_sums;
-            CUDA_TRY(slice_sums.alloc((size_t)slices * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
-            msm_window_sum_kernel<<<dim3(vsh.nwin, slices), MSM_TREE_THREADS, 0, stream>>>(
-                slice_sums.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), segs_per_win, per_block);
-            KERNEL_CHECK();
-            msm_window_sum_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
-                wsum.as<g1_xyzz_mem_t>(), slice_sums.as<g1_xyzz_mem_t>(), slices, slices);
-            KERNEL_CHECK();
-        } else {
-            msm_window_sum_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
-                wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), segs_per_win, segs_per_win);
-            KERNEL_CHECK();
-        }
-    }
-    STAGE("msm_fold", stream);
-    msm_fold_kernel<<<(nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(), n_reg ? vsh : sh, nmsm);
-    KERNEL_CHECK();
-    STAGE_END(stream);
+    if (r.code != 0) { delete st; return r; }
+    *session = st;
     return b200_ok();
 }
+
+b200_error_t msm_stream_add(void* session, const void* d_points, size_t n, const void* d_scalars, size_t stride,
+                            cudaStream_t stream) {
+    MsmStream* st = reinterpret_cast<MsmStream*>(session);
+    if (n == 0) return b200_ok();
+    if (st->first) {
+        B200_TRY(msm_front(st->plan, st->total.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
+        st->first = false;
+        return b200_ok();
+    }
+    B200_TRY(msm_front(st->plan, st->part.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
+    STAGE("msm_merge", stream);
+    const uint32_t K = (uint32_t)st->plan.K;
+    msm_merge_buckets_kernel<<<(K + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS, MSM_ACC_THREADS, 0, stream>>>(
+        st->total.as<g1_xyzz_mem_t>(), st->part.as<g1_xyzz_mem_t>(), K);
+    KERNEL_CHECK();
+    return b200_ok();
+}
+
+b200_error_t msm_stream_finish(void* session, void* d_out, cudaStream_t stream) {
+    MsmStream* st = reinterpret_cast<MsmStream*>(session);
+    b200_error_t r = b200_ok();
+    if (st->first) {
+        msm_write_infinity_kernel<<<1, 64, 0, stream>>>(reinterpret_cast<uint4*>(d_out), 1);
+        B200_LAUNCH_COUNT();
+    } else {
+        r = msm_back(st->plan, d_out, st->total.as<g1_xyzz_mem_t>(), stream);
+    }
+    delete st;          // stream-ordered frees
+    return r;
+}
+
+void msm_stream_abort(void* session) { delete reinterpret_cast<MsmStream*>(session); }
 
 extern "C" b200_error_t b200_g1_sum_jacobian_device(void* d_out, const void* d_in, size_t count, void* stream) {
     B200_TRY(b200_require_device());

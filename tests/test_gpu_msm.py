@@ -222,3 +222,17 @@ def test_tabulated_resident_bases(window_bits):
     torch.cuda.synchronize()
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == oracle_msm(hb, sc)
     rb.release()
+
+
+def test_host_buffer_streaming_path():
+    """host-buffer calls with >= 2^23 points stream 2^22-point ranges into one bucket array (copy of range i+1
+    overlapped with the accumulation of range i); exact identity check incl. a ragged last range"""
+    import torch
+    import snarkos_b200 as S
+    n, seed = (1 << 23) + 12345, 5
+    hb = _synthetic(n, seed).cpu().numpy()
+    sc = H.random_scalars_np(np.random.default_rng(23), n)
+    sc[:3] = H.scalars_array([0, O.R_MOD - 1, 1])
+    got = S.VariableBase.msm(hb, sc)
+    k = H.splitmix64_at(seed, np.arange(n))
+    assert H.jac_bytes_to_affine(got) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
