@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "msm_core.cuh"
+#include "msm_affine.cuh"
 
 #define MSM_ACC_THREADS 128
 #define MSM_RED_THREADS 64
@@ -230,6 +231,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 // ---------------------------------------------------------------------------------------------
 #define MSM_NONE 0xffffffffu
 
+// DIRECT: the entry stream IS the point list (output of the batched-affine rounds), no index / sign indirection.
+template <bool DIRECT>
 __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_xyzz_mem_t* __restrict__ buckets,
                                                                         g1_xyzz_mem_t* __restrict__ heads,
                                                                         g1_xyzz_mem_t* __restrict__ tails,
@@ -256,18 +259,18 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
     uint32_t bucket_end = offsets[k + 1];
     bool from_start = (offsets[k] == e);
     g1_xyzz_t acc = g1_xyzz_infinity();
-    uint32_t cur_id = entries[e];
-    g1_packed_t cur = pts[cur_id & 0x7fffffffu];
+    uint32_t cur_id = DIRECT ? e : entries[e];
+    g1_packed_t cur = pts[DIRECT ? cur_id : (cur_id & 0x7fffffffu)];
     for (;;) {
         const uint32_t nxt_e = e + 1;
         uint32_t nxt_id = 0;
         g1_packed_t nxt;
         if (nxt_e < end) {
-            nxt_id = entries[nxt_e];
-            nxt = pts[nxt_id & 0x7fffffffu];
+            nxt_id = DIRECT ? nxt_e : entries[nxt_e];
+            nxt = pts[DIRECT ? nxt_id : (nxt_id & 0x7fffffffu)];
         }
         g1_affine_t a = g1_unpack(cur);
-        if (cur_id >> 31) a.y = fp_neg(a.y);
+        if (!DIRECT && (cur_id >> 31)) a.y = fp_neg(a.y);
         g1_madd(acc, a);
         e = nxt_e;
         const bool at_bucket_end = (e == bucket_end), at_chunk_end = (e == end);
@@ -329,6 +332,59 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_tails_kernel(g1_x
     g1_xyzz_t b = g1_xyzz_load(heads + t + 1);
     g1_add(a, b);
     g1_xyzz_store(buckets + k, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched-affine pair rounds (msm_affine.cuh): one thread per MSM_PAIRS_PER_THREAD outputs
+// ---------------------------------------------------------------------------------------------
+#define MSM_PAIR_THREADS 128
+
+__global__ void msm_half_counts_kernel(uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off, uint32_t K) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) cnt[k] = (off[k + 1] - off[k] + 1) >> 1;
+}
+
+__global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_denoms_kernel(PairRound rd, uint4* __restrict__ pre,
+                                                                          uint4* __restrict__ partial, uint32_t nthreads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) pair_denoms_thread(rd, t, pre, partial);
+}
+
+__global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_add_kernel(PairRound rd, const uint4* __restrict__ pre,
+                                                                       const uint4* __restrict__ partial_inv,
+                                                                       g1_packed_t* __restrict__ out, uint32_t nthreads) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nthreads) pair_add_thread(rd, t, pre, partial_inv, out);
+}
+
+__global__ void __launch_bounds__(128) fq_inv_up_kernel(uint4* __restrict__ partial, const uint4* __restrict__ data, size_t n) {
+    fq_inv_up_thread(partial, data, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) fq_inv_down_kernel(uint4* __restrict__ data, const uint4* __restrict__ partial_inv, size_t n) {
+    fq_inv_down_thread(data, partial_inv, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+#define FQ_INV_SMALL_THREADS 512
+__global__ void __launch_bounds__(FQ_INV_SMALL_THREADS) fq_inv_small_kernel(uint4* __restrict__ data, size_t n) {
+    fq_inv_small_thread(data, n, threadIdx.x, FQ_INV_SMALL_THREADS);
+}
+
+// in-place inversion of n Fq values, none of them zero
+static b200_error_t fq_batch_inverse_nonzero(uint4* d_data, size_t n, cudaStream_t s) {
+    if (n == 0) return b200_ok();
+    if (n <= (size_t)FQ_INV_SMALL_THREADS * MSM_INV_SMALL_PER_THREAD) {
+        fq_inv_small_kernel<<<1, FQ_INV_SMALL_THREADS, 0, s>>>(d_data, n);
+        KERNEL_CHECK();
+        return b200_ok();
+    }
+    const size_t nt = (n + MSM_INV_CHUNK - 1) / MSM_INV_CHUNK;
+    DevBuf partial;
+    CUDA_TRY(partial.alloc(nt * 48, s));
+    fq_inv_up_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(partial.as<uint4>(), d_data, n);
+    KERNEL_CHECK();
+    B200_TRY(fq_batch_inverse_nonzero(partial.as<uint4>(), nt, s));
+    fq_inv_down_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(d_data, partial.as<uint4>(), n);
+    KERNEL_CHECK();
+    return b200_ok();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -551,6 +607,23 @@ static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n
     return b200_ok();
 }
 
+// list length after one pair round: sum_k ceil(m_k / 2) <= (E + #non-empty buckets) / 2
+static size_t msm_halved_bound(size_t E, size_t K) { return (E + (K < E ? K : E) + 1) / 2; }
+
+// Number of batched-affine rounds before the XYZZ finish: enough to leave lists of 2..4 points.  Small calls are
+// launch-bound (every round is ~10 launches and one serial Fermat inversion), they keep the one-kernel path.
+static uint32_t msm_affine_rounds(size_t E, size_t K) {
+    if (const char* e = getenv("B200_MSM_AFFINE_ROUNDS")) {
+        int r = atoi(e);
+        return r < 0 ? 0u : (r > 30 ? 30u : (uint32_t)r);
+    }
+    if (E < ((size_t)1 << 22)) return 0;
+    const size_t avg = E / K;
+    uint32_t r = 0;
+    while (r < 6 && (avg >> (r + 1)) >= 2) r++;
+    return r;
+}
+
 // bucket array (K x XYZZ) of one range of points; d_buckets is overwritten
 static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const void* d_points, size_t n,
                               const void* d_scalars, size_t stride, const void* d_packed,
@@ -582,13 +655,62 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
                                                  reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg);
     KERNEL_CHECK();
-    // ---- equal-work accumulation ----
+    // ---- batched-affine pair rounds: halve every bucket's list `rounds` times at ~6.3 products per addition ----
+    const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
+    const g1_packed_t* acc_pts = pts;
+    const uint32_t* acc_off = offsets.as<uint32_t>();
+    size_t acc_E = E;
+    bool direct = false;
+    DevBuf list_a, list_b, pre, partial, half, off_a, off_b;
+    uint32_t rounds = msm_affine_rounds(E, K);
+    if (rounds) {
+        const size_t e1 = msm_halved_bound(E, K), e2 = msm_halved_bound(e1, K);
+        const size_t t1 = (e1 + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD;
+        cudaError_t e = list_a.alloc(e1 * sizeof(g1_packed_t), stream);
+        if (e == cudaSuccess && rounds > 1) e = list_b.alloc(e2 * sizeof(g1_packed_t), stream);
+        if (e == cudaSuccess) e = pre.alloc(e1 * 48, stream);
+        if (e == cudaSuccess) e = partial.alloc(t1 * 48, stream);
+        if (e == cudaSuccess) e = half.alloc((K + 1) * 4, stream);
+        if (e == cudaSuccess) e = off_a.alloc((K + 1) * 4, stream);
+        if (e == cudaSuccess) e = off_b.alloc((K + 1) * 4, stream);
+        if (e != cudaSuccess) {
+            if (e != cudaErrorMemoryAllocation) return b200_cuda_err(e);
+            (void)cudaGetLastError();                                 // not enough HBM for the lists: XYZZ path only
+            rounds = 0;
+        }
+    }
+    for (uint32_t r = 0; r < rounds; r++) {
+        STAGE(r == 0 ? "msm_pairs_round0" : "msm_pairs_rounds", stream);
+        const size_t e_out = msm_halved_bound(acc_E, K);
+        uint32_t* noff = (r & 1) ? off_b.as<uint32_t>() : off_a.as<uint32_t>();
+        g1_packed_t* out = (r & 1) ? list_b.as<g1_packed_t>() : list_a.as<g1_packed_t>();
+        msm_half_counts_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(half.as<uint32_t>(), acc_off, (uint32_t)K);
+        KERNEL_CHECK();
+        B200_TRY(exclusive_scan(noff, half.as<uint32_t>(), K, stream));
+        PairRound rd;
+        rd.src = acc_pts;
+        rd.entries = direct ? nullptr : entries.as<uint32_t>();
+        rd.off = acc_off;
+        rd.noff = noff;
+        rd.K = (uint32_t)K;
+        const uint32_t nthr = (uint32_t)((e_out + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD);
+        const unsigned nblk_p = (nthr + MSM_PAIR_THREADS - 1) / MSM_PAIR_THREADS;
+        msm_pair_denoms_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), nthr);
+        KERNEL_CHECK();
+        B200_TRY(fq_batch_inverse_nonzero(partial.as<uint4>(), nthr, stream));
+        msm_pair_add_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), out, nthr);
+        KERNEL_CHECK();
+        acc_pts = out;
+        acc_off = noff;
+        acc_E = e_out;
+        direct = true;
+    }
+    // ---- equal-work XYZZ accumulation of what is left ----
     STAGE("msm_accumulate", stream);
     uint32_t chunk = 128;
     if (const char* e = getenv("B200_MSM_CHUNK")) chunk = (uint32_t)atoi(e);
     if (chunk < 8) chunk = 8;
-    const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
-    const size_t t_max = (E + chunk - 1) / chunk;
+    const size_t t_max = (acc_E + chunk - 1) / chunk;
     CUDA_TRY(heads.alloc((t_max + 1) * sizeof(g1_xyzz_mem_t), stream));
     CUDA_TRY(tails.alloc(t_max * sizeof(g1_xyzz_mem_t), stream));
     CUDA_TRY(head_bucket.alloc((t_max + 1) * 4, stream));
@@ -599,15 +721,20 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     CUDA_TRY(cudaMemsetAsync(tail_bucket.p, 0xff, t_max * 4, stream));
     CUDA_TRY(cudaMemsetAsync(d_buckets, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
     const unsigned tblocks = (unsigned)((t_max + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-    msm_accumulate_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
-        d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-        tail_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(), offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)K, chunk);
+    if (direct)
+        msm_accumulate_kernel<true><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
+            d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
+            tail_bucket.as<uint32_t>(), acc_pts, nullptr, acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
+    else
+        msm_accumulate_kernel<false><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
+            d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
+            tail_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(), acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
     KERNEL_CHECK();
     STAGE("msm_combine", stream);
     const size_t max_span = (n + chunk - 1) / chunk + 1;            // a bucket holds at most n entries
     for (uint32_t stride2 = 1; stride2 < max_span; stride2 <<= 1) {
         msm_combine_heads_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(heads.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-                                                                         offsets.as<uint32_t>(), max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride2);
+                                                                         acc_off, max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride2);
         KERNEL_CHECK();
     }
     msm_combine_tails_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(d_buckets, heads.as<g1_xyzz_mem_t>(),

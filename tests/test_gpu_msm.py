@@ -236,3 +236,70 @@ def test_host_buffer_streaming_path():
     got = S.VariableBase.msm(hb, sc)
     k = H.splitmix64_at(seed, np.arange(n))
     assert H.jac_bytes_to_affine(got) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+
+
+# ---------------------------------------------------------------------------------------------
+# batched-affine pair rounds (msm_affine.cuh), forced on at small sizes through B200_MSM_AFFINE_ROUNDS
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rounds", [1, 3, 8])
+@pytest.mark.parametrize("n,c", [(1, 4), (33, 4), (1000, 6), (5000, 8)])
+def test_affine_rounds_vs_oracle(monkeypatch, rounds, n, c):
+    """snarkVM batched::batch_add counterpart: pairwise affine additions with one batch inversion per round;
+    narrow windows make buckets of tens to hundreds of points, `rounds` beyond log2(bucket size) must be no-ops."""
+    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", str(rounds))
+    monkeypatch.setenv("B200_MSM_C", str(c))
+    rng = O.SplitMix64(1500 + n + rounds)
+    pts = O.random_points(rng, min(n, 64))
+    pts = [pts[i % len(pts)] for i in range(n)]               # repeated points: doublings appear in later rounds
+    sc = O.random_fr(rng, n)
+    bases, scal = H.bases_array(pts), H.scalars_array(sc)
+    want = O.msm_naive(pts, sc) if n <= 33 else oracle_msm(bases, scal)
+    assert gpu_msm(bases, scal) == want
+
+
+@pytest.mark.parametrize("rounds", [2, 7])
+def test_affine_rounds_edge_cases(monkeypatch, rounds):
+    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", str(rounds))
+    monkeypatch.setenv("B200_MSM_C", "4")
+    rng = O.SplitMix64(81)
+    n = 64
+    pts = O.random_points(rng, n)
+    sc = O.random_fr(rng, n)
+    sc[0], sc[1], sc[2], sc[3] = 0, 1, O.R_MOD - 1, O.R_MOD - 2
+    pts[4] = None
+    pts[6], sc[6] = pts[5], sc[5]                   # P + P as one pair
+    pts[8], sc[8] = O.g1_neg(pts[7]), sc[7]         # P + (-P) as one pair
+    pts[10], sc[10] = pts[9], O.R_MOD - sc[9]       # cancels through the sign bit
+    assert gpu_msm(H.bases_array(pts), H.scalars_array(sc)) == O.msm_naive(pts, sc)
+    assert gpu_msm(H.bases_array(pts), H.scalars_array([sc[11]] * n)) == O.msm_naive(pts, [sc[11]] * n)
+    assert gpu_msm(H.bases_array([pts[0]] * n), H.scalars_array(sc)) == O.g1_mul(pts[0], sum(sc) % O.R_MOD)
+    assert gpu_msm(H.bases_array([pts[0]] * n), H.scalars_array([sc[12]] * n)) == O.g1_mul(pts[0], n * sc[12] % O.R_MOD)
+    assert gpu_msm(H.bases_array(pts), H.scalars_array([0] * n)) is None
+    assert gpu_msm(H.bases_array([None] * n), H.scalars_array(sc)) is None
+    assert gpu_msm(H.bases_array([pts[0], pts[0]]), H.scalars_array([5, O.R_MOD - 5])) is None
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "two_values", "tiny", "top_heavy", "uniform"])
+def test_affine_rounds_skewed_distributions(monkeypatch, kind):
+    """2^16 points, 4 rounds: a bucket holding every point is halved four times and finished by the XYZZ chunks."""
+    import torch
+    import snarkos_b200 as S
+    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", "4")
+    n, seed = 1 << 16, 23
+    dbases = _synthetic(n, seed)
+    rng = np.random.default_rng(5)
+    if kind == "all_equal":
+        vals = [O.R_MOD - 12345] * n
+    elif kind == "two_values":
+        vals = [3 if i % 3 else (1 << 200) + 7 for i in range(n)]
+    elif kind == "tiny":
+        vals = [int(x) for x in rng.integers(0, 4, size=n)]
+    elif kind == "top_heavy":
+        vals = [(1 << 252) + int(x) for x in rng.integers(0, 1 << 20, size=n)]
+    else:
+        vals = None
+    sc = H.scalars_array(vals) if vals is not None else H.random_scalars_np(rng, n)
+    out = S.VariableBase.msm(dbases, torch.from_numpy(sc.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    k = H.splitmix64_at(seed, np.arange(n))
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
