@@ -345,27 +345,40 @@ def run_b200(args):
     hbm_peak, peak_src = measured_peaks()
     c = int(S.lib().b200_msm_window_bits(n))
     nwin = 253 // c + 1
-    acc_ms = stage.get("msm_accumulate", 0.0) / K
+    rounds = int(S.lib().b200_msm_affine_rounds(n))
+    # dominant kernel: msm_pair_add_kernel, launched once per pair round (all `rounds` launches of an MSM are one unit)
+    add_ms = sum(v for k_, v in stage.items() if k_ in ("msm_pairs0_add", "msm_pairs_add")) / K
+    dom_kernel, dom_ms = ("msm_pair_add_kernel", add_ms) if rounds else ("msm_accumulate_kernel", stage.get("msm_accumulate", 0.0) / K)
+    bucket_ms = sum(v for k_, v in stage.items() if k_.startswith("msm_pairs") or k_ in ("msm_accumulate", "msm_combine")) / K
     alg_bytes = (104 + 32) * n                                   # (104 + 32) B per point
-    roofline = {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+    roofline = {"bound": "hbm", "kernel": dom_kernel, "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
-                "traffic": NCU_TRAFFIC_BYTES["msm_accumulate_kernel@2^24"] if args.log_n == 24 else None,
-                "traffic_note": "bytes per launch, ncu capture profiles/r01_ncu_full_selected_metrics.txt; the bucket method "
-                                "re-reads every 96 B packed point once per window, so traffic >> the (104+32) B/point figure",
-                "avg_launch_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes}
+                "traffic": NCU_TRAFFIC_BYTES.get(dom_kernel + "@2^24") if args.log_n == 24 else None,
+                "traffic_note": "bytes per MSM (all launches of the kernel), ncu capture under profiles/; every round re-reads "
+                                "its operands (round 0: one 128 B line per gathered base, per window), so traffic >> (104+32) B/point",
+                "launches_per_step": max(rounds, 1), "avg_launch_ms": dom_ms / max(rounds, 1), "ms_per_step": dom_ms,
+                "algorithmic_bytes_per_step": alg_bytes, "bucket_accumulation_ms": bucket_ms}
     roofline["frac"] = roofline["achieved"] / hbm_peak if roofline["achieved"] else None
-    # integer-multiply pipe: Fq modmuls the accumulate kernel must execute vs the modmul rate of a pure fp_mul loop
+    # integer-multiply pipe: Fq modmuls the kernel must execute vs the modmul rate of a pure fp_mul loop
     import ctypes
     ms_, ops_ = ctypes.c_float(), ctypes.c_double()
     best = 0.0
     for _ in range(3):
         S._lib.check(S.lib().b200_debug_microbench(4, 256, ctypes.byref(ms_), ctypes.byref(ops_)))
         best = max(best, ops_.value / (ms_.value * 1e-3))
-    modmuls = 10.0 * n * nwin                                     # one XYZZ mixed add (8M + 2S) per non-zero digit
-    roofline_int = {"bound": "int_mul_pipe", "kernel": "msm_accumulate_kernel", "unit": "G Fq-modmul/s",
-                    "achieved": modmuls / (acc_ms * 1e-3) / 1e9 if acc_ms else None, "peak": best / 1e9,
+    if rounds:
+        # pair rounds halve the lists `rounds` times: ~E (1 - 2^-rounds) additions (E = n * windows entries), each
+        # 5 Fq products in msm_pair_add_kernel (2 to peel its inverse off the shared one, 2M + 1S for the addition)
+        modmuls = 5.0 * n * nwin * (1.0 - 0.5 ** rounds)
+        per_add = "5 (affine addition with a shared inversion; +1 in msm_pair_denoms_kernel, +~0.2 in the batch inversion)"
+    else:
+        modmuls = 10.0 * n * nwin                                 # one XYZZ mixed add (8M + 2S) per non-zero digit
+        per_add = "10 (XYZZ mixed addition)"
+    roofline_int = {"bound": "int_mul_pipe", "kernel": dom_kernel, "unit": "G Fq-modmul/s",
+                    "achieved": modmuls / (dom_ms * 1e-3) / 1e9 if dom_ms else None, "peak": best / 1e9,
                     "peak_source": "fp_mul<Fq> dependent-chain microbenchmark, same run, full occupancy",
-                    "modmul_per_launch": modmuls, "window_bits": c, "windows": nwin, "digits": "signed"}
+                    "modmul_per_step": modmuls, "modmul_per_addition": per_add, "window_bits": c, "windows": nwin,
+                    "digits": "signed", "affine_rounds": rounds}
     roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"] if roofline_int["achieved"] else None
     ntt_pass_ms = sum(v for k_, v in stage.items() if k_.startswith("ntt_pass")) / K
     ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,

@@ -114,6 +114,9 @@ b200_error_t b200_kzg_commit_device(void* d_out_jacobian_144B, uint64_t handle, 
 
 /* Window width the library would pick for `npoints` (0 = library default); B200_MSM_C overrides. */
 uint32_t b200_msm_window_bits(size_t npoints);
+/* number of batched-affine pair rounds (snarkVM batched::batch_add counterpart) a call of this size runs before the
+ * XYZZ finish, for the window width above (diagnostic: bench.py's roofline accounting) */
+uint32_t b200_msm_affine_rounds(size_t npoints);
 
 /* Sum of `count` Jacobian points (144 B each): the multi-GPU partial-sum combine.  Device pointers. */
 b200_error_t b200_g1_sum_jacobian_device(void* d_out_jacobian_144B, const void* d_in, size_t count,

@@ -45,6 +45,22 @@ cudaStream_t b200_thread_stream() {
     return t_stream.s;
 }
 
+// High-priority helper stream of the calling thread: the MSM runs the memory-bound half of a pair round (denominators
+// + inversion of slice i + 1) on it while the compute-bound half (additions of slice i) occupies the caller's stream.
+static thread_local ThreadStream t_aux_stream;
+cudaStream_t b200_thread_aux_stream() {
+    if (!t_aux_stream.s) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);               // hi = numerically smallest = highest priority
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        t_aux_stream.s = s;
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        g_api.streams.push_back(s);
+    }
+    return t_aux_stream.s;
+}
+
 b200_error_t b200_require_device() {
     if (g_api.initialized) {
         // a worker thread that never touched CUDA starts on device 0: bind it to the process's device
@@ -80,6 +96,14 @@ extern "C" b200_error_t b200_init(int device) {
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t threshold = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    if (const char* e = getenv("B200_L2_FETCH_GRANULARITY")) {
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[b200] L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(le));
+        (void)cudaGetLastError();
     }
     g_api.device = device;
     g_api.initialized = true;
@@ -306,7 +330,7 @@ extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, siz
     B200_TRY(b200_require_device());
     if (!out_handle || (n && !d_points)) return b200_err(B200_ERR_INVALID_ARG, "register_bases: null pointer");
     void* d_packed = nullptr;
-    CUDA_TRY(cudaMalloc(&d_packed, (n ? n : 1) * sizeof(g1_packed_t)));
+    CUDA_TRY(cudaMalloc(&d_packed, (n ? n : 1) * (size_t)G1_BASE_BYTES));
     b200_error_t r = msm_pack_bases_device(d_packed, d_points, n, stride, (cudaStream_t)stream);
     if (r.code == 0) {
         cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
@@ -343,14 +367,14 @@ extern "C" b200_error_t b200_msm_register_bases_tabulated_device(const void* d_p
     if (c == 0) {                                   // one bucket set for all windows: wider windows pay off
         uint32_t lg = 0;
         while (((size_t)1 << (lg + 1)) <= n) lg++;
-        c = lg < 17 ? 16 : lg - 1;                  // measured at 2^24: c = 23 (90.3 ms) vs 22 (96.7) vs 24 (99.7)
-        if (c > 23) c = 23;
+        c = lg < 20 ? 16 : lg - 4;                  // measured at 2^24 (pair rounds on): c = 20 (72.3 ms), 21 (72.9), 18 (77.1), 22 (77.5)
+        if (c > 22) c = 22;
     }
     if (c < 16 || c > 24) return b200_err(B200_ERR_INVALID_ARG, "register_bases_tabulated: window_bits must be 16..24");
     const uint32_t nwin = 253 / c + 1;
     if ((size_t)nwin * n >= ((size_t)1 << 31)) return b200_err(B200_ERR_TOO_LARGE, "register_bases_tabulated: windows * points >= 2^31");
     void* d_table = nullptr;
-    CUDA_TRY(cudaMalloc(&d_table, ((size_t)nwin * n + 1) * sizeof(g1_packed_t)));
+    CUDA_TRY(cudaMalloc(&d_table, ((size_t)nwin * n + 1) * (size_t)G1_BASE_BYTES));
     cudaStream_t s = (cudaStream_t)stream;
     b200_error_t r = msm_pack_bases_device(d_table, d_points, n, stride, s);
     if (r.code == 0) r = msm_build_window_table_device(d_table, n, c, s);

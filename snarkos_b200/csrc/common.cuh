@@ -79,3 +79,4 @@ b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t 
 void ntt_release_tables();
 b200_error_t b200_require_device();
 cudaStream_t b200_thread_stream();
+cudaStream_t b200_thread_aux_stream();

@@ -1,7 +1,7 @@
 // msm.cu -- kernels + launcher for VariableBase::msm over BLS12-377 G1 on B200.
 //
 // Pipeline (all on the device, one stream):
-//   pack      : G1Affine images (stride 104) -> 96-byte (x | y), infinity -> (0, 0)
+//   pack      : G1Affine images (stride 104) -> 128-byte records (x | y | pad), infinity -> (0, 0)
 //   count     : signed c-bit digits of every scalar; histogram of (window, bucket)        [atomics in L2]
 //   scan      : exclusive prefix sum of the histogram -> start offset of every bucket
 //   scatter   : point index (+ sign bit) of every non-zero digit into its bucket's slot      [counting sort]
@@ -9,7 +9,7 @@
 //               cross a chunk boundary are stitched by pairwise combine rounds
 //   reduce    : per window, segmented running sum  sum_b (b + 1) * B_b ; block tree per window
 //   fold      : Horner over the windows with c doublings each -> Jacobian result
-// HBM layout: packed bases n * 96 B | entries n * nwin * 4 B | offsets (nwin * 2^(c-1) + 1) * 4 B |
+// HBM layout: packed bases n * 128 B | entries n * nwin * 4 B | offsets (nwin * 2^(c-1) + 1) * 4 B |
 //             buckets nwin * 2^(c-1) * 192 B (XYZZ) | segment sums | window sums.
 #include <cstdlib>
 
@@ -25,7 +25,7 @@
 // ---------------------------------------------------------------------------------------------
 // pack / count / scatter
 // ---------------------------------------------------------------------------------------------
-__global__ void msm_pack_kernel(g1_packed_t* __restrict__ out, const uint8_t* __restrict__ pts, size_t n,
+__global__ void msm_pack_kernel(uint4* __restrict__ out, const uint8_t* __restrict__ pts, size_t n,
                                 size_t stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -42,7 +42,7 @@ __global__ void msm_pack_kernel(g1_packed_t* __restrict__ out, const uint8_t* __
         unsigned long long a = inf ? 0ull : v[2 * k], b = inf ? 0ull : v[2 * k + 1];
         p.w[k] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
     }
-    out[i] = p;
+    g1_store_packed(out + i * G1_BASE_U4, p);
 }
 
 // Warp-aggregated histogram update.  Structural hot spots (the top window of the signed-digit split has only a
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
                                                                         g1_xyzz_mem_t* __restrict__ tails,
                                                                         uint32_t* __restrict__ head_bucket,
                                                                         uint32_t* __restrict__ tail_bucket,
-                                                                        const g1_packed_t* __restrict__ pts,
+                                                                        const uint4* __restrict__ pts,
                                                                         const uint32_t* __restrict__ entries,
                                                                         const uint32_t* __restrict__ offsets,
                                                                         uint32_t* __restrict__ max_heads,
@@ -260,14 +260,14 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
     bool from_start = (offsets[k] == e);
     g1_xyzz_t acc = g1_xyzz_infinity();
     uint32_t cur_id = DIRECT ? e : entries[e];
-    g1_packed_t cur = pts[DIRECT ? cur_id : (cur_id & 0x7fffffffu)];
+    g1_packed_t cur = g1_load_packed(DIRECT ? pts + (size_t)cur_id * G1_LIST_U4 : pts + (size_t)(cur_id & 0x7fffffffu) * G1_BASE_U4);
     for (;;) {
         const uint32_t nxt_e = e + 1;
         uint32_t nxt_id = 0;
         g1_packed_t nxt;
         if (nxt_e < end) {
             nxt_id = DIRECT ? nxt_e : entries[nxt_e];
-            nxt = pts[DIRECT ? nxt_id : (nxt_id & 0x7fffffffu)];
+            nxt = g1_load_packed(DIRECT ? pts + (size_t)nxt_id * G1_LIST_U4 : pts + (size_t)(nxt_id & 0x7fffffffu) * G1_BASE_U4);
         }
         g1_affine_t a = g1_unpack(cur);
         if (!DIRECT && (cur_id >> 31)) a.y = fp_neg(a.y);
@@ -344,17 +344,19 @@ __global__ void msm_half_counts_kernel(uint32_t* __restrict__ cnt, const uint32_
     if (k < K) cnt[k] = (off[k + 1] - off[k] + 1) >> 1;
 }
 
+// both kernels work on the thread range [t0, t1) of the round: a round is issued in slices so that the additions of
+// one slice overlap the denominators of the next
 __global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_denoms_kernel(PairRound rd, uint4* __restrict__ pre,
-                                                                          uint4* __restrict__ partial, uint32_t nthreads) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nthreads) pair_denoms_thread(rd, t, pre, partial);
+                                                                          uint4* __restrict__ partial, uint32_t t0, uint32_t t1) {
+    const uint32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < t1) pair_denoms_thread(rd, t, pre, partial);
 }
 
 __global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_add_kernel(PairRound rd, const uint4* __restrict__ pre,
                                                                        const uint4* __restrict__ partial_inv,
-                                                                       g1_packed_t* __restrict__ out, uint32_t nthreads) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nthreads) pair_add_thread(rd, t, pre, partial_inv, out);
+                                                                       g1_packed_t* __restrict__ out, uint32_t t0, uint32_t t1) {
+    const uint32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < t1) pair_add_thread(rd, t, pre, partial_inv, out);
 }
 
 __global__ void __launch_bounds__(128) fq_inv_up_kernel(uint4* __restrict__ partial, const uint4* __restrict__ data, size_t n) {
@@ -363,16 +365,19 @@ __global__ void __launch_bounds__(128) fq_inv_up_kernel(uint4* __restrict__ part
 __global__ void __launch_bounds__(128) fq_inv_down_kernel(uint4* __restrict__ data, const uint4* __restrict__ partial_inv, size_t n) {
     fq_inv_down_thread(data, partial_inv, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-#define FQ_INV_SMALL_THREADS 512
-__global__ void __launch_bounds__(FQ_INV_SMALL_THREADS) fq_inv_small_kernel(uint4* __restrict__ data, size_t n) {
-    fq_inv_small_thread(data, n, threadIdx.x, FQ_INV_SMALL_THREADS);
+// Tail of the recursion: a Fermat inversion is a chain of ~570 dependent products, so its latency is what counts:
+// one value per thread, one warp per block, so that every warp has an SM sub-partition to itself (0.16 ms).
+#define FQ_INV_TAIL_MAX 16384u
+__global__ void __launch_bounds__(32) fq_inv_tail_kernel(uint4* __restrict__ data, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fq_to_u4x3(fp_inv(pair_load_fq(data + 3 * i)), data + 3 * i);
 }
 
 // in-place inversion of n Fq values, none of them zero
 static b200_error_t fq_batch_inverse_nonzero(uint4* d_data, size_t n, cudaStream_t s) {
     if (n == 0) return b200_ok();
-    if (n <= (size_t)FQ_INV_SMALL_THREADS * MSM_INV_SMALL_PER_THREAD) {
-        fq_inv_small_kernel<<<1, FQ_INV_SMALL_THREADS, 0, s>>>(d_data, n);
+    if (n <= FQ_INV_TAIL_MAX) {
+        fq_inv_tail_kernel<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(d_data, n);
         KERNEL_CHECK();
         return b200_ok();
     }
@@ -482,12 +487,12 @@ __global__ void g1_sum_jacobian_kernel(uint4* __restrict__ out_jac, const uint4*
 // ---------------------------------------------------------------------------------------------
 #define MSM_TABLE_MAX_WINDOWS 17
 
-__global__ void __launch_bounds__(64) msm_window_table_kernel(g1_packed_t* __restrict__ table, size_t n, uint32_t c, uint32_t nwin) {
+__global__ void __launch_bounds__(64) msm_window_table_kernel(uint4* __restrict__ table, size_t n, uint32_t c, uint32_t nwin) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_xyzz_t q[MSM_TABLE_MAX_WINDOWS];
     fq_t pre[MSM_TABLE_MAX_WINDOWS];
-    g1_xyzz_t cur = g1_xyzz_from_affine(g1_unpack(table[i]));
+    g1_xyzz_t cur = g1_xyzz_from_affine(g1_unpack(g1_load_packed(table + i * G1_BASE_U4)));
     fq_t acc = fp_one<FqP>();
     for (uint32_t w = 1; w < nwin; w++) {
         for (uint32_t k = 0; k < c; k++) g1_dbl(cur);
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(64) msm_window_table_kernel(g1_packed_t* __res
             fq_to_u4x3(x, out.w);
             fq_to_u4x3(y, out.w + 3);
         }
-        table[(size_t)w * n + i] = out;
+        g1_store_packed(table + ((size_t)w * n + i) * G1_BASE_U4, out);
     }
 }
 
@@ -517,7 +522,7 @@ b200_error_t msm_build_window_table_device(void* d_table, size_t n, uint32_t c, 
     const uint32_t nwin = msm_shape(c).nwin;
     if (nwin > MSM_TABLE_MAX_WINDOWS) return b200_err(B200_ERR_INVALID_ARG, "msm: window table needs c >= 16");
     if (n == 0) return b200_ok();
-    msm_window_table_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(reinterpret_cast<g1_packed_t*>(d_table), n, c, nwin);
+    msm_window_table_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(reinterpret_cast<uint4*>(d_table), n, c, nwin);
     KERNEL_CHECK();
     return b200_ok();
 }
@@ -532,10 +537,12 @@ extern "C" uint32_t b200_msm_window_bits(size_t n) {
     }
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    // measured sweeps (profiles/r01_msm_sweep_equal_work.json): 2^16 -> 11..13, 2^20 -> 15, 2^24 -> 20
-    int c = (int)lg - (lg >= 22 ? 4 : 5);
+    // measured sweeps with the batched-affine rounds on (gpurun_out/affine_sweep10.log -> profiles/r01_msm_affine_sweep.txt):
+    // 2^20 -> 15, 2^22 -> 17, 2^24 -> 18 (82.7 ms; 17: 83.2, 20: 85.4).  c = 19 is avoided: 253 = 13 * 19 + 6 leaves a
+    // 6-bit top window whose 64 buckets take n atomics each (count 4.6 ms instead of 1.3).
+    int c = (int)lg - 5;
     if (c < 4) c = 4;
-    if (c > 20) c = 20;
+    if (c > 18) c = lg >= 25 ? 20 : 18;
     return (uint32_t)c;
 }
 
@@ -544,7 +551,7 @@ b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t 
     if (n == 0) return b200_ok();
     if (stride < 97 || (stride & 7)) return b200_err(B200_ERR_INVALID_ARG, "msm: affine stride must be >= 104 and 8-byte aligned");
     if (reinterpret_cast<uintptr_t>(d_points) & 7) return b200_err(B200_ERR_INVALID_ARG, "msm: points must be 8-byte aligned");
-    msm_pack_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(reinterpret_cast<g1_packed_t*>(d_packed),
+    msm_pack_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(reinterpret_cast<uint4*>(d_packed),
                                                                       reinterpret_cast<const uint8_t*>(d_points), n, stride);
     KERNEL_CHECK();
     return b200_ok();
@@ -607,6 +614,17 @@ static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n
     return b200_ok();
 }
 
+// events for the fork / join between the caller's stream and the helper stream of one call
+struct EventPool {
+    std::vector<cudaEvent_t> used;
+    cudaError_t get(cudaEvent_t* ev) {
+        cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) used.push_back(*ev);
+        return e;
+    }
+    ~EventPool() { for (cudaEvent_t e : used) cudaEventDestroy(e); }       // deferred by the runtime until complete
+};
+
 // list length after one pair round: sum_k ceil(m_k / 2) <= (E + #non-empty buckets) / 2
 static size_t msm_halved_bound(size_t E, size_t K) { return (E + (K < E ? K : E) + 1) / 2; }
 
@@ -617,11 +635,18 @@ static uint32_t msm_affine_rounds(size_t E, size_t K) {
         int r = atoi(e);
         return r < 0 ? 0u : (r > 30 ? 30u : (uint32_t)r);
     }
-    if (E < ((size_t)1 << 22)) return 0;
+    // round r adds E / 2^(r+1) pairs at ~0.29 ns instead of ~0.40 ns each and costs ~0.7 ms of launches and latency-
+    // bound inversion chains: worth it above ~3.5 M pairs; a fifth round never paid (measured optimum: 2 rounds at
+    // 2^20, 4 at 2^22 and 2^24; the XYZZ finish is cheap on lists of 4..8)
     const size_t avg = E / K;
     uint32_t r = 0;
-    while (r < 6 && (avg >> (r + 1)) >= 2) r++;
+    while (r < 4 && (E >> (r + 1)) >= ((size_t)7 << 19) && (avg >> r) >= 4) r++;
     return r;
+}
+
+extern "C" uint32_t b200_msm_affine_rounds(size_t n) {
+    const MsmShape sh = msm_shape(b200_msm_window_bits(n));
+    return msm_affine_rounds(n * sh.nwin, (size_t)sh.nwin * sh.nbuckets);
 }
 
 // bucket array (K x XYZZ) of one range of points; d_buckets is overwritten
@@ -631,12 +656,12 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     const MsmShape& sh = pl.sh;
     const size_t K = pl.K;
     DevBuf packed, counts, offsets, cursor, entries, heads, tails, head_bucket, tail_bucket, max_heads;
-    const g1_packed_t* pts = reinterpret_cast<const g1_packed_t*>(d_packed);
+    const uint4* pts = reinterpret_cast<const uint4*>(d_packed);
     if (!pts) {
         STAGE("msm_pack", stream);
-        CUDA_TRY(packed.alloc(n * sizeof(g1_packed_t), stream));
+        CUDA_TRY(packed.alloc(n * (size_t)G1_BASE_BYTES, stream));
         B200_TRY(msm_pack_bases_device(packed.p, d_points, n, stride, stream));
-        pts = packed.as<g1_packed_t>();
+        pts = packed.as<uint4>();
     }
     CUDA_TRY(counts.alloc((K + 1) * 4, stream));
     CUDA_TRY(offsets.alloc((K + 1) * 4, stream));
@@ -657,7 +682,7 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     KERNEL_CHECK();
     // ---- batched-affine pair rounds: halve every bucket's list `rounds` times at ~6.3 products per addition ----
     const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
-    const g1_packed_t* acc_pts = pts;
+    const uint4* acc_pts = pts;
     const uint32_t* acc_off = offsets.as<uint32_t>();
     size_t acc_E = E;
     bool direct = false;
@@ -679,6 +704,15 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
             rounds = 0;
         }
     }
+    // A round CAN be issued in slices of its output range (B200_MSM_SLICES > 1): denominators + inversion of a slice
+    // go to the thread's high-priority helper stream, the additions to the caller's stream, so that the gather-bound
+    // first half of slice i + 1 runs under the multiplier-bound second half of slice i.  Measured at 2^24: 84.4 ms
+    // with 1 slice, 85.6 / 86.9 / 89.2 ms with 2 / 3 / 4 -- both halves gather at random and the memory system is what
+    // they share, while every extra slice adds one latency-bound inversion chain.  Default: one slice, one stream.
+    uint32_t max_slices = 1;
+    if (const char* e = getenv("B200_MSM_SLICES")) max_slices = (uint32_t)atoi(e);
+    cudaStream_t aux = rounds && max_slices > 1 ? b200_thread_aux_stream() : nullptr;
+    EventPool events;
     for (uint32_t r = 0; r < rounds; r++) {
         STAGE(r == 0 ? "msm_pairs_round0" : "msm_pairs_rounds", stream);
         const size_t e_out = msm_halved_bound(acc_E, K);
@@ -694,13 +728,36 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
         rd.noff = noff;
         rd.K = (uint32_t)K;
         const uint32_t nthr = (uint32_t)((e_out + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD);
-        const unsigned nblk_p = (nthr + MSM_PAIR_THREADS - 1) / MSM_PAIR_THREADS;
-        msm_pair_denoms_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), nthr);
-        KERNEL_CHECK();
-        B200_TRY(fq_batch_inverse_nonzero(partial.as<uint4>(), nthr, stream));
-        msm_pair_add_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), out, nthr);
-        KERNEL_CHECK();
-        acc_pts = out;
+        uint32_t nslices = aux ? nthr / (1u << 17) : 1;
+        if (nslices < 1) nslices = 1;
+        if (nslices > max_slices) nslices = max_slices;
+        cudaStream_t front = nslices > 1 ? aux : stream;
+        if (front != stream) {
+            cudaEvent_t ev;
+            CUDA_TRY(events.get(&ev));
+            CUDA_TRY(cudaEventRecord(ev, stream));                    // offsets of this round, lists of the previous one
+            CUDA_TRY(cudaStreamWaitEvent(front, ev, 0));
+        }
+        const uint32_t per = ((nthr + nslices - 1) / nslices + MSM_PAIR_THREADS - 1) / MSM_PAIR_THREADS * MSM_PAIR_THREADS;
+        for (uint32_t t0 = 0; t0 < nthr; t0 += per) {
+            const uint32_t t1 = t0 + per < nthr ? t0 + per : nthr;
+            const unsigned nblk_p = (t1 - t0 + MSM_PAIR_THREADS - 1) / MSM_PAIR_THREADS;
+            if (nslices == 1) STAGE(r == 0 ? "msm_pairs0_denoms" : "msm_pairs_denoms", stream);
+            msm_pair_denoms_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, front>>>(rd, pre.as<uint4>(), partial.as<uint4>(), t0, t1);
+            KERNEL_CHECK();
+            if (nslices == 1) STAGE(r == 0 ? "msm_pairs0_invert" : "msm_pairs_invert", stream);
+            B200_TRY(fq_batch_inverse_nonzero(partial.as<uint4>() + 3 * (size_t)t0, t1 - t0, front));
+            if (nslices == 1) STAGE(r == 0 ? "msm_pairs0_add" : "msm_pairs_add", stream);
+            if (front != stream) {
+                cudaEvent_t ev;
+                CUDA_TRY(events.get(&ev));
+                CUDA_TRY(cudaEventRecord(ev, front));
+                CUDA_TRY(cudaStreamWaitEvent(stream, ev, 0));
+            }
+            msm_pair_add_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), out, t0, t1);
+            KERNEL_CHECK();
+        }
+        acc_pts = reinterpret_cast<const uint4*>(out);
         acc_off = noff;
         acc_E = e_out;
         direct = true;

@@ -50,6 +50,22 @@ B200_HD uint32_t msm_signed_digit(const uint32_t* s, uint32_t w, uint32_t c, uin
 
 // 96-byte packed affine point used on the device: x | y (Montgomery), infinity = (0, 0)
 struct g1_packed_t { uint4 w[6]; };
+// The packed BASES (gathered at random by index) sit in 128-byte records, x | y | 32 B pad: an L2 miss on B200 fetches
+// the whole 128-byte line from HBM (ncu: 165 B per 48-byte and 202 B per 96-byte gather from 96-byte records), so a
+// record that never straddles a line costs one line per gather.  Point LISTS (read in order) stay at 96 bytes.
+#define G1_BASE_U4 8u
+#define G1_LIST_U4 6u
+#define G1_BASE_BYTES (16u * G1_BASE_U4)
+B200_HD g1_packed_t g1_load_packed(const uint4* p) {
+    g1_packed_t r;
+    B200_UNROLL
+    for (int k = 0; k < 6; k++) r.w[k] = p[k];
+    return r;
+}
+B200_HD void g1_store_packed(uint4* p, const g1_packed_t& v) {
+    B200_UNROLL
+    for (int k = 0; k < 6; k++) p[k] = v.w[k];
+}
 
 B200_HD g1_affine_t g1_unpack(const g1_packed_t& p) {
     g1_affine_t a;

@@ -28,11 +28,12 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
                                uint32_t c, uint32_t rounds, uint32_t* stats) {
     const MsmShape sh = msm_shape(c);
     const uint32_t K = sh.nwin * sh.nbuckets;
-    std::vector<g1_packed_t> packed(n ? n : 1);
+    std::vector<uint4> packed((n ? n : 1) * G1_BASE_U4);        // 128-byte base records, pad filled with junk
     for (size_t i = 0; i < n; i++) {
         const uint8_t* s = pts + i * stride;
-        memset(&packed[i], 0, sizeof(g1_packed_t));
-        if (!s[96]) memcpy(&packed[i], s, 96);
+        memset(&packed[i * G1_BASE_U4], 0, 96);
+        memset(&packed[i * G1_BASE_U4 + 6], 0xa5, 32);
+        if (!s[96]) memcpy(&packed[i * G1_BASE_U4], s, 96);
     }
     std::vector<std::vector<uint32_t>> lists(K);
     for (size_t i = 0; i < n; i++) {
@@ -61,7 +62,7 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
         }
         noff[K] = tot;
         PairRound rd;
-        rd.src = gathered ? packed.data() : cur.data();
+        rd.src = gathered ? packed.data() : reinterpret_cast<const uint4*>(cur.data());
         rd.entries = gathered ? entries.data() : nullptr;
         rd.off = off.data();
         rd.noff = noff.data();
@@ -83,7 +84,7 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
         for (uint32_t e = off[k]; e < off[k + 1]; e++) {
             g1_affine_t a;
             if (gathered) {
-                a = g1_unpack(packed[entries[e] & 0x7fffffffu]);
+                a = g1_unpack(g1_load_packed(&packed[(size_t)(entries[e] & 0x7fffffffu) * G1_BASE_U4]));
                 if (entries[e] >> 31) a.y = fp_neg(a.y);
             } else {
                 a = g1_unpack(cur[e]);
