@@ -43,8 +43,10 @@ def parse_args():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r01_ncu_full_selected_metrics.txt), valid for the default workload only (2^24, c = 20 / 8+8+8 passes)
-NCU_TRAFFIC_BYTES = {"msm_accumulate_kernel@2^24": 42.036437e9 + 1.545928e9, "ntt_pass_kernel@2^24": 3 * (0.537079e9 + 0.476968e9)}
+# (profiles/r01_ncu_full_selected_metrics.txt, r01_ncu_msm_affine_full.txt), valid for the default workload only (2^24)
+NCU_TRAFFIC_BYTES = {"msm_accumulate_kernel@2^24": 42.036437e9 + 1.545928e9, "ntt_pass_kernel@2^24": 3 * (0.537079e9 + 0.476968e9),
+                     # four launches (pair rounds 0..3) of one 2^24 MSM at c = 18: profiles/r01_ncu_msm_affine_full.txt
+                     "msm_pair_add_kernel@2^24": (41.942319 + 13.571245 + 16.897048 + 6.782277 + 8.588958 + 3.426414 + 4.411751 + 1.746776) * 1e9}
 
 
 def measured_peaks():

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
                                                                         uint32_t* __restrict__ head_bucket,
                                                                         uint32_t* __restrict__ tail_bucket,
                                                                         const uint4* __restrict__ pts,
+                                                                        const uint4* __restrict__ pts_y,
                                                                         const uint32_t* __restrict__ entries,
                                                                         const uint32_t* __restrict__ offsets,
                                                                         uint32_t* __restrict__ max_heads,
@@ -260,14 +261,14 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
     bool from_start = (offsets[k] == e);
     g1_xyzz_t acc = g1_xyzz_infinity();
     uint32_t cur_id = DIRECT ? e : entries[e];
-    g1_packed_t cur = g1_load_packed(DIRECT ? pts + (size_t)cur_id * G1_LIST_U4 : pts + (size_t)(cur_id & 0x7fffffffu) * G1_BASE_U4);
+    g1_packed_t cur = DIRECT ? g1_load_planes(pts + 3 * (size_t)cur_id, pts_y + 3 * (size_t)cur_id) : g1_load_packed(pts + (size_t)(cur_id & 0x7fffffffu) * G1_BASE_U4);
     for (;;) {
         const uint32_t nxt_e = e + 1;
         uint32_t nxt_id = 0;
         g1_packed_t nxt;
         if (nxt_e < end) {
             nxt_id = DIRECT ? nxt_e : entries[nxt_e];
-            nxt = g1_load_packed(DIRECT ? pts + (size_t)nxt_id * G1_LIST_U4 : pts + (size_t)(nxt_id & 0x7fffffffu) * G1_BASE_U4);
+            nxt = DIRECT ? g1_load_planes(pts + 3 * (size_t)nxt_id, pts_y + 3 * (size_t)nxt_id) : g1_load_packed(pts + (size_t)(nxt_id & 0x7fffffffu) * G1_BASE_U4);
         }
         g1_affine_t a = g1_unpack(cur);
         if (!DIRECT && (cur_id >> 31)) a.y = fp_neg(a.y);
@@ -354,9 +355,10 @@ __global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_denoms_kernel(PairR
 
 __global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_add_kernel(PairRound rd, const uint4* __restrict__ pre,
                                                                        const uint4* __restrict__ partial_inv,
-                                                                       g1_packed_t* __restrict__ out, uint32_t t0, uint32_t t1) {
+                                                                       uint4* __restrict__ out_x, uint4* __restrict__ out_y,
+                                                                       uint32_t t0, uint32_t t1) {
     const uint32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < t1) pair_add_thread(rd, t, pre, partial_inv, out);
+    if (t < t1) pair_add_thread(rd, t, pre, partial_inv, out_x, out_y);
 }
 
 __global__ void __launch_bounds__(128) fq_inv_up_kernel(uint4* __restrict__ partial, const uint4* __restrict__ data, size_t n) {
@@ -683,13 +685,14 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     // ---- batched-affine pair rounds: halve every bucket's list `rounds` times at ~6.3 products per addition ----
     const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
     const uint4* acc_pts = pts;
+    const uint4* acc_pts_y = nullptr;                              // lists: plane of y coordinates (x plane = acc_pts)
     const uint32_t* acc_off = offsets.as<uint32_t>();
     size_t acc_E = E;
     bool direct = false;
     DevBuf list_a, list_b, pre, partial, half, off_a, off_b;
     uint32_t rounds = msm_affine_rounds(E, K);
+    const size_t e1 = msm_halved_bound(E, K), e2 = msm_halved_bound(e1, K);
     if (rounds) {
-        const size_t e1 = msm_halved_bound(E, K), e2 = msm_halved_bound(e1, K);
         const size_t t1 = (e1 + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD;
         cudaError_t e = list_a.alloc(e1 * sizeof(g1_packed_t), stream);
         if (e == cudaSuccess && rounds > 1) e = list_b.alloc(e2 * sizeof(g1_packed_t), stream);
@@ -717,12 +720,14 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
         STAGE(r == 0 ? "msm_pairs_round0" : "msm_pairs_rounds", stream);
         const size_t e_out = msm_halved_bound(acc_E, K);
         uint32_t* noff = (r & 1) ? off_b.as<uint32_t>() : off_a.as<uint32_t>();
-        g1_packed_t* out = (r & 1) ? list_b.as<g1_packed_t>() : list_a.as<g1_packed_t>();
+        uint4* out_x = (r & 1) ? list_b.as<uint4>() : list_a.as<uint4>();
+        uint4* out_y = out_x + 3 * ((r & 1) ? e2 : e1);                // plane of y coordinates behind the x plane
         msm_half_counts_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(half.as<uint32_t>(), acc_off, (uint32_t)K);
         KERNEL_CHECK();
         B200_TRY(exclusive_scan(noff, half.as<uint32_t>(), K, stream));
         PairRound rd;
         rd.src = acc_pts;
+        rd.src_y = acc_pts_y;
         rd.entries = direct ? nullptr : entries.as<uint32_t>();
         rd.off = acc_off;
         rd.noff = noff;
@@ -754,10 +759,11 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
                 CUDA_TRY(cudaEventRecord(ev, front));
                 CUDA_TRY(cudaStreamWaitEvent(stream, ev, 0));
             }
-            msm_pair_add_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), out, t0, t1);
+            msm_pair_add_kernel<<<nblk_p, MSM_PAIR_THREADS, 0, stream>>>(rd, pre.as<uint4>(), partial.as<uint4>(), out_x, out_y, t0, t1);
             KERNEL_CHECK();
         }
-        acc_pts = reinterpret_cast<const uint4*>(out);
+        acc_pts = out_x;
+        acc_pts_y = out_y;
         acc_off = noff;
         acc_E = e_out;
         direct = true;
@@ -781,11 +787,11 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     if (direct)
         msm_accumulate_kernel<true><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
             d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-            tail_bucket.as<uint32_t>(), acc_pts, nullptr, acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
+            tail_bucket.as<uint32_t>(), acc_pts, acc_pts_y, nullptr, acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
     else
         msm_accumulate_kernel<false><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
             d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-            tail_bucket.as<uint32_t>(), pts, entries.as<uint32_t>(), acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
+            tail_bucket.as<uint32_t>(), pts, nullptr, entries.as<uint32_t>(), acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
     KERNEL_CHECK();
     STAGE("msm_combine", stream);
     const size_t max_span = (n + chunk - 1) / chunk + 1;            // a bucket holds at most n entries

@@ -33,7 +33,9 @@
 #endif
 
 struct PairRound {
-    const uint4* src;            // round 0: packed bases (128-byte records); later: the previous round's list (96-byte)
+    const uint4* src;            // round 0: packed bases (128-byte records x | y | pad); later: x list of the previous round
+    const uint4* src_y;          // later rounds: y list (lists are two planes of 48-byte coordinates, so that the
+                                 // denominator pass reads x only); unused in round 0
     const uint32_t* entries;     // round 0: sorted (index | sign << 31); nullptr afterwards
     const uint32_t* off;         // K + 1 offsets of the input lists
     const uint32_t* noff;        // K + 1 offsets of the output lists, noff[b+1] - noff[b] = ceil(count_b / 2)
@@ -54,19 +56,42 @@ B200_HD uint32_t pair_locate(const uint32_t* noff, uint32_t K, uint32_t q) {
 
 B200_HD fq_t pair_load_fq(const uint4* w) { return fq_from_u4x3(w); }
 
-// x (and on demand y, sign applied) of input slot i
-B200_HD const uint4* pair_slot(const PairRound& rd, uint32_t i, uint32_t& neg) {
+// where the coordinates of input slot i live (and the sign its y takes)
+struct PairSlot {
+    const uint4* x;
+    const uint4* y;
+    uint32_t neg;
+};
+B200_HD PairSlot pair_slot(const PairRound& rd, uint32_t i) {
+    PairSlot s;
     if (rd.entries) {
         const uint32_t id = rd.entries[i];
-        neg = id >> 31;
-        return rd.src + (size_t)(id & 0x7fffffffu) * G1_BASE_U4;
+        s.neg = id >> 31;
+        s.x = rd.src + (size_t)(id & 0x7fffffffu) * G1_BASE_U4;
+        s.y = s.x + 3;
+    } else {
+        s.neg = 0;
+        s.x = rd.src + 3 * (size_t)i;
+        s.y = rd.src_y + 3 * (size_t)i;
     }
-    neg = 0;
-    return rd.src + (size_t)i * G1_LIST_U4;
+    return s;
 }
-B200_HD fq_t pair_slot_y(const uint4* p, uint32_t neg) {
-    fq_t y = pair_load_fq(p + 3);
-    return neg ? fp_neg(y) : y;
+B200_HD fq_t pair_slot_y(const PairSlot& s) {
+    fq_t y = pair_load_fq(s.y);
+    return s.neg ? fp_neg(y) : y;
+}
+
+// both coordinates of a slot, sign applied (base records: three 256-bit loads)
+B200_HD void pair_load_point(const PairRound& rd, const PairSlot& s, fq_t& x, fq_t& y) {
+    if (rd.entries) {
+        const g1_affine_t a = g1_load_base(s.x);
+        x = a.x;
+        y = a.y;
+    } else {
+        x = pair_load_fq(s.x);
+        y = pair_load_fq(s.y);
+    }
+    if (s.neg) y = fp_neg(y);
 }
 
 // classification of the pair (A, B) and its denominator; y's already carry their signs
@@ -120,15 +145,14 @@ B200_HD void pair_denoms_thread(const PairRound& rd, uint32_t t, uint4* pre, uin
         pair_walk_to(rd, w, q, i0, has2);
         fq_to_u4x3(acc, pre + 3 * (size_t)q);
         if (!has2) continue;
-        uint32_t n1, n2;
-        const uint4* A = pair_slot(rd, i0, n1);
-        const uint4* B = pair_slot(rd, i0 + 1, n2);
-        const fq_t x1 = pair_load_fq(A), x2 = pair_load_fq(B);
+        const PairSlot A = pair_slot(rd, i0), B = pair_slot(rd, i0 + 1);
+        const fq_t x1 = rd.entries ? g1_load_base_x(A.x) : pair_load_fq(A.x);
+        const fq_t x2 = rd.entries ? g1_load_base_x(B.x) : pair_load_fq(B.x);
         fq_t d;
         if (!fp_is_zero(x1) && !fp_is_zero(x2) && !fp_eq(x1, x2)) {
             d = fp_sub(x2, x1);                                    // the only case random inputs ever see
         } else {
-            const fq_t y1 = pair_slot_y(A, n1), y2 = pair_slot_y(B, n2);
+            const fq_t y1 = pair_slot_y(A), y2 = pair_slot_y(B);
             const int kind = pair_classify(x1, y1, x2, y2, true);
             if (kind == PAIR_ADD) d = fp_sub(x2, x1);
             else if (kind == PAIR_DBL) d = fp_dbl(y1);
@@ -141,7 +165,7 @@ B200_HD void pair_denoms_thread(const PairRound& rd, uint32_t t, uint4* pre, uin
 
 // step 3: the additions, walking the same outputs backwards with the inverted thread products
 B200_HD void pair_add_thread(const PairRound& rd, uint32_t t, const uint4* pre, const uint4* partial_inv,
-                             g1_packed_t* out) {
+                             uint4* out_x, uint4* out_y) {
     const uint32_t total = rd.noff[rd.K];
     const unsigned long long q0l = (unsigned long long)t * MSM_PAIRS_PER_THREAD;
     if (q0l >= total) return;
@@ -159,16 +183,10 @@ B200_HD void pair_add_thread(const PairRound& rd, uint32_t t, const uint4* pre, 
         }
         const uint32_t i0 = ob + 2 * (q - nb);
         const bool has2 = i0 + 1 < oe;
-        uint32_t n1, n2 = 0;
-        const uint4* A = pair_slot(rd, i0, n1);
-        const fq_t x1 = pair_load_fq(A);
-        const fq_t y1 = pair_slot_y(A, n1);
+        fq_t x1, y1;
+        pair_load_point(rd, pair_slot(rd, i0), x1, y1);
         fq_t x2 = x1, y2 = y1;
-        if (has2) {
-            const uint4* B = pair_slot(rd, i0 + 1, n2);
-            x2 = pair_load_fq(B);
-            y2 = pair_slot_y(B, n2);
-        }
+        if (has2) pair_load_point(rd, pair_slot(rd, i0 + 1), x2, y2);
         const int kind = pair_classify(x1, y1, x2, y2, has2);
         fq_t x3, y3;
         if (kind == PAIR_ADD || kind == PAIR_DBL) {
@@ -196,9 +214,8 @@ B200_HD void pair_add_thread(const PairRound& rd, uint32_t t, const uint4* pre, 
             x3 = fp_zero<FqP>();
             y3 = fp_zero<FqP>();
         }
-        g1_packed_t* o = out + q;
-        fq_to_u4x3(x3, o->w);
-        fq_to_u4x3(y3, o->w + 3);
+        fq_to_u4x3(x3, out_x + 3 * (size_t)q);
+        fq_to_u4x3(y3, out_y + 3 * (size_t)q);
     }
 }
 

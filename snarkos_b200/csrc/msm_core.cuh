@@ -52,14 +52,42 @@ B200_HD uint32_t msm_signed_digit(const uint32_t* s, uint32_t w, uint32_t c, uin
 struct g1_packed_t { uint4 w[6]; };
 // The packed BASES (gathered at random by index) sit in 128-byte records, x | y | 32 B pad: an L2 miss on B200 fetches
 // the whole 128-byte line from HBM (ncu: 165 B per 48-byte and 202 B per 96-byte gather from 96-byte records), so a
-// record that never straddles a line costs one line per gather.  Point LISTS (read in order) stay at 96 bytes.
+// record that never straddles a line costs one line per gather.  Point LISTS (read in order) are two planes of
+// 48-byte coordinates (x plane, y plane).
 #define G1_BASE_U4 8u
-#define G1_LIST_U4 6u
 #define G1_BASE_BYTES (16u * G1_BASE_U4)
 B200_HD g1_packed_t g1_load_packed(const uint4* p) {
     g1_packed_t r;
     B200_UNROLL
     for (int k = 0; k < 6; k++) r.w[k] = p[k];
+    return r;
+}
+// affine point of a 128-byte base record with three 256-bit loads (x | y = bytes 0..95 of a 32-byte aligned record)
+B200_HD g1_affine_t g1_load_base(const uint4* rec) {
+    uint32_t w[24];
+    ptx::ld_global_256(rec, w);
+    ptx::ld_global_256(rec + 2, w + 8);
+    ptx::ld_global_256(rec + 4, w + 16);
+    g1_affine_t a;
+    B200_UNROLL
+    for (int k = 0; k < 12; k++) { a.x.v[k] = w[k]; a.y.v[k] = w[12 + k]; }
+    return a;
+}
+// x coordinate only: one 256-bit and one 128-bit load
+B200_HD fq_t g1_load_base_x(const uint4* rec) {
+    uint32_t w[8];
+    ptx::ld_global_256(rec, w);
+    const uint4 t = rec[2];
+    fq_t x;
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) x.v[k] = w[k];
+    x.v[8] = t.x; x.v[9] = t.y; x.v[10] = t.z; x.v[11] = t.w;
+    return x;
+}
+B200_HD g1_packed_t g1_load_planes(const uint4* x, const uint4* y) {
+    g1_packed_t r;
+    B200_UNROLL
+    for (int k = 0; k < 3; k++) { r.w[k] = x[k]; r.w[3 + k] = y[k]; }
     return r;
 }
 B200_HD void g1_store_packed(uint4* p, const g1_packed_t& v) {

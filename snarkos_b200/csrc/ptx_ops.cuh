@@ -76,7 +76,22 @@ __device__ __forceinline__ unsigned long long mul_wide(uint32_t a, uint32_t b) {
     unsigned long long r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
 }
 
+// 256-bit global load / store (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256), p 32-byte aligned: one request per 32-byte
+// sector instead of two 16-byte ones -- the gather-bound MSM kernels are limited by outstanding sector requests
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t* r) {
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "l"(p)
+                 : "memory");
+}
+
 #else  // ---------------------------------------------------------------- host emulation
+static inline void ld_global_256(const void* p, uint32_t* r) { __builtin_memcpy(r, p, 32); }
+static inline void st_global_256(void* p, const uint32_t* r) { __builtin_memcpy(p, r, 32); }
 
 static thread_local uint32_t CF = 0;   // the PTX condition-code carry flag CC.CF
 

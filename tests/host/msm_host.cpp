@@ -51,7 +51,7 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
     }
     off[K] = (uint32_t)entries.size();
 
-    std::vector<g1_packed_t> cur;           // list of the current round (empty: still the gather form)
+    std::vector<uint4> cur_x, cur_y;        // planes of the current round's list (empty: still the gather form)
     bool gathered = true;
     for (uint32_t r = 0; r < rounds; r++) {
         std::vector<uint32_t> noff(K + 1);
@@ -62,18 +62,20 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
         }
         noff[K] = tot;
         PairRound rd;
-        rd.src = gathered ? packed.data() : reinterpret_cast<const uint4*>(cur.data());
+        rd.src = gathered ? packed.data() : cur_x.data();
+        rd.src_y = gathered ? nullptr : cur_y.data();
         rd.entries = gathered ? entries.data() : nullptr;
         rd.off = off.data();
         rd.noff = noff.data();
         rd.K = K;
         const uint32_t T = (tot + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD + 2;     // + idle threads past the end
         std::vector<uint4> pre(3 * (size_t)(tot ? tot : 1)), partial(3 * (size_t)T);
-        std::vector<g1_packed_t> next(tot ? tot : 1);
+        std::vector<uint4> next_x(3 * (size_t)(tot ? tot : 1)), next_y(3 * (size_t)(tot ? tot : 1));
         for (uint32_t t = 0; t < T; t++) pair_denoms_thread(rd, t, pre.data(), partial.data());
         invert_all(partial, T);
-        for (uint32_t t = 0; t < T; t++) pair_add_thread(rd, t, pre.data(), partial.data(), next.data());
-        cur.swap(next);
+        for (uint32_t t = 0; t < T; t++) pair_add_thread(rd, t, pre.data(), partial.data(), next_x.data(), next_y.data());
+        cur_x.swap(next_x);
+        cur_y.swap(next_y);
         off.swap(noff);
         gathered = false;
         if (stats) stats[r] = tot;
@@ -87,7 +89,7 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
                 a = g1_unpack(g1_load_packed(&packed[(size_t)(entries[e] & 0x7fffffffu) * G1_BASE_U4]));
                 if (entries[e] >> 31) a.y = fp_neg(a.y);
             } else {
-                a = g1_unpack(cur[e]);
+                a = g1_unpack(g1_load_planes(&cur_x[3 * (size_t)e], &cur_y[3 * (size_t)e]));
             }
             g1_madd(acc, a);
         }
