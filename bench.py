@@ -35,8 +35,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=24, help="log2 of MSM points and NTT elements per GPU")
-    ap.add_argument("--cpu-msm-log-n", type=int, default=18, help="bounded CPU-baseline MSM sample")
-    ap.add_argument("--cpu-ntt-log-n", type=int, default=22, help="bounded CPU-baseline NTT sample")
+    ap.add_argument("--cpu-msm-log-n", type=int, default=22, help="bounded CPU-baseline MSM sample")
+    ap.add_argument("--cpu-ntt-log-n", type=int, default=24, help="bounded CPU-baseline NTT sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

@@ -202,7 +202,11 @@ static cudaStream_t b200_thread_copy_stream() {
     return t_copy_stream.s;
 }
 
-#define MSM_HOST_CHUNK_LOG 22       // host-buffer calls with >= 2^23 points stream the inputs in 2^22-point ranges
+// host-buffer calls with >= 2^23 points stream the inputs in point ranges that grow geometrically: 2^20, 2^20, 2^21,
+// ... capped at 2^23.  Only the first (small) range crosses PCIe with nothing to overlap; every later range is twice the
+// one being accumulated, and a range takes about twice as long to accumulate as to transfer (~5 vs ~2.5 ns per point).
+#define MSM_HOST_FIRST_LOG 20
+#define MSM_HOST_CHUNK_LOG 23
 
 extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, size_t n, const void* scalars,
                                               size_t stride) {
@@ -212,7 +216,7 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     cudaStream_t s = b200_thread_stream();
     if (!s) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
     const size_t chunk = (size_t)1 << MSM_HOST_CHUNK_LOG;
-    if (n < 2 * chunk || getenv("B200_MSM_NO_HOST_PIPELINE")) {
+    if (n < chunk || getenv("B200_MSM_NO_HOST_PIPELINE")) {
         DevBuf d_pts, d_sc, d_out;
         CUDA_TRY(d_pts.alloc(n * stride, s));
         CUDA_TRY(d_sc.alloc(n * 32, s));
@@ -231,7 +235,15 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     // is reduced and folded once at the end.
     cudaStream_t cs = b200_thread_copy_stream();
     if (!cs) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
-    const size_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<size_t> range_off, range_cnt;
+    for (size_t done = 0, cur = (size_t)1 << MSM_HOST_FIRST_LOG; done < n;) {
+        const size_t cnt = n - done < cur ? n - done : cur;
+        range_off.push_back(done);
+        range_cnt.push_back(cnt);
+        done += cnt;
+        if (range_off.size() > 1 && cur < chunk) cur <<= 1;
+    }
+    const size_t nchunks = range_off.size();
     DevBuf d_pts[2], d_sc[2], d_out;
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(d_pts[b].alloc(chunk * stride, s));
@@ -255,7 +267,7 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     }
     for (size_t i = 0; i < nchunks && rc.code == 0; i++) {
         const int b = (int)(i & 1);
-        const size_t off = i * chunk, cnt = (n - off < chunk) ? n - off : chunk;
+        const size_t off = range_off[i], cnt = range_cnt[i];
         cudaError_t e = cudaSuccess;
         if (i >= 2) e = cudaStreamWaitEvent(cs, computed[i - 2], 0);        // staging buffer b is free again
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_pts[b].p, (const uint8_t*)points + off * stride, cnt * stride, cudaMemcpyHostToDevice, cs);

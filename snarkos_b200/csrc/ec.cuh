@@ -165,6 +165,36 @@ B200_HD void g1_xyzz_to_jacobian(const g1_xyzz_t& p, fq_t& X, fq_t& Y, fq_t& Z) 
     Z = p.ZZZ;
 }
 
+// Jacobian doubling for a = 0 (dbl-2009-l: 2M + 5S = 7 products against the 9 of the XYZZ doubling), used where a
+// long run of doublings sits on ONE thread's critical path (the window fold: 253 - c dependent doublings).
+// Z = 0 (infinity) maps to Z = 0.
+B200_HD void g1_jac_dbl(fq_t& X, fq_t& Y, fq_t& Z) {
+    const fq_t A = fp_sqr(X);
+    const fq_t B = fp_sqr(Y);
+    const fq_t C = fp_sqr(B);
+    const fq_t XB = fp_add(X, B);
+    const fq_t D = fp_dbl(fp_sub(fp_sub(fp_sqr(XB), A), C));
+    const fq_t E = fp_add(fp_dbl(A), A);
+    const fq_t F = fp_sqr(E);
+    const fq_t Z3 = fp_dbl(fp_mul(Y, Z));
+    X = fp_sub(F, fp_dbl(D));
+    const fq_t C8 = fp_dbl(fp_dbl(fp_dbl(C)));
+    Y = fp_sub(fp_mul(E, fp_sub(D, X)), C8);
+    Z = Z3;
+}
+// p <- 2^k p through Jacobian coordinates (4 products in, 2 out, 7 per doubling)
+B200_HD void g1_dbl_k(g1_xyzz_t& p, uint32_t k) {
+    if (g1_xyzz_is_infinity(p) || k == 0) return;
+    fq_t X, Y, Z;
+    g1_xyzz_to_jacobian(p, X, Y, Z);
+    for (uint32_t i = 0; i < k; i++) g1_jac_dbl(X, Y, Z);
+    if (fp_is_zero(Z)) { p = g1_xyzz_infinity(); return; }       // only for a point of order 2^j (y = 0 on the way)
+    p.X = X;
+    p.Y = Y;
+    p.ZZ = fp_sqr(Z);
+    p.ZZZ = fp_mul(p.ZZ, Z);
+}
+
 // XYZZ -> affine (one Fermat inversion; utility paths only)
 B200_HD g1_affine_t g1_xyzz_to_affine(const g1_xyzz_t& p) {
     if (g1_xyzz_is_infinity(p)) return g1_affine_infinity();

@@ -367,12 +367,13 @@ __global__ void __launch_bounds__(128) fq_inv_up_kernel(uint4* __restrict__ part
 __global__ void __launch_bounds__(128) fq_inv_down_kernel(uint4* __restrict__ data, const uint4* __restrict__ partial_inv, size_t n) {
     fq_inv_down_thread(data, partial_inv, n, (size_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-// Tail of the recursion: a Fermat inversion is a chain of ~570 dependent products, so its latency is what counts:
-// one value per thread, one warp per block, so that every warp has an SM sub-partition to itself (0.16 ms).
+// Tail of the recursion: what counts is the latency of one inversion.  Binary extended Euclid (fp_inv_gcd: ALU pipe,
+// ~550 iterations of ~130 instructions) instead of the Fermat ladder (~570 dependent Fq products, 0.52 ms per round
+// measured); one value per thread, one warp per block, so that every warp has an SM sub-partition to itself.
 #define FQ_INV_TAIL_MAX 16384u
 __global__ void __launch_bounds__(32) fq_inv_tail_kernel(uint4* __restrict__ data, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) fq_to_u4x3(fp_inv(pair_load_fq(data + 3 * i)), data + 3 * i);
+    if (i < n) fq_to_u4x3(fp_inv_gcd(pair_load_fq(data + 3 * i)), data + 3 * i);
 }
 
 // in-place inversion of n Fq values, none of them zero
@@ -637,12 +638,12 @@ static uint32_t msm_affine_rounds(size_t E, size_t K) {
         int r = atoi(e);
         return r < 0 ? 0u : (r > 30 ? 30u : (uint32_t)r);
     }
-    // round r adds E / 2^(r+1) pairs at ~0.29 ns instead of ~0.40 ns each and costs ~0.7 ms of launches and latency-
-    // bound inversion chains: worth it above ~3.5 M pairs; a fifth round never paid (measured optimum: 2 rounds at
-    // 2^20, 4 at 2^22 and 2^24; the XYZZ finish is cheap on lists of 4..8)
+    // round r adds E / 2^(r+1) pairs at ~0.29 ns instead of ~0.40 ns each and costs ~0.4 ms of launches and the
+    // latency-bound inversion chain: worth it above ~3.5 M pairs (measured optimum: 0 rounds at 2^18, 2 at 2^20,
+    // 4 at 2^22, 5 at 2^24; the XYZZ finish is cheap on lists of 4..8)
     const size_t avg = E / K;
     uint32_t r = 0;
-    while (r < 4 && (E >> (r + 1)) >= ((size_t)7 << 19) && (avg >> r) >= 4) r++;
+    while (r < 5 && (E >> (r + 1)) >= ((size_t)7 << 19) && (avg >> r) >= 4) r++;
     return r;
 }
 

@@ -157,7 +157,7 @@ B200_HD g1_xyzz_t msm_reduce_segment(const g1_xyzz_mem_t* buckets, uint32_t s0, 
 B200_HD g1_xyzz_t msm_fold_windows(const g1_xyzz_mem_t* wsum, uint32_t nwin, uint32_t c) {
     g1_xyzz_t total = g1_xyzz_infinity();
     for (uint32_t w = nwin; w-- > 0;) {
-        for (uint32_t k = 0; k < c; k++) g1_dbl(total);
+        g1_dbl_k(total, c);
         g1_xyzz_t s = g1_xyzz_load(wsum + w);
         g1_add(total, s);
     }

@@ -44,6 +44,8 @@ UNOP(host_fr_neg, FrP, fp_neg<FrP>)
 UNOP(host_fq_neg, FqP, fp_neg<FqP>)
 UNOP(host_fr_inv, FrP, fp_inv<FrP>)
 UNOP(host_fq_inv, FqP, fp_inv<FqP>)
+UNOP(host_fr_inv_gcd, FrP, fp_inv_gcd<FrP>)
+UNOP(host_fq_inv_gcd, FqP, fp_inv_gcd<FqP>)
 UNOP(host_fr_to_mont, FrP, fp_to_mont<FrP>)
 UNOP(host_fr_from_mont, FrP, fp_from_mont<FrP>)
 
@@ -89,6 +91,13 @@ void host_g1_mul_u64(uint8_t* out_jac, const uint8_t* pt, uint64_t k) {
 void host_g1_dbl(uint8_t* out_jac, const uint8_t* pt) {
     g1_xyzz_t p = g1_xyzz_from_affine(ld_aff(pt));
     g1_dbl(p);
+    st_jac(out_jac, p);
+}
+// 2^k * P through the Jacobian doubling run used by the window fold
+void host_g1_dbl_k(uint8_t* out_jac, const uint8_t* pt, uint32_t k) {
+    g1_xyzz_t p = g1_xyzz_from_affine(ld_aff(pt));
+    g1_dbl(p);                       // start from a non-trivial XYZZ representation (ZZ, ZZZ != 1)
+    g1_dbl_k(p, k);
     st_jac(out_jac, p);
 }
 // affine normalisation on the "device" code path: Jacobian-free (x, y) from XYZZ of k * P

@@ -225,7 +225,7 @@ def test_tabulated_resident_bases(window_bits):
 
 
 def test_host_buffer_streaming_path():
-    """host-buffer calls with >= 2^23 points stream 2^22-point ranges into one bucket array (copy of range i+1
+    """host-buffer calls with >= 2^23 points stream geometrically growing point ranges (2^20, 2^20, 2^21, ...) into one bucket array (copy of range i+1
     overlapped with the accumulation of range i); exact identity check incl. a ragged last range"""
     import torch
     import snarkos_b200 as S

@@ -71,6 +71,10 @@ def test_field_ops(hostlib, name, mod, bits, nl, rinv):
     for x, xi in zip(a[:40] + e, inv):
         want = 0 if x == 0 else pow(x * rinv % mod, -1, mod) * R % mod
         assert xi == want
+    # binary extended Euclid (the batch-inversion tail of the MSM pair rounds): same Montgomery inverse, 0 -> 0
+    xs = a[:600] + e
+    inv = _un(hostlib, f"host_{name}_inv_gcd", xs, nl)
+    assert inv == [0 if x == 0 else pow(x * rinv % mod, -1, mod) * R % mod for x in xs]
 
 
 def test_fr_mont_conversions(hostlib):
@@ -131,3 +135,16 @@ def test_g1_add_tree_dbl_mul(hostlib):
         aff = np.zeros(104, dtype=np.uint8)
         hostlib.host_g1_mul_u64_affine(_p(aff), _p(g), ctypes.c_uint64(k), ctypes.c_size_t(104))
         assert O.affine_from_bytes(bytes(aff)) == O.g1_mul(O.G1_GEN, k)
+
+
+def test_g1_jacobian_doubling_run(hostlib):
+    """g1_dbl_k (dbl-2009-l in Jacobian, a = 0) against the oracle: 2^(k+1) * P, and infinity stays infinity"""
+    rng = O.SplitMix64(9)
+    pts = O.random_points(rng, 3)
+    for p in pts:
+        b = H.bases_array([p])
+        for k in (0, 1, 2, 11, 18):
+            got = _jac(lambda out: hostlib.host_g1_dbl_k(_p(out), _p(b), ctypes.c_uint32(k)))
+            assert got == O.g1_mul(p, 1 << (k + 1))
+    inf = H.bases_array([None])
+    assert _jac(lambda out: hostlib.host_g1_dbl_k(_p(out), _p(inf), ctypes.c_uint32(7))) is None
