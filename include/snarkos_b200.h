@@ -153,6 +153,22 @@ b200_error_t b200_fr_mul_powers_device(void* d_data, uint32_t log_n, int directi
                                        unsigned long long rows, unsigned long long cols,
                                        unsigned long long row_base, unsigned long long col_base, void* stream);
 
+/* Fused exchange of the four-step NTT ("fuse twiddle multiply into the pack kernel", all-to-all over
+ * NVLink): the local slab [r_local x c] (row-major, 32 B Montgomery Fr) of a matrix distributed by rows over `world`
+ * ranks is transposed, optionally multiplied by w_N^((row_base + r) * col), and every element is written straight to
+ * its place in the [c / world x r_local * world] slab of the rank that owns its column.  dst_ptrs: HOST array of `world`
+ * device pointers, dst_ptrs[d] = that rank's destination slab (this rank's own buffer for d == rank, peer memory opened
+ * with b200_peer_buffer_open otherwise).  The caller separates writers and readers of a buffer with a barrier. */
+b200_error_t b200_fr_exchange_transpose_device(const void* d_src, void* const* dst_ptrs, uint32_t world, uint32_t rank,
+                                               unsigned long long r_local, unsigned long long c, uint32_t log_n,
+                                               int direction, int twiddle, unsigned long long row_base, void* stream);
+/* Exchange buffers: cudaMalloc memory with its 64-byte CUDA IPC handle (sent to the other ranks by the caller), the
+ * mapping of a peer's buffer into this process, and their release. */
+b200_error_t b200_peer_buffer_alloc(size_t bytes, void** d_ptr, void* handle64);
+b200_error_t b200_peer_buffer_open(const void* handle64, void** d_ptr);
+b200_error_t b200_peer_buffer_close(void* d_ptr);
+b200_error_t b200_peer_buffer_free(void* d_ptr);
+
 /* ---- synthetic inputs & diagnostics (used by bench.py / tests; not on the snarkVM call path) ---- */
 /* points[i] = k_i * G with k_i = splitmix64(seed, i), written as G1Affine images (Montgomery). */
 b200_error_t b200_g1_synthetic_bases_device(void* d_out_points, size_t npoints, size_t affine_stride,

@@ -733,6 +733,8 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
         rd.off = acc_off;
         rd.noff = noff;
         rd.K = (uint32_t)K;
+        rd.idx_mask = 0x7fffffffu;
+        if (const char* e = getenv("B200_DEBUG_IDX_MASK")) rd.idx_mask = (uint32_t)strtoul(e, nullptr, 0);
         const uint32_t nthr = (uint32_t)((e_out + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD);
         uint32_t nslices = aux ? nthr / (1u << 17) : 1;
         if (nslices < 1) nslices = 1;

@@ -220,6 +220,123 @@ extern "C" b200_error_t b200_fr_mul_powers_device(void* d_data, uint32_t log_n, 
     return b200_ok();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused exchange of the multi-GPU four-step NTT: transpose + all-to-all (+ the twiddle between the two transform
+// axes) in ONE pass.  The local slab [r_local x c] of a row-distributed matrix is read in 32 x 32 tiles (coalesced
+// rows), optionally multiplied by w_N^(row * col), transposed through shared memory and every column of the tile is
+// written as a run of 32 x 32 B straight to its place in the [c / world x r_local * world] slab of the rank that owns
+// that column -- peer memory over NVLink when that rank is another GPU (dst[d] = that rank's buffer, opened through
+// CUDA IPC).  Replaces: local re-tiling pass, NCCL all-to-all, second re-tiling pass and the separate twiddle pass.
+// ---------------------------------------------------------------------------------------------
+#define NTT_XCHG_MAX_WORLD 16
+#define NTT_XCHG_TILE 32
+struct NttExchangeParams {
+    const uint4* src;
+    uint4* dst[NTT_XCHG_MAX_WORLD];
+    const uint4* pow_lo;
+    const uint4* pow_hi;
+    unsigned long long r_local, c, c_local, row_base;
+    uint32_t rank, world, log_n, twiddle;
+};
+
+__global__ void __launch_bounds__(256) ntt_exchange_transpose_kernel(NttExchangeParams p) {
+    __shared__ uint4 sm_lo[NTT_XCHG_TILE][NTT_XCHG_TILE + 1];
+    __shared__ uint4 sm_hi[NTT_XCHG_TILE][NTT_XCHG_TILE + 1];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * NTT_XCHG_TILE, r0 = (unsigned long long)blockIdx.y * NTT_XCHG_TILE;
+    for (uint32_t rr = ty; rr < NTT_XCHG_TILE; rr += 8) {
+        const unsigned long long row = r0 + rr, col = c0 + tx;
+        if (row < p.r_local && col < p.c) {
+            fr_t x = fr_load(p.src, row * p.c + col);
+            if (p.twiddle) {
+                const unsigned long long e = ((p.row_base + row) * col) & ((1ull << p.log_n) - 1);
+                if (e) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, e));
+            }
+            fr_to_u4(x, sm_lo[rr][tx], sm_hi[rr][tx]);
+        }
+    }
+    __syncthreads();
+    const unsigned long long R = p.r_local * p.world;
+    for (uint32_t cc = ty; cc < NTT_XCHG_TILE; cc += 8) {
+        const unsigned long long col = c0 + cc, row = r0 + tx;
+        if (row < p.r_local && col < p.c) {
+            const unsigned long long d = col / p.c_local, cl = col - d * p.c_local;
+            uint4* out = p.dst[d] + 2 * (cl * R + (unsigned long long)p.rank * p.r_local + row);
+            out[0] = sm_lo[tx][cc];
+            out[1] = sm_hi[tx][cc];
+        }
+    }
+}
+
+extern "C" b200_error_t b200_fr_exchange_transpose_device(const void* d_src, void* const* dst_ptrs, uint32_t world,
+                                                          uint32_t rank, unsigned long long r_local, unsigned long long c,
+                                                          uint32_t log_n, int direction, int twiddle,
+                                                          unsigned long long row_base, void* stream) {
+    B200_TRY(b200_require_device());
+    if (world == 0 || world > NTT_XCHG_MAX_WORLD || rank >= world || (direction != 0 && direction != 1) || log_n > NTT_MAX_LOG_N)
+        return b200_err(B200_ERR_INVALID_ARG, "fr_exchange_transpose: bad argument");
+    if (r_local == 0 || c == 0) return b200_ok();
+    if (c % world) return b200_err(B200_ERR_INVALID_ARG, "fr_exchange_transpose: columns must divide by the world size");
+    if (!d_src || !dst_ptrs) return b200_err(B200_ERR_INVALID_ARG, "fr_exchange_transpose: null pointer");
+    NttExchangeParams p;
+    memset(&p, 0, sizeof(p));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (twiddle) {
+        NttDomainTables tabs;
+        const uint4* tile_tw = nullptr;
+        B200_TRY(get_tables(log_n, direction, s, &tabs, &tile_tw));
+        p.pow_lo = tabs.pow_lo;
+        p.pow_hi = tabs.pow_hi;
+    }
+    p.src = reinterpret_cast<const uint4*>(d_src);
+    for (uint32_t d = 0; d < world; d++) {
+        if (!dst_ptrs[d]) return b200_err(B200_ERR_INVALID_ARG, "fr_exchange_transpose: null destination");
+        p.dst[d] = reinterpret_cast<uint4*>(dst_ptrs[d]);
+    }
+    p.r_local = r_local;
+    p.c = c;
+    p.c_local = c / world;
+    p.row_base = row_base;
+    p.rank = rank;
+    p.world = world;
+    p.log_n = log_n;
+    p.twiddle = twiddle ? 1u : 0u;
+    const dim3 grid((unsigned)((c + NTT_XCHG_TILE - 1) / NTT_XCHG_TILE), (unsigned)((r_local + NTT_XCHG_TILE - 1) / NTT_XCHG_TILE));
+    if (grid.y > 65535) return b200_err(B200_ERR_TOO_LARGE, "fr_exchange_transpose: more than 2^21 local rows");
+    ntt_exchange_transpose_kernel<<<grid, 256, 0, s>>>(p);
+    KERNEL_CHECK();
+    return b200_ok();
+}
+
+// Exchange buffers other ranks' GPUs write into: plain cudaMalloc memory exported / opened through CUDA IPC
+extern "C" b200_error_t b200_peer_buffer_alloc(size_t bytes, void** d_ptr, void* handle64) {
+    B200_TRY(b200_require_device());
+    if (!d_ptr || !handle64) return b200_err(B200_ERR_INVALID_ARG, "peer_buffer_alloc: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    CUDA_TRY(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return b200_cuda_err(e); }
+    memcpy(handle64, &h, 64);
+    return b200_ok();
+}
+extern "C" b200_error_t b200_peer_buffer_open(const void* handle64, void** d_ptr) {
+    B200_TRY(b200_require_device());
+    if (!d_ptr || !handle64) return b200_err(B200_ERR_INVALID_ARG, "peer_buffer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return b200_ok();
+}
+extern "C" b200_error_t b200_peer_buffer_close(void* d_ptr) {
+    if (d_ptr) CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return b200_ok();
+}
+extern "C" b200_error_t b200_peer_buffer_free(void* d_ptr) {
+    if (d_ptr) CUDA_TRY(cudaFree(d_ptr));
+    return b200_ok();
+}
+
 void ntt_release_tables() {
     std::lock_guard<std::mutex> lock(g_ntt.mu);
     for (int d = 0; d < 2; d++) {

@@ -13,6 +13,11 @@
     Forward coset scaling is applied to the natural-order input block, inverse coset scaling to the natural-order
     output block.
 
+  * `ntt_distributed_fused` is the same schedule with every exchange done by ONE kernel
+    (`b200_fr_exchange_transpose_device`): transpose + all-to-all (+ the twiddle) in a single pass whose stores go
+    straight into the destination rank's slab over NVLink (peer memory mapped through CUDA IPC, `PeerExchange`);
+    NCCL only provides the barriers between writers and readers of a slab.
+
 The local operations are injectable (`ops`), so the exchange / index logic is tested on CPU with the gloo backend and
 the oracle standing in for the kernels (tests/test_dist_cpu.py); on GPUs the default ops call the CUDA library.
 """
@@ -148,5 +153,129 @@ def ntt_distributed(block: torch.Tensor, log_n: int, direction: int = 0, coset: 
     f = _exchange_transpose(e, world, group)                       # [N2/world, N1]: my k2 range, all k1 = natural block
     out = f.view(per, FR_LIMBS)
     if coset and direction == 1:                                   # distribute_powers(coeffs, g^-1) on the natural-order output
+        ops.mul_powers(out, log_n, 1, 1, per, 1, rank * per, 0)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused four-step: exchanges as peer-memory stores
+# ----------------------------------------------------------------------------------------------------------------
+class _DevMem:
+    """raw device memory as a torch tensor (zero copy) through __cuda_array_interface__"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr: int, elems: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DevMem(ptr, elems * 32), device=device).view(elems, FR_LIMBS)
+
+
+class PeerExchange:
+    """Two exchange slabs (B, C) of `per_elems` Fr elements on every rank, allocated by the library with cudaMalloc and
+    mapped into every other rank's address space through CUDA IPC, so that a kernel on one GPU stores into the slab of
+    another.  `barrier()` is a one-element NCCL all-reduce on the current stream: it orders the writers of a slab before
+    its readers without blocking the host."""
+
+    NBUF = 2
+
+    def __init__(self, per_elems: int, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.per = per_elems
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        L = _lib.lib()
+        self._own, handles = [], torch.zeros((self.NBUF, 64), dtype=torch.uint8)
+        for b in range(self.NBUF):
+            ptr = ctypes.c_void_p()
+            h = (ctypes.c_uint8 * 64)()
+            _lib.check(L.b200_peer_buffer_alloc(per_elems * 32, ctypes.byref(ptr), h))
+            self._own.append(ptr.value)
+            handles[b] = torch.frombuffer(bytearray(h), dtype=torch.uint8)
+        self.ptrs = [[None] * self.world for _ in range(self.NBUF)]
+        self._opened = []
+        if self.world > 1:
+            allh = torch.empty((self.world, self.NBUF, 64), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh.view(-1), handles.to(self.device).view(-1), group=group)
+            allh = allh.cpu()
+        else:
+            allh = handles.view(1, self.NBUF, 64)
+        for d in range(self.world):
+            for b in range(self.NBUF):
+                if d == self.rank:
+                    self.ptrs[b][d] = self._own[b]
+                    continue
+                raw = (ctypes.c_uint8 * 64).from_buffer_copy(bytes(allh[d, b].numpy().tobytes()))
+                ptr = ctypes.c_void_p()
+                _lib.check(L.b200_peer_buffer_open(raw, ctypes.byref(ptr)))
+                self.ptrs[b][d] = ptr.value
+                self._opened.append(ptr.value)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def dst_array(self, b: int):
+        return (ctypes.c_void_p * self.world)(*self.ptrs[b])
+
+    def local(self, b: int) -> torch.Tensor:
+        return _as_tensor(self._own[b], self.per, self.device)
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def close(self) -> None:
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        L = _lib.lib()
+        for p in self._opened:
+            _lib.check(L.b200_peer_buffer_close(ctypes.c_void_p(p)))
+        for p in self._own:
+            _lib.check(L.b200_peer_buffer_free(ctypes.c_void_p(p)))
+        self._opened, self._own = [], []
+
+
+def exchange_transpose(src: torch.Tensor, dst_ptrs, world: int, rank: int, r_local: int, c: int, log_n: int, direction: int,
+                       twiddle: bool, row_base: int = 0) -> None:
+    """one fused exchange: src = this rank's [r_local, c] slab; dst_ptrs[d] = rank d's [c / world, r_local * world] slab"""
+    _lib.check(_lib.lib().b200_fr_exchange_transpose_device(
+        ctypes.c_void_p(src.data_ptr()), dst_ptrs, world, rank, r_local, c, log_n, direction, 1 if twiddle else 0, row_base,
+        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def ntt_distributed_fused(block: torch.Tensor, log_n: int, fabric: PeerExchange, direction: int = 0, coset: int = 0,
+                          natural_out: bool = True, log_n1: Optional[int] = None) -> torch.Tensor:
+    """`ntt_distributed` with the exchanges fused into peer-memory stores.  Returns a VIEW of one of the fabric's
+    slabs (valid until the next call on the same fabric): natural-order block, or the k1 slab if not natural_out."""
+    ops = CudaOps()
+    world, rank = fabric.world, fabric.rank
+    n = 1 << log_n
+    n1_log = log_n1 if log_n1 is not None else log_n // 2
+    n2_log = log_n - n1_log
+    n1, n2 = 1 << n1_log, 1 << n2_log
+    if n1 % world or n2 % world:
+        raise ValueError("both matrix sides must be divisible by the world size")
+    per = n // world
+    if block.shape[0] != per or fabric.per != per:
+        raise ValueError("block and fabric must hold 2^log_n / world elements")
+    block = block.contiguous()
+    if coset and direction == 0:
+        ops.mul_powers(block, log_n, 0, 1, per, 1, rank * per, 0)
+    B, C = fabric.local(0), fabric.local(1)
+    fabric.barrier()                                               # every rank is done with the slabs of the previous call
+    exchange_transpose(block, fabric.dst_array(0), world, rank, n1 // world, n2, log_n, direction, False)
+    fabric.barrier()                                               # B = [N2/world, N1]: my columns j2, all j1
+    ops.ntt_rows(B.view(n2 // world, n1, FR_LIMBS), n1_log, direction)
+    exchange_transpose(B, fabric.dst_array(1), world, rank, n2 // world, n1, log_n, direction, True, rank * (n2 // world))
+    fabric.barrier()                                               # C = [N1/world, N2]: my k1, all j2, twiddled
+    ops.ntt_rows(C.view(n1 // world, n2, FR_LIMBS), n2_log, direction)
+    if not natural_out:
+        if coset and direction == 1:
+            raise ValueError("inverse coset scaling needs natural order out")
+        return C.view(n1 // world, n2, FR_LIMBS)
+    exchange_transpose(C, fabric.dst_array(0), world, rank, n1 // world, n2, log_n, direction, False)
+    fabric.barrier()                                               # B = [N2/world, N1]: my k2 range = natural block
+    out = B.view(per, FR_LIMBS)
+    if coset and direction == 1:
         ops.mul_powers(out, log_n, 1, 1, per, 1, rank * per, 0)
     return out

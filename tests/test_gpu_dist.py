@@ -53,3 +53,55 @@ def test_msm_sharded_single_rank():
     out = D.msm_sharded(bases, torch.from_numpy(sc.view(np.int64)).cuda())
     torch.cuda.synchronize()
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == H.jac_bytes_to_affine(C.msm(bases.cpu().numpy(), sc))
+
+
+@pytest.mark.parametrize("log_n,world", [(10, 2), (12, 4), (13, 2), (16, 8)])
+@pytest.mark.parametrize("direction", [0, 1])
+def test_fused_exchange_virtual_world(log_n, world, direction):
+    """b200_fr_exchange_transpose_device (transpose + all-to-all + twiddle in one kernel) with `world` virtual ranks on
+    ONE GPU: every rank's slabs are separate buffers of this device, the destination pointer table is the same one a
+    real run fills with CUDA-IPC peer pointers.  The full fused four-step schedule must equal the oracle's NTT."""
+    import ctypes
+    import torch
+    from snarkos_b200 import dist as D
+    ops = D.CudaOps()
+    n = 1 << log_n
+    n1_log = log_n // 2
+    n2_log = log_n - n1_log
+    n1, n2, per = 1 << n1_log, 1 << n2_log, n // world
+    x = H.random_fr_mont_np(np.random.default_rng(7 * log_n + direction), (n,))
+    blocks = [torch.from_numpy(x[r * per:(r + 1) * per].view(np.int64)).cuda() for r in range(world)]
+    B = [torch.empty((per, 4), dtype=torch.int64, device="cuda") for _ in range(world)]
+    Cb = [torch.empty((per, 4), dtype=torch.int64, device="cuda") for _ in range(world)]
+    dst_b = (ctypes.c_void_p * world)(*[t.data_ptr() for t in B])
+    dst_c = (ctypes.c_void_p * world)(*[t.data_ptr() for t in Cb])
+    for r in range(world):
+        D.exchange_transpose(blocks[r], dst_b, world, r, n1 // world, n2, log_n, direction, False)
+    for r in range(world):
+        ops.ntt_rows(B[r].view(n2 // world, n1, 4), n1_log, direction)
+    for r in range(world):
+        D.exchange_transpose(B[r], dst_c, world, r, n2 // world, n1, log_n, direction, True, r * (n2 // world))
+    for r in range(world):
+        ops.ntt_rows(Cb[r].view(n1 // world, n2, 4), n2_log, direction)
+    for r in range(world):
+        D.exchange_transpose(Cb[r], dst_b, world, r, n1 // world, n2, log_n, direction, False)
+    torch.cuda.synchronize()
+    got = torch.cat(B).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, C.ntt(x, log_n, direction=direction))
+
+
+def test_peer_exchange_single_rank():
+    """PeerExchange / ntt_distributed_fused with world = 1 (no process group): IPC export of the slabs, zero-copy
+    tensor views, all four transform kinds against the oracle"""
+    import torch
+    from snarkos_b200 import dist as D
+    log_n = 12
+    n = 1 << log_n
+    x = H.random_fr_mont_np(np.random.default_rng(3), (n,))
+    fab = D.PeerExchange(n)
+    for direction, coset in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        blk = torch.from_numpy(x.view(np.int64)).cuda()
+        out = D.ntt_distributed_fused(blk, log_n, fab, direction, coset)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), C.ntt(x, log_n, direction=direction, coset=coset))
+    fab.close()

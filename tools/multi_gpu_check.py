@@ -117,6 +117,26 @@ for log_n in (20, 26):
     res[f"ntt_2^{log_n}"] = {"ms_natural_out": ms, "ms_slab_out": ms_slab, "gelem_per_s": n / ms / 1e6}
     if rank == 0:
         print(f"four-step ntt 2^{log_n} over {world} GPUs: ok, natural {ms:.3f} ms ({n / ms / 1e6:.2f} Gelem/s), slab-out {ms_slab:.3f} ms", flush=True)
+    # ---- the same transform with the exchanges fused into peer-memory stores (one kernel per exchange) --------------
+    if os.environ.get("B200_NO_FUSED") != "1":
+        fab = D.PeerExchange(per)
+        f1 = D.ntt_distributed_fused(orig.clone(), log_n, fab, 0, 0).clone()
+        sync()
+        assert torch.equal(f1, fwd), f"fused four-step NTT 2^{log_n} != NCCL four-step"
+        for direction, coset in ((1, 0), (0, 1), (1, 1)):
+            a = D.ntt_distributed_fused(orig.clone(), log_n, fab, direction, coset).clone()
+            b = D.ntt_distributed(orig.clone(), log_n, direction, coset)
+            sync()
+            assert torch.equal(a, b), ("fused", log_n, direction, coset)
+        slab = D.ntt_distributed_fused(orig.clone(), log_n, fab, 0, 0, natural_out=False).clone()
+        sync()
+        assert torch.equal(slab, D.ntt_distributed(orig.clone(), log_n, 0, 0, natural_out=False))
+        msf = timed(lambda: D.ntt_distributed_fused(work, log_n, fab, 0, 0))
+        msf_slab = timed(lambda: D.ntt_distributed_fused(work, log_n, fab, 0, 0, natural_out=False))
+        res[f"ntt_2^{log_n}"].update({"fused_ms_natural_out": msf, "fused_ms_slab_out": msf_slab, "fused_gelem_per_s": n / msf / 1e6})
+        if rank == 0:
+            print(f"fused four-step ntt 2^{log_n} over {world} GPUs: identical, natural {msf:.3f} ms ({n / msf / 1e6:.2f} Gelem/s), slab-out {msf_slab:.3f} ms", flush=True)
+        fab.close()
     del blk, orig, fwd, back, cf, work
 
 if rank == 0:
