@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256) ntt_exchange_transpose_kernel(NttExchange
     for (uint32_t rr = ty; rr < NTT_XCHG_TILE; rr += 8) {
         const unsigned long long row = r0 + rr, col = c0 + tx;
         if (row < p.r_local && col < p.c) {
-            fr_t x = fr_load(p.src, row * p.c + col);
+            fr_t x;
+            ptx::ld_global_256(p.src + 2 * (row * p.c + col), x.v);
             if (p.twiddle) {
                 const unsigned long long e = ((p.row_base + row) * col) & ((1ull << p.log_n) - 1);
                 if (e) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, e));
@@ -262,8 +263,11 @@ __global__ void __launch_bounds__(256) ntt_exchange_transpose_kernel(NttExchange
         if (row < p.r_local && col < p.c) {
             const unsigned long long d = col / p.c_local, cl = col - d * p.c_local;
             uint4* out = p.dst[d] + 2 * (cl * R + (unsigned long long)p.rank * p.r_local + row);
-            out[0] = sm_lo[tx][cc];
-            out[1] = sm_hi[tx][cc];
+            // one 256-bit store per element: a warp writes 1 KB of whole sectors per instruction (16-byte halves with
+            // 16-byte gaps travel over NVLink as many small packets)
+            const uint4 lo = sm_lo[tx][cc], hi = sm_hi[tx][cc];
+            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            ptx::st_global_256(out, w);
         }
     }
 }
