@@ -303,3 +303,19 @@ def test_affine_rounds_skewed_distributions(monkeypatch, kind):
     torch.cuda.synchronize()
     k = H.splitmix64_at(seed, np.arange(n))
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+
+
+def test_affine_rounds_sliced_on_helper_stream(monkeypatch):
+    """B200_MSM_SLICES > 1: denominators + inversion of slice i + 1 on the thread's high-priority helper stream under
+    the additions of slice i (kept as a measured alternative, default off) -- same result"""
+    import torch
+    import snarkos_b200 as S
+    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", "3")
+    monkeypatch.setenv("B200_MSM_SLICES", "3")
+    n, seed = 1 << 20, 31
+    dbases = _synthetic(n, seed)
+    sc = H.random_scalars_np(np.random.default_rng(6), n)
+    out = S.VariableBase.msm(dbases, torch.from_numpy(sc.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    k = H.splitmix64_at(seed, np.arange(n))
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
