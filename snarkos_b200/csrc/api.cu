@@ -222,8 +222,8 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         CUDA_TRY(d_sc.alloc(n * 32, s));
         CUDA_TRY(d_out.alloc(144, s));
         if (n) {
-            CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+            B200_TRY(b200_h2d(d_pts.p, points, n * stride, s));
+            B200_TRY(b200_h2d(d_sc.p, scalars, n * 32, s));
         }
         B200_TRY(msm_run_device(d_out.p, d_pts.p, n, d_sc.p, stride, nullptr, s));
         CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
@@ -270,8 +270,11 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         const size_t off = range_off[i], cnt = range_cnt[i];
         cudaError_t e = cudaSuccess;
         if (i >= 2) e = cudaStreamWaitEvent(cs, computed[i - 2], 0);        // staging buffer b is free again
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pts[b].p, (const uint8_t*)points + off * stride, cnt * stride, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sc[b].p, (const uint8_t*)scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) {
+            rc = b200_h2d(d_pts[b].p, (const uint8_t*)points + off * stride, cnt * stride, cs);
+            if (rc.code == 0) rc = b200_h2d(d_sc[b].p, (const uint8_t*)scalars + off * 32, cnt * 32, cs);
+            if (rc.code != 0) break;
+        }
         if (e == cudaSuccess) e = cudaEventRecord(copied[i], cs);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(s, copied[i], 0);
         if (e != cudaSuccess) { rc = b200_cuda_err(e); break; }
@@ -327,8 +330,8 @@ extern "C" b200_error_t b200_msm_batch_g1_bls12_377(void* out, const void* point
     CUDA_TRY(d_off.alloc((nmsm + 1) * 8, s));
     CUDA_TRY(d_out.alloc(nmsm * 144, s));
     if (n) {
-        CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+        B200_TRY(b200_h2d(d_pts.p, points, n * stride, s));
+        B200_TRY(b200_h2d(d_sc.p, scalars, n * 32, s));
     }
     CUDA_TRY(cudaMemcpyAsync(d_off.p, offsets, (nmsm + 1) * 8, cudaMemcpyHostToDevice, s));
     B200_TRY(b200_msm_batch_g1_bls12_377_device(d_out.p, d_pts.p, d_sc.p, d_off.p, nmsm, n, stride, s));
@@ -365,7 +368,7 @@ extern "C" b200_error_t b200_msm_register_bases(const void* points, size_t n, si
     cudaStream_t s = b200_thread_stream();
     DevBuf d_pts;
     CUDA_TRY(d_pts.alloc(n * stride, s));
-    if (n) CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
+    if (n) B200_TRY(b200_h2d(d_pts.p, points, n * stride, s));
     return b200_msm_register_bases_device(d_pts.p, n, stride, s, out_handle);
 }
 
@@ -412,7 +415,7 @@ extern "C" b200_error_t b200_msm_register_bases_tabulated(const void* points, si
     cudaStream_t s = b200_thread_stream();
     DevBuf d_pts;
     CUDA_TRY(d_pts.alloc(n * stride, s));
-    if (n) CUDA_TRY(cudaMemcpyAsync(d_pts.p, points, n * stride, cudaMemcpyHostToDevice, s));
+    if (n) B200_TRY(b200_h2d(d_pts.p, points, n * stride, s));
     return b200_msm_register_bases_tabulated_device(d_pts.p, n, stride, window_bits, s, out_handle);
 }
 
@@ -441,7 +444,7 @@ extern "C" b200_error_t b200_msm_registered(void* out, uint64_t handle, const vo
     DevBuf d_sc, d_out;
     CUDA_TRY(d_sc.alloc(n * 32, s));
     CUDA_TRY(d_out.alloc(144, s));
-    if (n) CUDA_TRY(cudaMemcpyAsync(d_sc.p, scalars, n * 32, cudaMemcpyHostToDevice, s));
+    if (n) B200_TRY(b200_h2d(d_sc.p, scalars, n * 32, s));
     B200_TRY(b200_msm_registered_device(d_out.p, handle, d_sc.p, n, s));
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -491,7 +494,7 @@ extern "C" b200_error_t b200_kzg_commit(void* out, uint64_t handle, const void* 
     DevBuf d_c, d_out;
     CUDA_TRY(d_c.alloc(n * 32, s));
     CUDA_TRY(d_out.alloc(144, s));
-    if (n) CUDA_TRY(cudaMemcpyAsync(d_c.p, coeffs_mont, n * 32, cudaMemcpyHostToDevice, s));
+    if (n) B200_TRY(b200_h2d(d_c.p, coeffs_mont, n * 32, s));
     B200_TRY(b200_kzg_commit_device(d_out.p, handle, d_c.p, n, s));
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -528,9 +531,9 @@ extern "C" b200_error_t b200_ntt_fr_bls12_377(void* inout, uint32_t log_n, size_
     cudaStream_t s = b200_thread_stream();
     DevBuf d;
     CUDA_TRY(d.alloc(bytes, s));
-    CUDA_TRY(cudaMemcpyAsync(d.p, inout, bytes, cudaMemcpyHostToDevice, s));
+    B200_TRY(b200_h2d(d.p, inout, bytes, s));
     B200_TRY(ntt_run_device(d.p, log_n, batch, stride, direction, coset, s));
-    CUDA_TRY(cudaMemcpyAsync(inout, d.p, bytes, cudaMemcpyDeviceToHost, s));
+    B200_TRY(b200_d2h(inout, d.p, bytes, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return b200_ok();
 }

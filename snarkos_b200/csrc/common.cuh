@@ -76,6 +76,9 @@ void msm_stream_abort(void* session);
 b200_error_t msm_build_window_table_device(void* d_table, size_t n, uint32_t c, cudaStream_t stream);
 b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t n, size_t stride,
                                    cudaStream_t stream);
+// host <-> device copies that stay fast for pageable caller memory (hostcopy.cu)
+b200_error_t b200_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream);
+b200_error_t b200_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream);
 void ntt_release_tables();
 b200_error_t b200_require_device();
 cudaStream_t b200_thread_stream();

@@ -110,3 +110,20 @@ def test_full_size_properties(log_n, batch):
     w = O.EvaluationDomain(n).group_gen
     for k in (0, 1, 2, 12345, n // 2, n - 1):
         assert H.fr_from_mont_array(out[k:k + 1])[0] == pow(w, k, O.R_MOD)
+
+
+def test_pageable_host_buffers_staged_copies(monkeypatch):
+    """Ordinary (pageable) caller memory, as a Rust Vec is: uploads and downloads above 8 MiB go through the library's
+    pinned staging slots on worker threads (hostcopy.cu) -- several slices per worker, both directions; the result must
+    equal the driver's own pageable path bit for bit, and the round trip must be the identity."""
+    log_n, batch = 20, 5                                     # 160 MiB: 40 slices of 4 MiB over 8 workers
+    n = 1 << log_n
+    data = H.random_fr_mont_np(np.random.default_rng(77), (batch, n))
+    d = dom(n)
+    staged = d.fft_in_place(data.copy())
+    monkeypatch.setenv("B200_NO_STAGED_COPIES", "1")
+    plain = d.fft_in_place(data.copy())
+    monkeypatch.delenv("B200_NO_STAGED_COPIES")
+    assert np.array_equal(staged, plain)
+    assert np.array_equal(staged[3], C.ntt(data[3], log_n))
+    assert np.array_equal(d.ifft_in_place(staged.copy()), data)
