@@ -162,6 +162,16 @@ b200_error_t b200_fr_mul_powers_device(void* d_data, uint32_t log_n, int directi
 b200_error_t b200_fr_exchange_transpose_device(const void* d_src, void* const* dst_ptrs, uint32_t world, uint32_t rank,
                                                unsigned long long r_local, unsigned long long c, uint32_t log_n,
                                                int direction, int twiddle, unsigned long long row_base, void* stream);
+/* The same for a PART of the slab: rows [row_off, row_off + r_count) of the r_local rows (d_src_slab points at row 0)
+ * and, for every destination rank, columns [col_lo, col_lo + col_cnt) of that rank's c / world columns -- a slab can be
+ * exchanged in chunks while the transforms of the chunks that have arrived are already running.  cta_limit != 0
+ * bounds the grid (the kernel strides over its tiles) so that a concurrently running transform keeps its SM slots. */
+b200_error_t b200_fr_exchange_transpose_part_device(const void* d_src_slab, void* const* dst_ptrs, uint32_t world, uint32_t rank,
+                                                    unsigned long long r_local, unsigned long long row_off,
+                                                    unsigned long long r_count, unsigned long long c,
+                                                    unsigned long long col_lo, unsigned long long col_cnt, uint32_t log_n,
+                                                    int direction, int twiddle, unsigned long long row_base,
+                                                    uint32_t cta_limit, void* stream);
 /* Exchange buffers: cudaMalloc memory with its 64-byte CUDA IPC handle (sent to the other ranks by the caller), the
  * mapping of a peer's buffer into this process, and their release. */
 b200_error_t b200_peer_buffer_alloc(size_t bytes, void** d_ptr, void* handle64);

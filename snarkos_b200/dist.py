@@ -223,6 +223,16 @@ class PeerExchange:
         if self.world > 1:
             dist.all_reduce(self._flag, group=self.group)
 
+    def exchange_stream(self) -> "torch.cuda.Stream":
+        if getattr(self, "_xstream", None) is None:
+            self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
+        return self._xstream
+
+    def transform_stream(self) -> "torch.cuda.Stream":
+        if getattr(self, "_tstream", None) is None:
+            self._tstream = torch.cuda.Stream(device=self.device)
+        return self._tstream
+
     def close(self) -> None:
         torch.cuda.synchronize()
         if self.world > 1:
@@ -241,6 +251,104 @@ def exchange_transpose(src: torch.Tensor, dst_ptrs, world: int, rank: int, r_loc
     _lib.check(_lib.lib().b200_fr_exchange_transpose_device(
         ctypes.c_void_p(src.data_ptr()), dst_ptrs, world, rank, r_local, c, log_n, direction, 1 if twiddle else 0, row_base,
         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def exchange_transpose_part(src_slab: torch.Tensor, dst_ptrs, world: int, rank: int, r_local: int, row_off: int, r_count: int,
+                            c: int, col_lo: int, col_cnt: int, log_n: int, direction: int, twiddle: bool, row_base: int = 0,
+                            cta_limit: int = 0) -> None:
+    """a part of one fused exchange: rows [row_off, row_off + r_count) of the slab, columns [col_lo, col_lo + col_cnt)
+    of every destination rank's range"""
+    _lib.check(_lib.lib().b200_fr_exchange_transpose_part_device(
+        ctypes.c_void_p(src_slab.data_ptr()), dst_ptrs, world, rank, r_local, row_off, r_count, c, col_lo, col_cnt, log_n,
+        direction, 1 if twiddle else 0, row_base, cta_limit, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def ntt_distributed_overlapped(block: torch.Tensor, log_n: int, fabric: PeerExchange, direction: int = 0, coset: int = 0,
+                               natural_out: bool = True, log_n1: Optional[int] = None, chunks: int = 4,
+                               cta_limit: Optional[int] = None) -> torch.Tensor:
+    """`ntt_distributed_fused` with every slab cut into `chunks` parts and two streams, so that the exchanges run under
+    the local transforms:
+        exchange stream : X1(0) | X1(1) | ... | X2(0) X2(1) ...      | X3(0) X3(1) ...
+        transform stream:        NTT_B(0) NTT_B(1) ...               NTT_C(0) NTT_C(1) ...
+    X1(q) delivers rows chunk q of every rank's B (a column sub-range of every destination), after a barrier NTT_B(q)
+    transforms them and X2(q) sends them on (twiddled) while NTT_B(q+1) runs; the N2-point transforms need all of C, so
+    one barrier separates the phases; X3(q) follows NTT_C(q).  Same results as the unchunked schedule, bit for bit."""
+    ops = CudaOps()
+    world, rank = fabric.world, fabric.rank
+    n = 1 << log_n
+    n1_log = log_n1 if log_n1 is not None else log_n // 2
+    n2_log = log_n - n1_log
+    n1, n2 = 1 << n1_log, 1 << n2_log
+    if n1 % world or n2 % world:
+        raise ValueError("both matrix sides must be divisible by the world size")
+    per = n // world
+    if block.shape[0] != per or fabric.per != per:
+        raise ValueError("block and fabric must hold 2^log_n / world elements")
+    if cta_limit is None:                                           # two exchange CTAs per SM leave room for the transforms
+        cta_limit = 2 * torch.cuda.get_device_properties(block.device).multi_processor_count
+    rb, rc = n2 // world, n1 // world                               # rows of my B slab / of my C slab
+    q_n = max(1, min(chunks, rb, rc))
+    while rb % q_n or rc % q_n:
+        q_n -= 1
+    block = block.contiguous()
+    cur = torch.cuda.current_stream()
+    xs = fabric.exchange_stream()                                   # exchanges + barriers: HIGH priority, so that their CTAs
+    ts = fabric.transform_stream()                                  # get SM slots while the (compute-bound) transforms run
+    if coset and direction == 0:
+        ops.mul_powers(block, log_n, 0, 1, per, 1, rank * per, 0)
+    B, C = fabric.local(0), fabric.local(1)
+    Bm, Cm = B.view(rb, n1, FR_LIMBS), C.view(rc, n2, FR_LIMBS)
+    dst_b, dst_c = fabric.dst_array(0), fabric.dst_array(1)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    arrived, done_b, done_c = [], [], []
+    with torch.cuda.stream(xs):
+        xs.wait_event(ready)
+        fabric.barrier()                                           # every rank is done with the slabs of the previous call
+        for q in range(q_n):                                       # X1(q): B rows [q * rb/Q, ..) on every rank
+            exchange_transpose_part(block, dst_b, world, rank, rc, 0, rc, n2, q * (rb // q_n), rb // q_n, log_n, direction, False, 0, cta_limit)
+            fabric.barrier()
+            ev = torch.cuda.Event()
+            ev.record(xs)
+            arrived.append(ev)
+    with torch.cuda.stream(ts):
+        for q in range(q_n):
+            ts.wait_event(arrived[q])
+            ops.ntt_rows(Bm[q * (rb // q_n):(q + 1) * (rb // q_n)], n1_log, direction)
+            ev = torch.cuda.Event()
+            ev.record(ts)
+            done_b.append(ev)
+    ev_c = torch.cuda.Event()
+    with torch.cuda.stream(xs):
+        for q in range(q_n):                                       # X2(q): my B rows chunk q, twiddled, into everybody's C
+            xs.wait_event(done_b[q])
+            exchange_transpose_part(B, dst_c, world, rank, rb, q * (rb // q_n), rb // q_n, n1, 0, rc, log_n, direction, True, rank * rb, cta_limit)
+        fabric.barrier()                                           # C complete everywhere
+        ev_c.record(xs)
+    with torch.cuda.stream(ts):
+        ts.wait_event(ev_c)
+        for q in range(q_n):
+            ops.ntt_rows(Cm[q * (rc // q_n):(q + 1) * (rc // q_n)], n2_log, direction)
+            ev = torch.cuda.Event()
+            ev.record(ts)
+            done_c.append(ev)
+    if not natural_out:
+        if coset and direction == 1:
+            raise ValueError("inverse coset scaling needs natural order out")
+        cur.wait_event(done_c[-1])
+        return Cm
+    fin = torch.cuda.Event()
+    with torch.cuda.stream(xs):
+        for q in range(q_n):                                       # X3(q): my C rows chunk q into everybody's B
+            xs.wait_event(done_c[q])
+            exchange_transpose_part(C, dst_b, world, rank, rc, q * (rc // q_n), rc // q_n, n2, 0, rb, log_n, direction, False, 0, cta_limit)
+        fabric.barrier()
+        fin.record(xs)
+    cur.wait_event(fin)
+    out = B.view(per, FR_LIMBS)
+    if coset and direction == 1:
+        ops.mul_powers(out, log_n, 1, 1, per, 1, rank * per, 0)
+    return out
 
 
 def ntt_distributed_fused(block: torch.Tensor, log_n: int, fabric: PeerExchange, direction: int = 0, coset: int = 0,

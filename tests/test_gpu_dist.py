@@ -55,9 +55,9 @@ def test_msm_sharded_single_rank():
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == H.jac_bytes_to_affine(C.msm(bases.cpu().numpy(), sc))
 
 
-@pytest.mark.parametrize("log_n,world", [(10, 2), (12, 4), (13, 2), (16, 8)])
+@pytest.mark.parametrize("log_n,world,parts", [(10, 2, 1), (12, 4, 1), (13, 2, 1), (16, 8, 1), (12, 4, 2), (16, 8, 4), (16, 2, 3)])
 @pytest.mark.parametrize("direction", [0, 1])
-def test_fused_exchange_virtual_world(log_n, world, direction):
+def test_fused_exchange_virtual_world(log_n, world, parts, direction):
     """b200_fr_exchange_transpose_device (transpose + all-to-all + twiddle in one kernel) with `world` virtual ranks on
     ONE GPU: every rank's slabs are separate buffers of this device, the destination pointer table is the same one a
     real run fills with CUDA-IPC peer pointers.  The full fused four-step schedule must equal the oracle's NTT."""
@@ -75,16 +75,31 @@ def test_fused_exchange_virtual_world(log_n, world, direction):
     Cb = [torch.empty((per, 4), dtype=torch.int64, device="cuda") for _ in range(world)]
     dst_b = (ctypes.c_void_p * world)(*[t.data_ptr() for t in B])
     dst_c = (ctypes.c_void_p * world)(*[t.data_ptr() for t in Cb])
+    rb, rc = n2 // world, n1 // world
+
+    def cuts(total):                                       # `parts` ragged pieces of [0, total)
+        edges = [total * i // parts for i in range(parts + 1)]
+        return [(a, b - a) for a, b in zip(edges, edges[1:]) if b > a]
+
     for r in range(world):
-        D.exchange_transpose(blocks[r], dst_b, world, r, n1 // world, n2, log_n, direction, False)
+        if parts == 1:
+            D.exchange_transpose(blocks[r], dst_b, world, r, rc, n2, log_n, direction, False)
+        else:                                              # column sub-ranges of every destination (chunks of B's rows)
+            for lo, cnt in cuts(rb):
+                D.exchange_transpose_part(blocks[r], dst_b, world, r, rc, 0, rc, n2, lo, cnt, log_n, direction, False)
     for r in range(world):
-        ops.ntt_rows(B[r].view(n2 // world, n1, 4), n1_log, direction)
+        ops.ntt_rows(B[r].view(rb, n1, 4), n1_log, direction)
     for r in range(world):
-        D.exchange_transpose(B[r], dst_c, world, r, n2 // world, n1, log_n, direction, True, r * (n2 // world))
+        if parts == 1:
+            D.exchange_transpose(B[r], dst_c, world, r, rb, n1, log_n, direction, True, r * rb)
+        else:                                              # row ranges of the source slab
+            for lo, cnt in cuts(rb):
+                D.exchange_transpose_part(B[r], dst_c, world, r, rb, lo, cnt, n1, 0, rc, log_n, direction, True, r * rb)
     for r in range(world):
-        ops.ntt_rows(Cb[r].view(n1 // world, n2, 4), n2_log, direction)
+        ops.ntt_rows(Cb[r].view(rc, n2, 4), n2_log, direction)
     for r in range(world):
-        D.exchange_transpose(Cb[r], dst_b, world, r, n1 // world, n2, log_n, direction, False)
+        for lo, cnt in cuts(rc):
+            D.exchange_transpose_part(Cb[r], dst_b, world, r, rc, lo, cnt, n2, 0, rb, log_n, direction, False)
     torch.cuda.synchronize()
     got = torch.cat(B).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, C.ntt(x, log_n, direction=direction))
@@ -102,6 +117,10 @@ def test_peer_exchange_single_rank():
     for direction, coset in ((0, 0), (1, 0), (0, 1), (1, 1)):
         blk = torch.from_numpy(x.view(np.int64)).cuda()
         out = D.ntt_distributed_fused(blk, log_n, fab, direction, coset)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), C.ntt(x, log_n, direction=direction, coset=coset))
+        blk = torch.from_numpy(x.view(np.int64)).cuda()
+        out = D.ntt_distributed_overlapped(blk, log_n, fab, direction, coset, chunks=4)      # two streams, chunked slabs
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy().view(np.uint64), C.ntt(x, log_n, direction=direction, coset=coset))
     fab.close()

@@ -136,6 +136,19 @@ for log_n in (20, 26):
         res[f"ntt_2^{log_n}"].update({"fused_ms_natural_out": msf, "fused_ms_slab_out": msf_slab, "fused_gelem_per_s": n / msf / 1e6})
         if rank == 0:
             print(f"fused four-step ntt 2^{log_n} over {world} GPUs: identical, natural {msf:.3f} ms ({n / msf / 1e6:.2f} Gelem/s), slab-out {msf_slab:.3f} ms", flush=True)
+        for q_n in (2, 4, 8):
+            o1 = D.ntt_distributed_overlapped(orig.clone(), log_n, fab, 0, 0, chunks=q_n).clone()
+            sync()
+            assert torch.equal(o1, fwd), f"overlapped four-step NTT 2^{log_n} (chunks={q_n}) != NCCL four-step"
+            o2 = D.ntt_distributed_overlapped(orig.clone(), log_n, fab, 1, 1, chunks=q_n).clone()
+            sync()
+            assert torch.equal(o2, D.ntt_distributed(orig.clone(), log_n, 1, 1)), ("overlapped", log_n, q_n)
+            mso = timed(lambda: D.ntt_distributed_overlapped(work, log_n, fab, 0, 0, chunks=q_n))
+            mso_slab = timed(lambda: D.ntt_distributed_overlapped(work, log_n, fab, 0, 0, natural_out=False, chunks=q_n))
+            res[f"ntt_2^{log_n}"][f"overlapped_{q_n}_ms_natural_out"] = mso
+            res[f"ntt_2^{log_n}"][f"overlapped_{q_n}_ms_slab_out"] = mso_slab
+            if rank == 0:
+                print(f"overlapped four-step ntt 2^{log_n} over {world} GPUs, {q_n} chunks: identical, natural {mso:.3f} ms ({n / mso / 1e6:.2f} Gelem/s), slab-out {mso_slab:.3f} ms", flush=True)
         fab.close()
     del blk, orig, fwd, back, cf, work
 
