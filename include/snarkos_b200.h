@@ -84,7 +84,9 @@ b200_error_t b200_msm_batch_g1_bls12_377_device(void* d_out_jacobian, const void
                                                 size_t affine_stride, void* stream);
 
 /* Resident bases (the SRS `powers_of_beta_g` is fixed for the process lifetime -- KZG10::commit
- * [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs] calls msm on a prefix of it every time). */
+ * [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs] calls msm on a prefix of it every time).  Sets of 2^10 .. 2^20
+ * points are stored with their window table (see b200_msm_register_bases_tabulated: 16 x the memory, no window fold,
+ * half the latency of a small commit); larger sets as packed points only. */
 b200_error_t b200_msm_register_bases(const void* points, size_t npoints, size_t affine_stride,
                                      uint64_t* out_handle);
 b200_error_t b200_msm_register_bases_device(const void* d_points, size_t npoints, size_t affine_stride,

@@ -344,6 +344,11 @@ extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, siz
                                                        void* stream, uint64_t* out_handle) {
     B200_TRY(b200_require_device());
     if (!out_handle || (n && !d_points)) return b200_err(B200_ERR_INVALID_ARG, "register_bases: null pointer");
+    // Sets of the size a Varuna circuit commits against (2^10 .. 2^20 powers) get their window table right away:
+    // 16 x the memory (2 GiB at 2^20) buys MSMs with one bucket set and NO window fold -- the 253 - c dependent
+    // doublings that are half of a small call (2^16: 4.4 -> 2.6 ms per commit, 2^18: 7.3 -> 3.3 ms).
+    if (n >= ((size_t)1 << 10) && n <= ((size_t)1 << 20) && !getenv("B200_MSM_NO_AUTO_TABLE"))
+        return b200_msm_register_bases_tabulated_device(d_points, n, stride, 0, stream, out_handle);
     void* d_packed = nullptr;
     CUDA_TRY(cudaMalloc(&d_packed, (n ? n : 1) * (size_t)G1_BASE_BYTES));
     b200_error_t r = msm_pack_bases_device(d_packed, d_points, n, stride, (cudaStream_t)stream);

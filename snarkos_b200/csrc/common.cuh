@@ -44,7 +44,8 @@ struct DevBuf {
         s = stream;
         return cudaMallocAsync(&p, bytes ? bytes : 16, stream);
     }
-    ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+    void release() { if (p) cudaFreeAsync(p, s); p = nullptr; }
+    ~DevBuf() { release(); }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
