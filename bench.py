@@ -336,6 +336,28 @@ def run_b200(args):
         ntt_e2e = {"value": world * n * Ke / e_ntt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": int(h_ntt.numel() * 8),
                    "d2h_bytes_per_step": int(h_ntt.numel() * 8), "steps": Ke,
                    "api": "snarkos_b200.EvaluationDomain.fft_in_place(pinned host tensor) -> b200_ntt_fr_bls12_377"}
+        # BASELINE configs[1]: 16 polynomials of 2^20 (same 2^24 elements viewed as a batch), device-resident and end to end
+        # (host batches are pipelined in groups over three streams: upload / transforms / download)
+        if args.log_n >= 21 and world == 1:
+            dom20, b20 = S.EvaluationDomain(1 << 20), n >> 20
+            dv = ntt_data.view(b20, 1 << 20, 4)
+            dom20.fft_in_place(dv)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(Ke):
+                dom20.fft_in_place(dv)
+            ev1.record()
+            torch.cuda.synchronize()
+            hv = h_ntt.view(b20, 1 << 20, 4)
+            dom20.fft_in_place(hv)
+            t6 = time.perf_counter()
+            for _ in range(Ke):
+                dom20.fft_in_place(hv)
+            t7 = time.perf_counter()
+            ntt_e2e["batch_2^20"] = {"workload": f"{b20} polynomials of 2^20 (BASELINE configs[1] shape)",
+                                     "device_resident_value": n * Ke / (ev0.elapsed_time(ev1) * 1e-3) / 1e9,
+                                     "value": n * Ke / (t7 - t6) / 1e9, "unit": "Gelem/s"}
         del h_bases, h_scalars, h_ntt
 
     if rank != 0:

@@ -205,6 +205,18 @@ static cudaStream_t b200_thread_copy_stream() {
 // host-buffer calls with >= 2^23 points stream the inputs in point ranges that grow geometrically: 2^20, 2^20, 2^21,
 // ... capped at 2^23.  Only the first (small) range crosses PCIe with nothing to overlap; every later range is twice the
 // one being accumulated, and a range takes about twice as long to accumulate as to transfer (~5 vs ~2.5 ns per point).
+static thread_local ThreadStream t_copy_stream2;
+static cudaStream_t b200_thread_copy_stream2() {
+    if (!t_copy_stream2.s) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        t_copy_stream2.s = s;
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        g_api.streams.push_back(s);
+    }
+    return t_copy_stream2.s;
+}
+
 #define MSM_HOST_FIRST_LOG 20
 #define MSM_HOST_CHUNK_LOG 23
 
@@ -536,10 +548,82 @@ extern "C" b200_error_t b200_ntt_fr_bls12_377(void* inout, uint32_t log_n, size_
     cudaStream_t s = b200_thread_stream();
     DevBuf d;
     CUDA_TRY(d.alloc(bytes, s));
-    B200_TRY(b200_h2d(d.p, inout, bytes, s));
-    B200_TRY(ntt_run_device(d.p, log_n, batch, stride, direction, coset, s));
-    B200_TRY(b200_d2h(inout, d.p, bytes, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    // A batch is pipelined in groups of polynomials over three streams: upload of group g + 1, transforms of group g
+    // and download of group g - 1 run together (PCIe is full duplex), so a large batch costs about one direction of the
+    // transfer instead of both plus the compute (2^20 x 16: the call is PCIe-bound either way).
+    size_t ngroups = 1;
+    if (batch >= 2 && !getenv("B200_NTT_NO_HOST_PIPELINE")) {
+        ngroups = bytes / ((size_t)32 << 20);                     // groups of >= 32 MiB
+        if (ngroups > batch) ngroups = batch;
+        if (ngroups > 8) ngroups = 8;
+        if (ngroups < 1) ngroups = 1;
+    }
+    if (ngroups == 1) {
+        B200_TRY(b200_h2d(d.p, inout, bytes, s));
+        B200_TRY(ntt_run_device(d.p, log_n, batch, stride, direction, coset, s));
+        B200_TRY(b200_d2h(inout, d.p, bytes, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return b200_ok();
+    }
+    cudaStream_t ci = b200_thread_copy_stream(), co = b200_thread_copy_stream2();
+    if (!ci || !co) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
+    std::vector<cudaEvent_t> ev;
+    auto new_event = [&](cudaEvent_t* e) {
+        cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        if (r == cudaSuccess) ev.push_back(*e);
+        return r;
+    };
+    b200_error_t rc = b200_ok();
+    cudaEvent_t ready = nullptr, prev_done = nullptr;
+    size_t prev_lo = 0, prev_hi = 0;
+    auto group_bytes = [&](size_t lo, size_t hi, size_t* off, size_t* len) {    // polynomials [lo, hi)
+        *off = lo * stride * 32;
+        *len = ((hi - 1 - lo) * stride + n) * 32;
+    };
+    cudaError_t e = new_event(&ready);
+    if (e == cudaSuccess) e = cudaEventRecord(ready, s);                        // the device buffer exists from here on
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ci, ready, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(co, ready, 0);
+    for (size_t g = 0; g < ngroups && e == cudaSuccess && rc.code == 0; g++) {
+        const size_t lo = batch * g / ngroups, hi = batch * (g + 1) / ngroups;
+        size_t off, len;
+        group_bytes(lo, hi, &off, &len);
+        cudaEvent_t in = nullptr, done = nullptr;
+        rc = b200_h2d((uint8_t*)d.p + off, (const uint8_t*)inout + off, len, ci);
+        if (rc.code != 0) break;
+        e = new_event(&in);
+        if (e == cudaSuccess) e = cudaEventRecord(in, ci);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, in, 0);
+        if (e != cudaSuccess) break;
+        rc = ntt_run_device((uint8_t*)d.p + off, log_n, hi - lo, stride, direction, coset, s);
+        if (rc.code != 0) break;
+        e = new_event(&done);
+        if (e == cudaSuccess) e = cudaEventRecord(done, s);
+        if (e != cudaSuccess) break;
+        if (prev_done) {                                                        // download of the previous group
+            size_t poff, plen;
+            group_bytes(prev_lo, prev_hi, &poff, &plen);
+            e = cudaStreamWaitEvent(co, prev_done, 0);
+            if (e == cudaSuccess) rc = b200_d2h((uint8_t*)inout + poff, (const uint8_t*)d.p + poff, plen, co);
+        }
+        prev_done = done;
+        prev_lo = lo;
+        prev_hi = hi;
+    }
+    if (e == cudaSuccess && rc.code == 0 && prev_done) {
+        size_t poff, plen;
+        group_bytes(prev_lo, prev_hi, &poff, &plen);
+        e = cudaStreamWaitEvent(co, prev_done, 0);
+        if (e == cudaSuccess) rc = b200_d2h((uint8_t*)inout + poff, (const uint8_t*)d.p + poff, plen, co);
+    }
+    cudaStreamSynchronize(ci);
+    cudaError_t e2 = cudaStreamSynchronize(co);
+    cudaError_t e3 = cudaStreamSynchronize(s);
+    for (cudaEvent_t x : ev) cudaEventDestroy(x);
+    if (rc.code != 0) return rc;
+    if (e != cudaSuccess) return b200_cuda_err(e);
+    if (e2 != cudaSuccess) return b200_cuda_err(e2);
+    if (e3 != cudaSuccess) return b200_cuda_err(e3);
     return b200_ok();
 }
 

@@ -127,3 +127,31 @@ def test_pageable_host_buffers_staged_copies(monkeypatch):
     assert np.array_equal(staged, plain)
     assert np.array_equal(staged[3], C.ntt(data[3], log_n))
     assert np.array_equal(d.ifft_in_place(staged.copy()), data)
+
+
+def test_host_batch_pipeline_matches_single_shot(monkeypatch):
+    """Host batches above 64 MiB are pipelined in groups over three streams (upload / transforms / download); ragged
+    groups (7 polynomials), a padded batch stride and pinned memory: same bytes as the single-shot path, padding
+    between the polynomials untouched."""
+    import torch
+    log_n, batch, pad = 19, 7, 1000
+    n = 1 << log_n
+    stride = n + pad
+    rng = np.random.default_rng(5)
+    flat = H.random_fr_mont_np(rng, (batch * stride,))
+    import snarkos_b200 as S
+    from snarkos_b200 import _lib
+    import ctypes
+
+    def run(buf):
+        t = torch.from_numpy(buf.copy().view(np.int64)).pin_memory()
+        _lib.check(_lib.lib().b200_ntt_fr_bls12_377(ctypes.c_void_p(t.data_ptr()), log_n, batch, stride, 0, 1))
+        return t.numpy().view(np.uint64).copy()
+
+    piped = run(flat)
+    monkeypatch.setenv("B200_NTT_NO_HOST_PIPELINE", "1")
+    single = run(flat)
+    assert np.array_equal(piped, single)
+    for b in (0, 3, 6):
+        assert np.array_equal(piped[b * stride:b * stride + n], C.ntt(flat[b * stride:b * stride + n], log_n, coset=1))
+        assert np.array_equal(piped[b * stride + n:(b + 1) * stride], flat[b * stride + n:(b + 1) * stride])
