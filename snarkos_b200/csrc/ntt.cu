@@ -12,7 +12,10 @@
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const NttPassParams p) {
+#ifndef NTT_MIN_CTAS
+#define NTT_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const NttPassParams p) {
     extern __shared__ uint4 sm[];
     const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     const uint32_t L = p.log_len[p.pass];
