@@ -368,9 +368,11 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
     hbm_peak, peak_src = measured_peaks()
-    c = int(S.lib().b200_msm_window_bits(n))
-    nwin = 253 // c + 1
-    rounds = int(S.lib().b200_msm_affine_rounds(n))
+    import ctypes
+    desc = (ctypes.c_uint32 * 4)()
+    S.lib().b200_msm_describe(n, desc)                            # what VariableBase.msm runs with at this size
+    c, nwin, rounds, glv = int(desc[0]), int(desc[1]), int(desc[2]), int(desc[3])
+    n_eff = n * (2 if glv else 1)                                 # GLV: 2n points, 127-bit scalars
     # dominant kernel: msm_pair_add_kernel, launched once per pair round (all `rounds` launches of an MSM are one unit)
     add_ms = sum(v for k_, v in stage.items() if k_ in ("msm_pairs0_add", "msm_pairs_add")) / K
     dom_kernel, dom_ms = ("msm_pair_add_kernel", add_ms) if rounds else ("msm_accumulate_kernel", stage.get("msm_accumulate", 0.0) / K)
@@ -394,16 +396,17 @@ def run_b200(args):
     if rounds:
         # pair rounds halve the lists `rounds` times: ~E (1 - 2^-rounds) additions (E = n * windows entries), each
         # 5 Fq products in msm_pair_add_kernel (2 to peel its inverse off the shared one, 2M + 1S for the addition)
-        modmuls = 5.0 * n * nwin * (1.0 - 0.5 ** rounds)
+        modmuls = 5.0 * n_eff * nwin * (1.0 - 0.5 ** rounds)
         per_add = "5 (affine addition with a shared inversion; +1 in msm_pair_denoms_kernel, +~0.2 in the batch inversion)"
     else:
-        modmuls = 10.0 * n * nwin                                 # one XYZZ mixed add (8M + 2S) per non-zero digit
+        modmuls = 10.0 * n_eff * nwin                             # one XYZZ mixed add (8M + 2S) per non-zero digit
         per_add = "10 (XYZZ mixed addition)"
     roofline_int = {"bound": "int_mul_pipe", "kernel": dom_kernel, "unit": "G Fq-modmul/s",
                     "achieved": modmuls / (dom_ms * 1e-3) / 1e9 if dom_ms else None, "peak": best / 1e9,
                     "peak_source": "fp_mul<Fq> dependent-chain microbenchmark, same run, full occupancy",
                     "modmul_per_step": modmuls, "modmul_per_addition": per_add, "window_bits": c, "windows": nwin,
-                    "digits": "signed", "affine_rounds": rounds}
+                    "digits": "signed", "affine_rounds": rounds, "glv": bool(glv),
+                    "entries": n_eff * nwin}
     roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"] if roofline_int["achieved"] else None
     ntt_pass_ms = sum(v for k_, v in stage.items() if k_.startswith("ntt_pass")) / K
     ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,
@@ -460,7 +463,7 @@ def run_b200(args):
         "dtype": "u32 limbs (Montgomery, 377-bit Fq / 253-bit Fr), integer", "data": "synthetic",
         "config": {"workload": f"BLS12-377 G1 MSM 2^{args.log_n} + Fr NTT 2^{args.log_n} per GPU (BASELINE configs[4] shard size; "
                                f"headline metric size)",
-                   "msm_points_per_gpu": n, "ntt_elems_per_gpu": n, "window_bits": c, "windows": nwin,
+                   "msm_points_per_gpu": n, "ntt_elems_per_gpu": n, "window_bits": c, "windows": nwin, "glv_split": bool(glv),
                    "l2": "inputs larger than L2 (packed bases 1.5 GiB, scalars 0.5 GiB, NTT data 0.5 GiB vs 126 MB)",
                    "parallelism": f"msm: point-range shard x{world} + gather/add of partial sums; ntt: independent per GPU",
                    "bases": "k_i * G, k_i = splitmix64(seed, i), generated on the device; scalars / Fr data uniform < 2^252"},

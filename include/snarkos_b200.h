@@ -119,6 +119,8 @@ uint32_t b200_msm_window_bits(size_t npoints);
 /* number of batched-affine pair rounds (snarkVM batched::batch_add counterpart) a call of this size runs before the
  * XYZZ finish, for the window width above (diagnostic: bench.py's roofline accounting) */
 uint32_t b200_msm_affine_rounds(size_t npoints);
+/* what b200_msm_g1_bls12_377 runs with for npoints points: out4 = {window bits, windows, pair rounds, GLV split (0/1)} */
+void b200_msm_describe(size_t npoints, uint32_t* out4);
 
 /* Sum of `count` Jacobian points (144 B each): the multi-GPU partial-sum combine.  Device pointers. */
 b200_error_t b200_g1_sum_jacobian_device(void* d_out_jacobian_144B, const void* d_in, size_t count,

@@ -42,6 +42,7 @@ SYMBOLS = {
     "b200_kzg_commit_device": (b200_error_t, [_vp, _u64, _vp, _sz, _vp]),
     "b200_msm_window_bits": (_u32, [_sz]),
     "b200_msm_affine_rounds": (_u32, [_sz]),
+    "b200_msm_describe": (None, [_sz, ctypes.POINTER(_u32)]),
     "b200_g1_sum_jacobian_device": (b200_error_t, [_vp, _vp, _sz, _vp]),
     "b200_ntt_fr_bls12_377": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i]),
     "b200_ntt_fr_bls12_377_device": (b200_error_t, [_vp, _u32, _sz, _sz, _i, _i, _vp]),

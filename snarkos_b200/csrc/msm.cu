@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "msm_core.cuh"
 #include "msm_affine.cuh"
+#include "msm_glv.cuh"
 
 #define MSM_ACC_THREADS 128
 #define MSM_RED_THREADS 64
@@ -43,6 +44,37 @@ __global__ void msm_pack_kernel(uint4* __restrict__ out, const uint8_t* __restri
         p.w[k] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
     }
     g1_store_packed(out + i * G1_BASE_U4, p);
+}
+
+// GLV form of the inputs (msm_glv.cuh): point i becomes records 2i = P_i and 2i + 1 = phi(P_i) = (beta x, y), scalar i
+// becomes the 128-bit halves 2i = k mod lambda and 2i + 1 = k div lambda.
+__global__ void msm_pack_glv_kernel(uint4* __restrict__ out, const uint8_t* __restrict__ pts, size_t n, size_t stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* src = pts + i * stride;
+    const unsigned long long* s64 = reinterpret_cast<const unsigned long long*>(src);
+    const bool inf = src[96] != 0;
+    g1_packed_t p;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        unsigned long long a = inf ? 0ull : s64[2 * k], b = inf ? 0ull : s64[2 * k + 1];
+        p.w[k] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+    }
+    g1_store_packed(out + 2 * i * G1_BASE_U4, p);
+    g1_affine_t a = g1_unpack(p);
+    a.x = fp_mul(a.x, msm_glv_beta());                     // infinity (0, 0) stays (0, 0)
+    fq_to_u4x3(a.x, p.w);
+    g1_store_packed(out + (2 * i + 1) * G1_BASE_U4, p);
+}
+__global__ void msm_glv_split_kernel(uint4* __restrict__ half, const uint4* __restrict__ scalars, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+    const uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t k1[4], k2[4];
+    msm_glv_split(k, k1, k2);
+    half[2 * i] = make_uint4(k1[0], k1[1], k1[2], k1[3]);
+    half[2 * i + 1] = make_uint4(k2[0], k2[1], k2[2], k2[3]);
 }
 
 // Warp-aggregated histogram update.  Structural hot spots (the top window of the signed-digit split has only a
@@ -88,19 +120,27 @@ __device__ __forceinline__ uint32_t msm_segment_of(const unsigned long long* seg
     return lo;
 }
 
+// scalar i as 8 limbs: a 256-bit canonical scalar (two uint4) or, after the GLV split, one 128-bit half
+__device__ __forceinline__ void msm_load_scalar(uint32_t* s, const uint4* __restrict__ scalars, size_t i, uint32_t glv) {
+    if (glv) {
+        const uint4 a = scalars[i];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    } else {
+        const uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    }
+}
+
 // Tabulated bases (n_reg != 0): the caller holds 2^(c*w) * P_i for every window w at index w * n_reg + i, so all
 // windows share ONE set of 2^(c-1) buckets -- the key is the bucket alone and the entry points into the table.
 __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __restrict__ scalars, size_t n,
                                  MsmShape sh, const unsigned long long* __restrict__ seg_off, uint32_t nmsm,
-                                 size_t n_reg) {
+                                 size_t n_reg, uint32_t glv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
-    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, i) * sh.nwin : 0;
+    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, glv ? i >> 1 : i) * sh.nwin : 0;
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (valid) {
-        uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
-        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-    }
+    if (valid) msm_load_scalar(s, scalars, i, glv);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t neg;
@@ -115,16 +155,14 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
 // thread re-derives the carry chain of the lower windows (a few shifts per window).
 __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __restrict__ cursor,
                                    const uint4* __restrict__ scalars, size_t n, MsmShape sh,
-                                   const unsigned long long* __restrict__ seg_off, uint32_t nmsm, size_t n_reg) {
+                                   const unsigned long long* __restrict__ seg_off, uint32_t nmsm, size_t n_reg,
+                                   uint32_t glv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t w = blockIdx.y;
-    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, i) * sh.nwin : 0;
+    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, glv ? i >> 1 : i) * sh.nwin : 0;
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (valid) {
-        uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
-        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-    }
+    if (valid) msm_load_scalar(s, scalars, i, glv);
     uint32_t carry = 0, neg = 0, d = 0;
     for (uint32_t ww = 0; ww <= w; ww++) d = msm_signed_digit(s, ww, sh.c, carry, neg);
     const bool active = valid && d != 0;
@@ -596,10 +634,39 @@ struct MsmPlan {
     uint32_t nmsm;
     size_t n_reg;            // != 0: tabulated bases, table row length
     uint32_t seg_len, segs_per_win;
+    bool glv;                // inputs split by the endomorphism: 2n points, 127-bit scalars (msm_glv.cuh)
 };
 
-static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n_reg, uint32_t c_force) {
-    pl->sh = msm_shape(c_force ? c_force : b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
+// GLV applies where the call packs its own points (VariableBase::msm proper, the streamed host path, the batched
+// verifier MSMs); resident sets keep their stored form (tabulated sets have no fold to shorten anyway).
+static bool msm_use_glv(const void* d_packed, size_t n_reg) {
+    return !d_packed && !n_reg && !getenv("B200_MSM_NO_GLV");
+}
+
+// window width for 2n points with 127-bit scalars: the usual log2 - 5, then the narrowest window with the same
+// number of windows (127 / c + 1 is a step function: 19 bits already give the 7 windows of 20 and 21)
+static uint32_t msm_glv_window_bits(size_t n_eff) {
+    if (const char* e = getenv("B200_MSM_C")) {
+        int c = atoi(e);
+        if (c >= 2 && c <= 22) return (uint32_t)c;
+    }
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n_eff) lg++;
+    int c = (int)lg - 5;
+    if (c < 4) c = 4;
+    if (c > 19) c = 19;
+    while (c > 4 && MSM_GLV_BITS / (c - 1) == MSM_GLV_BITS / c) c--;
+    return (uint32_t)c;
+}
+
+static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n_reg, uint32_t c_force, bool glv = false) {
+    pl->glv = glv;
+    if (glv) {
+        n *= 2;
+        pl->sh = msm_shape(c_force ? c_force : msm_glv_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n), MSM_GLV_BITS);
+    } else {
+        pl->sh = msm_shape(c_force ? c_force : b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
+    }
     pl->vsh = pl->sh;
     pl->vsh.nwin = n_reg ? 1 : pl->sh.nwin * nmsm;           // tabulated: one bucket set, nothing to fold
     pl->K = (size_t)pl->vsh.nwin * pl->sh.nbuckets;
@@ -652,15 +719,41 @@ extern "C" uint32_t b200_msm_affine_rounds(size_t n) {
     return msm_affine_rounds(n * sh.nwin, (size_t)sh.nwin * sh.nbuckets);
 }
 
+// what a plain VariableBase::msm call of n points runs with: out = {window bits, windows, pair rounds, GLV (0 / 1)}
+extern "C" void b200_msm_describe(size_t n, uint32_t* out4) {
+    const bool glv = msm_use_glv(nullptr, 0);
+    const size_t n_eff = glv ? 2 * n : n;
+    const MsmShape sh = glv ? msm_shape(msm_glv_window_bits(n_eff), MSM_GLV_BITS) : msm_shape(b200_msm_window_bits(n));
+    out4[0] = sh.c;
+    out4[1] = sh.nwin;
+    out4[2] = msm_affine_rounds(n_eff * sh.nwin, (size_t)sh.nwin * sh.nbuckets);
+    out4[3] = glv ? 1u : 0u;
+}
+
 // bucket array (K x XYZZ) of one range of points; d_buckets is overwritten
 static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const void* d_points, size_t n,
                               const void* d_scalars, size_t stride, const void* d_packed,
                               const unsigned long long* d_seg_off, cudaStream_t stream) {
     const MsmShape& sh = pl.sh;
     const size_t K = pl.K;
-    DevBuf packed, counts, offsets, cursor, entries, heads, tails, head_bucket, tail_bucket, max_heads;
+    DevBuf packed, halves, counts, offsets, cursor, entries, heads, tails, head_bucket, tail_bucket, max_heads;
     const uint4* pts = reinterpret_cast<const uint4*>(d_packed);
-    if (!pts) {
+    const uint32_t glv = pl.glv ? 1u : 0u;
+    if (glv) {
+        if (pts) return b200_err(B200_ERR_INVALID_ARG, "msm: GLV plan with pre-packed bases");
+        if (stride < 97 || (stride & 7) || (reinterpret_cast<uintptr_t>(d_points) & 7))
+            return b200_err(B200_ERR_INVALID_ARG, "msm: affine stride must be >= 104 and points 8-byte aligned");
+        STAGE("msm_pack", stream);
+        CUDA_TRY(packed.alloc(2 * n * (size_t)G1_BASE_BYTES, stream));
+        CUDA_TRY(halves.alloc(2 * n * 16, stream));
+        msm_pack_glv_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(packed.as<uint4>(), reinterpret_cast<const uint8_t*>(d_points), n, stride);
+        KERNEL_CHECK();
+        msm_glv_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(halves.as<uint4>(), reinterpret_cast<const uint4*>(d_scalars), n);
+        KERNEL_CHECK();
+        pts = packed.as<uint4>();
+        d_scalars = halves.p;
+        n *= 2;                                            // from here on: 2n points, 128-bit scalars
+    } else if (!pts) {
         STAGE("msm_pack", stream);
         CUDA_TRY(packed.alloc(n * (size_t)G1_BASE_BYTES, stream));
         B200_TRY(msm_pack_bases_device(packed.p, d_points, n, stride, stream));
@@ -674,14 +767,14 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     STAGE("msm_count", stream);
     CUDA_TRY(cudaMemsetAsync(counts.p, 0, (K + 1) * 4, stream));
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg);
+    msm_count_kernel<<<nblk, 256, 0, stream>>>(counts.as<uint32_t>(), reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg, glv);
     KERNEL_CHECK();
     STAGE("msm_scan", stream);
     B200_TRY(exclusive_scan(offsets.as<uint32_t>(), counts.as<uint32_t>(), K, stream));
     CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
     STAGE("msm_scatter", stream);
     msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
-                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg);
+                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg, glv);
     KERNEL_CHECK();
     // ---- batched-affine pair rounds: halve every bucket's list `rounds` times at ~6.3 products per addition ----
     const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
@@ -882,7 +975,7 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
     if (n >= ((size_t)1 << 28)) return b200_err(B200_ERR_TOO_LARGE, "msm: more than 2^28 - 1 points per call");
     if (reinterpret_cast<uintptr_t>(d_scalars) & 15) return b200_err(B200_ERR_INVALID_ARG, "msm: scalars must be 16-byte aligned on the device");
     MsmPlan pl;
-    B200_TRY(msm_make_plan(&pl, n, nmsm, n_reg, n_reg ? c_tab : 0));
+    B200_TRY(msm_make_plan(&pl, n, nmsm, n_reg, n_reg ? c_tab : 0, msm_use_glv(d_packed, n_reg)));
     DevBuf buckets;
     CUDA_TRY(buckets.alloc(pl.K * sizeof(g1_xyzz_mem_t), stream));
     B200_TRY(msm_front(pl, buckets.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, d_packed, d_seg_off, stream));
@@ -901,9 +994,10 @@ b200_error_t msm_stream_begin(void** session, size_t n_total, cudaStream_t strea
     MsmStream* st = new MsmStream();
     // one window narrower than the single-shot choice: every range pays one group addition per touched bucket when it
     // is merged, so fewer, fuller buckets win (2^24 in 2^22 ranges: c = 19)
-    uint32_t c = b200_msm_window_bits(n_total);
-    if (!getenv("B200_MSM_C") && c > 6) c -= 1;
-    b200_error_t r = msm_make_plan(&st->plan, n_total, 1, 0, c);
+    const bool glv = msm_use_glv(nullptr, 0);
+    uint32_t c = glv ? msm_glv_window_bits(2 * n_total) : b200_msm_window_bits(n_total);
+    if (!glv && !getenv("B200_MSM_C") && c > 6) c -= 1;
+    b200_error_t r = msm_make_plan(&st->plan, n_total, 1, 0, c, glv);
     if (r.code == 0) {
         cudaError_t e = st->total.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);
         if (e == cudaSuccess) e = st->part.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);

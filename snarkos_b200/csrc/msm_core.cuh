@@ -16,10 +16,10 @@ struct MsmShape {
     uint32_t nwin;       // floor(253 / c) + 1: always room for the last signed-digit carry
     uint32_t nbuckets;   // per window: 2^(c-1), bucket b holds digit magnitude b + 1
 };
-B200_HOSTDEV MsmShape msm_shape(uint32_t c) {
+B200_HOSTDEV MsmShape msm_shape(uint32_t c, uint32_t bits = MSM_SCALAR_BITS) {
     MsmShape s;
     s.c = c;
-    s.nwin = MSM_SCALAR_BITS / c + 1;
+    s.nwin = bits / c + 1;
     s.nbuckets = 1u << (c - 1);
     return s;
 }

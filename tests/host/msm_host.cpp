@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../snarkos_b200/csrc/msm_affine.cuh"
+#include "../../snarkos_b200/csrc/msm_glv.cuh"
 
 static void invert_all(std::vector<uint4>& data, size_t n) {
     if (n <= 64) {
@@ -106,4 +107,17 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
     memcpy(out_jac + 48, Y.v, 48);
     memcpy(out_jac + 96, Z.v, 48);
     return 0;
+}
+
+// GLV split of n scalars (8 x u32 each) -> k1, k2 (4 x u32 each), and phi(P) = (beta x, y) of n affine points
+extern "C" void host_glv_split(uint32_t* k1, uint32_t* k2, const uint32_t* k, size_t n) {
+    for (size_t i = 0; i < n; i++) msm_glv_split(k + 8 * i, k1 + 4 * i, k2 + 4 * i);
+}
+extern "C" void host_glv_endo_x(uint32_t* out_x, const uint32_t* x, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fq_t a;
+        memcpy(a.v, x + 12 * i, 48);
+        a = fp_mul(a, msm_glv_beta());
+        memcpy(out_x + 12 * i, a.v, 48);
+    }
 }

@@ -319,3 +319,22 @@ def test_affine_rounds_sliced_on_helper_stream(monkeypatch):
     torch.cuda.synchronize()
     k = H.splitmix64_at(seed, np.arange(n))
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+
+
+@pytest.mark.parametrize("n", [1, 3, 100, 4097])
+def test_glv_split_path_equals_plain_path(monkeypatch, n):
+    """VariableBase::msm splits every scalar by the endomorphism (k = k1 + k2 * lambda, phi(P) = (beta x, y): 2n points,
+    127-bit scalars, half the windows); with B200_MSM_NO_GLV the same call runs on the 253-bit scalars -- both must give
+    the oracle's point, including infinity among the bases and the extreme scalars"""
+    rng = O.SplitMix64(3100 + n)
+    pts = O.random_points(rng, min(n, 32))
+    pts = [pts[i % len(pts)] for i in range(n)]
+    sc = O.random_fr(rng, n)
+    sc[0] = O.R_MOD - 1
+    if n > 2:
+        pts[1], sc[2] = None, 0
+    bases, scal = H.bases_array(pts), H.scalars_array(sc)
+    want = O.msm_naive(pts, sc) if n <= 100 else oracle_msm(bases, scal)
+    assert gpu_msm(bases, scal) == want
+    monkeypatch.setenv("B200_MSM_NO_GLV", "1")
+    assert gpu_msm(bases, scal) == want

@@ -24,7 +24,7 @@ def hostlib():
     src = os.path.join(HERE, "host", "msm_host.cpp")
     so = os.path.join(HERE, "host", "libmsm_host.so")
     deps = [src] + [os.path.join(ROOT, "snarkos_b200", "csrc", f)
-                    for f in ("field.cuh", "ec.cuh", "msm_core.cuh", "msm_affine.cuh", "ptx_ops.cuh")]
+                    for f in ("field.cuh", "ec.cuh", "msm_core.cuh", "msm_affine.cuh", "msm_glv.cuh", "ptx_ops.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so], check=True)
     return ctypes.CDLL(so)
@@ -83,3 +83,29 @@ def test_exceptional_pairs(hostlib):
     # total exactly infinity
     assert run(hostlib, [pts[0], pts[0]], [5, O.R_MOD - 5], 4, 2)[0] is None
     assert run(hostlib, [None] * 5, sc[:5], 4, 2)[0] is None
+
+
+def test_glv_split_and_endomorphism(hostlib):
+    """k = k1 + k2 * lambda with k1, k2 < 2^127 (device code of msm_glv.cuh against Python divmod), and
+    (beta x, y) = lambda * (x, y) on the oracle's curve arithmetic"""
+    u = 0x8508C00000000001
+    lam = u * u - 1
+    assert (lam * lam + lam + 1) % O.R_MOD == 0
+    rng = O.SplitMix64(4242)
+    ks = [0, 1, lam - 1, lam, lam + 1, 2 * lam - 1, 2 * lam, O.R_MOD - 1, O.R_MOD - 2, (O.R_MOD // lam) * lam, (O.R_MOD // lam) * lam - 1]
+    ks += [rng.below(O.R_MOD, 253) for _ in range(20000)]
+    K = H.ints_to_limbs(ks, 4)
+    k1 = np.zeros((len(ks), 2), dtype=np.uint64)
+    k2 = np.zeros((len(ks), 2), dtype=np.uint64)
+    hostlib.host_glv_split(k1.ctypes.data_as(ctypes.c_void_p), k2.ctypes.data_as(ctypes.c_void_p),
+                           K.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(ks)))
+    a, b = H.limbs_to_ints(k1), H.limbs_to_ints(k2)
+    for k, x, y in zip(ks, a, b):
+        assert (x, y) == (k % lam, k // lam) and x < (1 << 127) and y < (1 << 127)
+    pts = O.random_points(rng, 4)
+    xs = H.ints_to_limbs([p[0] * (1 << 384) % O.P_MOD for p in pts], 6)
+    out = np.zeros_like(xs)
+    hostlib.host_glv_endo_x(out.ctypes.data_as(ctypes.c_void_p), xs.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(pts)))
+    rinv = pow(1 << 384, -1, O.P_MOD)
+    for p, bx in zip(pts, H.limbs_to_ints(out)):
+        assert (bx * rinv % O.P_MOD, p[1]) == O.g1_mul(p, lam)

@@ -13,16 +13,20 @@ g = torch.Generator(device="cuda"); g.manual_seed(1)
 sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
 sc[:, 3] &= (1 << 60) - 1
 rb = S.ResidentBases(bases)
+plain = os.environ.get("PLAIN") == "1"            # VariableBase.msm on raw points (GLV path) instead of resident bases
+call = (lambda: S.VariableBase.msm(bases, sc)) if plain else (lambda: rb.msm(sc))
 ref = None
 for c in [int(x) for x in os.environ.get("CS", "20").split(",")]:
     for r in [int(x) for x in os.environ.get("ROUNDS", "0,3,4,5").split(",")]:
-        os.environ["B200_MSM_C"] = str(c)
-        os.environ["B200_MSM_AFFINE_ROUNDS"] = str(r)
-        out = rb.msm(sc); torch.cuda.synchronize()
+        if c > 0:
+            os.environ["B200_MSM_C"] = str(c)
+        if r >= 0:
+            os.environ["B200_MSM_AFFINE_ROUNDS"] = str(r)
+        out = call(); torch.cuda.synchronize()
         best = None
         for _ in range(2):
             with S.profile() as p:
-                rb.msm(sc)
+                call()
             tot = sum(v for _, v in p.stages)
             if best is None or tot < best[0]:
                 best = (tot, p.totals())
