@@ -18,6 +18,7 @@ struct RegisteredBases {
     void* d_packed;      // n packed points; with a window table: nwin * n (window 0 first)
     size_t n;
     uint32_t c_tab;      // 0: plain; else the window width of the table 2^(c*w) * P_i
+    bool glv;            // plain sets: stored as 2n records (P_i, phi(P_i)) for the GLV split (msm_glv.cuh)
 };
 struct ApiState {
     std::mutex mu;
@@ -362,8 +363,10 @@ extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, siz
     if (n >= ((size_t)1 << 10) && n <= ((size_t)1 << 20) && !getenv("B200_MSM_NO_AUTO_TABLE"))
         return b200_msm_register_bases_tabulated_device(d_points, n, stride, 0, stream, out_handle);
     void* d_packed = nullptr;
-    CUDA_TRY(cudaMalloc(&d_packed, (n ? n : 1) * (size_t)G1_BASE_BYTES));
-    b200_error_t r = msm_pack_bases_device(d_packed, d_points, n, stride, (cudaStream_t)stream);
+    const bool glv = msm_glv_enabled();                 // larger sets: both P_i and phi(P_i) resident (2 x 128 B per point)
+    CUDA_TRY(cudaMalloc(&d_packed, (n ? n : 1) * (size_t)G1_BASE_BYTES * (glv ? 2 : 1)));
+    b200_error_t r = glv ? msm_pack_bases_glv_device(d_packed, d_points, n, stride, (cudaStream_t)stream)
+                         : msm_pack_bases_device(d_packed, d_points, n, stride, (cudaStream_t)stream);
     if (r.code == 0) {
         cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
         if (e != cudaSuccess) r = b200_cuda_err(e);
@@ -374,7 +377,7 @@ extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, siz
     }
     std::lock_guard<std::mutex> lock(g_api.mu);
     uint64_t h = g_api.next_handle++;
-    g_api.bases[h] = RegisteredBases{d_packed, n, 0};
+    g_api.bases[h] = RegisteredBases{d_packed, n, 0, glv};
     *out_handle = h;
     return b200_ok();
 }
@@ -420,7 +423,7 @@ extern "C" b200_error_t b200_msm_register_bases_tabulated_device(const void* d_p
     }
     std::lock_guard<std::mutex> lock(g_api.mu);
     uint64_t h = g_api.next_handle++;
-    g_api.bases[h] = RegisteredBases{d_table, n, c};
+    g_api.bases[h] = RegisteredBases{d_table, n, c, false};
     *out_handle = h;
     return b200_ok();
 }
@@ -451,7 +454,7 @@ extern "C" b200_error_t b200_msm_registered_device(void* d_out, uint64_t handle,
     B200_TRY(lookup_bases(handle, &rb));
     if (n > rb.n) return b200_err(B200_ERR_INVALID_ARG, "msm_registered: more scalars than registered bases");
     if (rb.c_tab) return msm_run_tabulated_device(d_out, n, d_scalars, rb.d_packed, rb.n, rb.c_tab, (cudaStream_t)stream);
-    return msm_run_device(d_out, nullptr, n, d_scalars, 0, rb.d_packed, (cudaStream_t)stream);
+    return msm_run_device(d_out, nullptr, n, d_scalars, 0, rb.d_packed, (cudaStream_t)stream, rb.glv);
 }
 
 extern "C" b200_error_t b200_msm_registered(void* out, uint64_t handle, const void* scalars, size_t n) {
@@ -501,7 +504,7 @@ extern "C" b200_error_t b200_kzg_commit_device(void* d_out, uint64_t handle, con
         KERNEL_CHECK();
     }
     if (rb.c_tab) return msm_run_tabulated_device(d_out, n, d_sc.p, rb.d_packed, rb.n, rb.c_tab, s);
-    return msm_run_device(d_out, nullptr, n, d_sc.p, 0, rb.d_packed, s);
+    return msm_run_device(d_out, nullptr, n, d_sc.p, 0, rb.d_packed, s, rb.glv);
 }
 
 extern "C" b200_error_t b200_kzg_commit(void* out, uint64_t handle, const void* coeffs_mont, size_t n) {

@@ -63,10 +63,13 @@ struct StageTimer {
 b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction,
                             int coset, cudaStream_t stream);
 b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
-                            const void* d_packed /* non-null: pre-packed 96 B bases */, cudaStream_t stream);
+                            const void* d_packed /* non-null: pre-packed bases */, cudaStream_t stream,
+                            bool packed_glv = false /* d_packed holds (P_i, phi(P_i)) pairs: msm_pack_bases_glv_device */);
 b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                                   const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
-                                  cudaStream_t stream, size_t n_reg = 0, uint32_t c_tab = 0);
+                                  cudaStream_t stream, size_t n_reg = 0, uint32_t c_tab = 0, bool packed_glv = false);
+b200_error_t msm_pack_bases_glv_device(void* d_packed_2n, const void* d_points, size_t n, size_t stride, cudaStream_t stream);
+bool msm_glv_enabled();
 b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scalars, const void* d_table, size_t n_reg,
                                       uint32_t c, cudaStream_t stream);
 b200_error_t msm_stream_begin(void** session, size_t n_total, cudaStream_t stream);

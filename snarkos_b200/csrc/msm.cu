@@ -613,8 +613,21 @@ static b200_error_t exclusive_scan(uint32_t* d_out, const uint32_t* d_in, size_t
 }
 
 b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
-                            const void* d_packed, cudaStream_t stream) {
-    return msm_run_batch_device(d_out, d_points, n, d_scalars, stride, d_packed, nullptr, 1, stream);
+                            const void* d_packed, cudaStream_t stream, bool packed_glv) {
+    return msm_run_batch_device(d_out, d_points, n, d_scalars, stride, d_packed, nullptr, 1, stream, 0, 0, packed_glv);
+}
+
+bool msm_glv_enabled() { return !getenv("B200_MSM_NO_GLV"); }
+
+// resident sets stored in GLV form: 2n records (P_i, phi(P_i))
+b200_error_t msm_pack_bases_glv_device(void* d_packed_2n, const void* d_points, size_t n, size_t stride, cudaStream_t stream) {
+    if (n == 0) return b200_ok();
+    if (stride < 97 || (stride & 7)) return b200_err(B200_ERR_INVALID_ARG, "msm: affine stride must be >= 104 and 8-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d_points) & 7) return b200_err(B200_ERR_INVALID_ARG, "msm: points must be 8-byte aligned");
+    msm_pack_glv_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(reinterpret_cast<uint4*>(d_packed_2n),
+                                                                          reinterpret_cast<const uint8_t*>(d_points), n, stride);
+    KERNEL_CHECK();
+    return b200_ok();
 }
 
 b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scalars, const void* d_table, size_t n_reg,
@@ -740,17 +753,15 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     const uint4* pts = reinterpret_cast<const uint4*>(d_packed);
     const uint32_t glv = pl.glv ? 1u : 0u;
     if (glv) {
-        if (pts) return b200_err(B200_ERR_INVALID_ARG, "msm: GLV plan with pre-packed bases");
-        if (stride < 97 || (stride & 7) || (reinterpret_cast<uintptr_t>(d_points) & 7))
-            return b200_err(B200_ERR_INVALID_ARG, "msm: affine stride must be >= 104 and points 8-byte aligned");
         STAGE("msm_pack", stream);
-        CUDA_TRY(packed.alloc(2 * n * (size_t)G1_BASE_BYTES, stream));
+        if (!pts) {                                        // resident GLV sets come packed as (P_i, phi(P_i)) already
+            CUDA_TRY(packed.alloc(2 * n * (size_t)G1_BASE_BYTES, stream));
+            B200_TRY(msm_pack_bases_glv_device(packed.p, d_points, n, stride, stream));
+            pts = packed.as<uint4>();
+        }
         CUDA_TRY(halves.alloc(2 * n * 16, stream));
-        msm_pack_glv_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(packed.as<uint4>(), reinterpret_cast<const uint8_t*>(d_points), n, stride);
-        KERNEL_CHECK();
         msm_glv_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(halves.as<uint4>(), reinterpret_cast<const uint4*>(d_scalars), n);
         KERNEL_CHECK();
-        pts = packed.as<uint4>();
         d_scalars = halves.p;
         n *= 2;                                            // from here on: 2n points, 128-bit scalars
     } else if (!pts) {
@@ -961,7 +972,7 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
 // d_out receives nmsm Jacobian points.  d_seg_off == nullptr means a single MSM over everything.
 b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                                   const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
-                                  cudaStream_t stream, size_t n_reg, uint32_t c_tab) {
+                                  cudaStream_t stream, size_t n_reg, uint32_t c_tab, bool packed_glv) {
     if (!d_out) return b200_err(B200_ERR_INVALID_ARG, "msm: null output pointer");
     if (n_reg && (nmsm != 1 || !d_packed || c_tab < 2 || n > n_reg))
         return b200_err(B200_ERR_INVALID_ARG, "msm: tabulated bases need a single MSM over a prefix of the table");
@@ -975,7 +986,7 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
     if (n >= ((size_t)1 << 28)) return b200_err(B200_ERR_TOO_LARGE, "msm: more than 2^28 - 1 points per call");
     if (reinterpret_cast<uintptr_t>(d_scalars) & 15) return b200_err(B200_ERR_INVALID_ARG, "msm: scalars must be 16-byte aligned on the device");
     MsmPlan pl;
-    B200_TRY(msm_make_plan(&pl, n, nmsm, n_reg, n_reg ? c_tab : 0, msm_use_glv(d_packed, n_reg)));
+    B200_TRY(msm_make_plan(&pl, n, nmsm, n_reg, n_reg ? c_tab : 0, packed_glv || msm_use_glv(d_packed, n_reg)));
     DevBuf buckets;
     CUDA_TRY(buckets.alloc(pl.K * sizeof(g1_xyzz_mem_t), stream));
     B200_TRY(msm_front(pl, buckets.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, d_packed, d_seg_off, stream));

@@ -338,3 +338,27 @@ def test_glv_split_path_equals_plain_path(monkeypatch, n):
     assert gpu_msm(bases, scal) == want
     monkeypatch.setenv("B200_MSM_NO_GLV", "1")
     assert gpu_msm(bases, scal) == want
+
+
+def test_resident_set_in_glv_form(monkeypatch):
+    """resident sets above 2^20 points (and smaller ones with the window table switched off) are stored as
+    (P_i, phi(P_i)) pairs and every MSM against them runs on the GLV halves: exact identity at 2^20 + 77 points, a
+    prefix call against the oracle, KZG commit on a small GLV-resident set"""
+    import torch
+    import snarkos_b200 as S
+    n, seed = (1 << 20) + 77, 41
+    dbases = _synthetic(n, seed)
+    sc = H.random_scalars_np(np.random.default_rng(9), n)
+    sc[:3] = H.scalars_array([O.R_MOD - 1, 0, 1])
+    rb = S.ResidentBases(dbases)
+    out = rb.msm(torch.from_numpy(sc.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    k = H.splitmix64_at(seed, np.arange(n))
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+    hb = dbases[:600 * 104].cpu().numpy()
+    assert H.jac_bytes_to_affine(rb.msm(sc[:600])) == oracle_msm(hb, sc[:600])
+    rb.release()
+    monkeypatch.setenv("B200_MSM_NO_AUTO_TABLE", "1")
+    small = S.ResidentBases(dbases[:4096 * 104])
+    assert H.jac_bytes_to_affine(small.msm(sc[:4096])) == oracle_msm(dbases[:4096 * 104].cpu().numpy(), sc[:4096])
+    small.release()
