@@ -45,9 +45,8 @@ def parse_args():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/r01_ncu_full_selected_metrics.txt, r01_ncu_msm_affine_full.txt), valid for the default workload only (2^24)
 NCU_TRAFFIC_BYTES = {"msm_accumulate_kernel@2^24": 42.036437e9 + 1.545928e9, "ntt_pass_kernel@2^24": (1.071753 + 0.504116 + 0.539175 + 0.480226 + 0.536956 + 0.487881) * 1e9,   # profiles/r01_ncu_ntt_full.txt
-                     # five launches (pair rounds 0..4) of one 2^24 MSM at c = 18: profiles/r01_ncu_msm_affine_full.txt
-                     "msm_pair_add_kernel@2^24": (41.940586 + 13.569590 + 16.896102 + 6.786489 + 8.583088 + 3.427714 + 4.404794 + 1.747778
-                                                  + 2.324402 + 0.909176) * 1e9}
+                     # five launches (pair rounds 0..4) of one 2^24 MSM, GLV split, c = 19: profiles/r01_ncu_msm_affine_full.txt
+                     "msm_pair_add_kernel@2^24": (40.571 + 13.103 + 16.321 + 6.539 + 8.275 + 3.298 + 4.233 + 1.676 + 2.220 + 0.865) * 1e9}
 
 
 def measured_peaks():

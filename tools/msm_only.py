@@ -10,7 +10,7 @@ bases = S.synthetic_bases(n, seed=5)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
 sc[:, 3] &= (1 << 60) - 1
-rb = S.ResidentBases(bases)
+rb = S.ResidentBases(bases)   # stored as (P, phi(P)) pairs: the GLV path, as VariableBase.msm takes
 for _ in range(int(os.environ.get("CALLS", "1"))):
     rb.msm(sc)
 torch.cuda.synchronize()
