@@ -249,7 +249,11 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     cudaStream_t cs = b200_thread_copy_stream();
     if (!cs) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
     std::vector<size_t> range_off, range_cnt;
-    for (size_t done = 0, cur = (size_t)1 << MSM_HOST_FIRST_LOG; done < n;) {
+    uint32_t first_log = MSM_HOST_FIRST_LOG;
+    if (const char* e = getenv("B200_MSM_HOST_FIRST_LOG")) first_log = (uint32_t)atoi(e);
+    if (first_log < 16) first_log = 16;
+    if (first_log > MSM_HOST_CHUNK_LOG) first_log = MSM_HOST_CHUNK_LOG;
+    for (size_t done = 0, cur = (size_t)1 << first_log; done < n;) {
         const size_t cnt = n - done < cur ? n - done : cur;
         range_off.push_back(done);
         range_cnt.push_back(cnt);
