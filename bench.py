@@ -134,12 +134,21 @@ def cpu_inputs(msm_log_n, ntt_log_n):
     return bases, rnd(1 << msm_log_n), rnd(1 << ntt_log_n)
 
 
+def host_threads():
+    """all the host threads this process may use -- NOT OMP_NUM_THREADS, which torchrun forces to 1 for every rank"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_time_once(bases, scalars, ntt_data, ntt_log_n):
     from oracle import c_oracle as C
+    nt = host_threads()
     t0 = time.perf_counter()
-    C.msm(bases, scalars)
+    C.msm(bases, scalars, nthreads=nt)
     t1 = time.perf_counter()
-    C.ntt(ntt_data, ntt_log_n)
+    C.ntt(ntt_data, ntt_log_n, nthreads=nt)
     t2 = time.perf_counter()
     return t1 - t0, t2 - t1
 
@@ -150,7 +159,7 @@ def run_reference(args):
         return
     from oracle import c_oracle as C
     C.build()
-    cores = C.num_threads()
+    cores = host_threads()
     bases, scalars, ntt_data = cpu_inputs(args.cpu_msm_log_n, args.cpu_ntt_log_n)
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_time_once(bases, scalars, ntt_data, args.cpu_ntt_log_n)
@@ -425,7 +434,7 @@ def run_b200(args):
         hs = scalars[: 1 << ml].cpu().numpy().view(np.uint64)
         hn = ntt_data[: 1 << nl].cpu().numpy().view(np.uint64)
         tm, tn = cpu_time_once(hb, hs, hn, nl)
-        cores = C.num_threads()
+        cores = host_threads()
         cpu = {"value": (1 << ml) / tm / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
                "sample": f"first 2^{ml} of the same bases/scalars, {tm:.2f} s; C restatement of snarkVM standard::msm "
                          f"(c = ln n + 2, Jacobian buckets), OpenMP over windows; NOT snarkVM itself (no Rust toolchain)"}
