@@ -91,8 +91,8 @@ b200_error_t b200_msm_register_bases(const void* points, size_t npoints, size_t 
                                      uint64_t* out_handle);
 b200_error_t b200_msm_register_bases_device(const void* d_points, size_t npoints, size_t affine_stride,
                                             void* stream, uint64_t* out_handle);
-/* Same, and additionally tabulates 2^(c*w) * P_i for every window w in HBM (nwin * npoints * 96 bytes: 17.7 GB for
- * a 2^24-point SRS at c = 24 -- a B200 has 180 GB): MSMs against the handle then share ONE bucket set across windows,
+/* Same, and additionally tabulates 2^(c*w) * P_i for every window w in HBM (nwin * npoints * 128 bytes: 27.9 GB for
+ * a 2^24-point SRS at the automatic c = 20 -- a B200 has 180 GB): MSMs against the handle then share ONE bucket set across windows,
  * skip the window fold and reduce 2^(c-1) buckets once.  window_bits 0 = automatic (16..24).  Registration costs about
  * 2900 Fq products per point, once. */
 b200_error_t b200_msm_register_bases_tabulated(const void* points, size_t npoints, size_t affine_stride,
