@@ -19,7 +19,8 @@
  *   Fr element      32 B, Montgomery form (value * 2^256 mod r), fully reduced
  *   Fq element      48 B, Montgomery form (value * 2^384 mod p), fully reduced
  *   G1Affine        `affine_stride` bytes (104 for rustc's layout): x @0, y @48, infinity flag byte @96
- *   scalar          32 B BigInteger256, canonical (NOT Montgomery), < r
+ *   scalar          32 B BigInteger256, canonical (NOT Montgomery), < r (a non-canonical value k >= r is reduced mod r
+ *                   on the device: the result is still k * P)
  *   G1Projective    144 B Jacobian (X, Y, Z) Montgomery; Z = 0 <=> infinity (returned as (1, 1, 0))
  *
  * Error model: every call returns b200_error_t; code == 0 is success, code > 0 is a cudaError_t,
@@ -62,6 +63,15 @@ b200_error_t b200_init(int device);
 void b200_shutdown(void);
 /* ABI version of this header (for the -sys crate's build-time check). */
 uint32_t b200_abi_version(void);
+/* Tuning knobs.  The B200_* environment variables are read once, on first use; this call changes a knob afterwards
+ * (sweep tools, tests, the -sys crate's init).  Keys: msm_window_bits, msm_glv, msm_affine_rounds, msm_slices,
+ * msm_chunk, msm_host_pipeline, msm_host_first_log, msm_auto_table, msm_list_budget_bytes, msm_fuse_denoms,
+ * msm_queue_threshold, ntt_plan ("a,b,c"), ntt_tile_log, ntt_radix4, ntt_boundary_tables, ntt_host_pipeline, ntt_variant,
+ * staged_copies, graphs.  Unknown key -> B200_ERR_INVALID_ARG. */
+b200_error_t b200_set_option(const char* key, const char* value);
+/* Observable fallbacks / activity: kernel_launches, msm_xyzz_fallbacks (calls whose pair-round lists did not fit in HBM
+ * and ran the XYZZ-only accumulation), queue_submits, queue_batches, graph_captures, graph_replays. */
+b200_error_t b200_get_counter(const char* name, uint64_t* out);
 
 /* ---- VariableBase::msm ------------------------------------------------------------------------
  * out_jacobian_144B = sum_i scalars[i] * points[i].  Host buffers; copies are done internally.    */
@@ -82,6 +92,18 @@ b200_error_t b200_msm_batch_g1_bls12_377(void* out_jacobian, const void* points,
 b200_error_t b200_msm_batch_g1_bls12_377_device(void* d_out_jacobian, const void* d_points, const void* d_scalars,
                                                 const void* d_offsets_u64, size_t nmsm, size_t npoints,
                                                 size_t affine_stride, void* stream);
+
+/* Coalescing queue for concurrent SMALL MSMs (BASELINE configs[3]: a validator verifies the transactions of a block on
+ * up to 512 threads -- /root/reference/cli/src/commands/start.rs:623-640, node/bft/ledger-service/src/ledger.rs:341-347 --
+ * and each verification ends in VariableBase::msm calls over tens of points).  b200_msm_submit enqueues one MSM and
+ * returns a ticket at once; a dispatcher thread packs everything pending into ONE segmented launch set; b200_msm_wait
+ * blocks until that MSM is done and copies its 144-byte result.  points / scalars must stay valid until the wait
+ * returns; a ticket is waited on exactly once.  No lock is held while the GPU works.  With option
+ * msm_queue_threshold = T, b200_msm_g1_bls12_377 routes every call of <= T points through this queue by itself, so the
+ * Rust call sites need no change. */
+b200_error_t b200_msm_submit(const void* points, size_t npoints, const void* scalars_32B_canonical, size_t affine_stride,
+                             uint64_t* out_ticket);
+b200_error_t b200_msm_wait(uint64_t ticket, void* out_jacobian_144B);
 
 /* Resident bases (the SRS `powers_of_beta_g` is fixed for the process lifetime -- KZG10::commit
  * [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs] calls msm on a prefix of it every time).  Sets of 2^10 .. 2^20

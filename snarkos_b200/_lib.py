@@ -27,6 +27,10 @@ SYMBOLS = {
     "b200_init": (b200_error_t, [_i]),
     "b200_shutdown": (None, []),
     "b200_abi_version": (_u32, []),
+    "b200_set_option": (b200_error_t, [ctypes.c_char_p, ctypes.c_char_p]),
+    "b200_get_counter": (b200_error_t, [ctypes.c_char_p, ctypes.POINTER(_u64)]),
+    "b200_msm_submit": (b200_error_t, [_vp, _sz, _vp, _sz, ctypes.POINTER(_u64)]),
+    "b200_msm_wait": (b200_error_t, [_u64, _vp]),
     "b200_msm_g1_bls12_377": (b200_error_t, [_vp, _vp, _sz, _vp, _sz]),
     "b200_msm_g1_bls12_377_device": (b200_error_t, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200_msm_batch_g1_bls12_377": (b200_error_t, [_vp, _vp, _vp, _vp, _sz, _sz]),
@@ -115,6 +119,17 @@ class profile:
         for k, v in self.stages:
             out[k] = out.get(k, 0.0) + v
         return out
+
+
+def set_option(key: str, value) -> None:
+    """b200_set_option: change a tuning knob at run time (the B200_* environment is only read on first use)."""
+    check(lib().b200_set_option(key.encode(), str(value).encode()))
+
+
+def counter(name: str) -> int:
+    v = _u64(0)
+    check(lib().b200_get_counter(name.encode(), ctypes.byref(v)))
+    return int(v.value)
 
 
 def kernel_launch_count() -> int:

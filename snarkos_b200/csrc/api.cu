@@ -3,7 +3,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <unordered_map>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "common.cuh"
 #include "msm_core.cuh"
@@ -27,39 +30,119 @@ struct ApiState {
     std::unordered_map<uint64_t, RegisteredBases> bases;
     uint64_t next_handle = 1;
     std::vector<cudaStream_t> streams;       // every per-thread stream ever created (for shutdown)
+    uint64_t generation = 0;                 // bumped by every successful b200_init: stale per-thread streams are dropped
+    bool generator_uploaded = false;         // c_gen_x / c_gen_y live in the bound device's constant memory
 };
 static ApiState g_api;
 
 struct ThreadStream {
     cudaStream_t s = nullptr;
+    uint64_t generation = 0;
 };
+// the calling thread's stream of this kind, (re)created when the library was shut down and bound again
+static cudaStream_t thread_stream_get(ThreadStream& t, bool high_priority) {
+    if (t.s && t.generation == g_api.generation) return t.s;
+    cudaStream_t s = nullptr;
+    cudaError_t e;
+    if (high_priority) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);               // hi = numerically smallest = highest priority
+        e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi);
+    } else {
+        e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    t.s = s;
+    t.generation = g_api.generation;
+    g_api.streams.push_back(s);
+    return s;
+}
 static thread_local ThreadStream t_stream;
 
-cudaStream_t b200_thread_stream() {
-    if (!t_stream.s) {
-        cudaStream_t s = nullptr;
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        t_stream.s = s;
-        std::lock_guard<std::mutex> lock(g_api.mu);
-        g_api.streams.push_back(s);
-    }
-    return t_stream.s;
-}
+cudaStream_t b200_thread_stream() { return thread_stream_get(t_stream, false); }
 
 // High-priority helper stream of the calling thread: the MSM runs the memory-bound half of a pair round (denominators
 // + inversion of slice i + 1) on it while the compute-bound half (additions of slice i) occupies the caller's stream.
 static thread_local ThreadStream t_aux_stream;
-cudaStream_t b200_thread_aux_stream() {
-    if (!t_aux_stream.s) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);               // hi = numerically smallest = highest priority
-        cudaStream_t s = nullptr;
-        if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-        t_aux_stream.s = s;
-        std::lock_guard<std::mutex> lock(g_api.mu);
-        g_api.streams.push_back(s);
-    }
-    return t_aux_stream.s;
+cudaStream_t b200_thread_aux_stream() { return thread_stream_get(t_aux_stream, true); }
+
+B200Counters g_counters;
+
+// ---------------------------------------------------------------------------------------------
+// tuning knobs: environment read once, b200_set_option afterwards
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static void config_from_env(B200Config& c) {
+    c.msm_c = env_int("B200_MSM_C", 0);
+    c.msm_glv = !getenv("B200_MSM_NO_GLV");
+    c.msm_affine_rounds = env_int("B200_MSM_AFFINE_ROUNDS", -1);
+    c.msm_slices = env_int("B200_MSM_SLICES", 1);
+    c.msm_chunk = env_int("B200_MSM_CHUNK", 0);
+    c.msm_host_pipeline = !getenv("B200_MSM_NO_HOST_PIPELINE");
+    c.msm_host_first_log = env_int("B200_MSM_HOST_FIRST_LOG", 20);
+    c.msm_auto_table = !getenv("B200_MSM_NO_AUTO_TABLE");
+    c.msm_fuse_denoms = getenv("B200_MSM_NO_FUSE_DENOMS") ? 0 : 1;
+    c.msm_queue_threshold = env_int("B200_MSM_QUEUE_THRESHOLD", 0);
+    if (const char* e = getenv("B200_NTT_PLAN")) { strncpy(c.ntt_plan, e, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
+    c.ntt_tile_log = env_int("B200_NTT_TILE_LOG", 11);
+    c.ntt_radix4 = !getenv("B200_NTT_RADIX2");
+    c.ntt_boundary_tables = !getenv("B200_NTT_NO_BOUNDARY_TABLES");
+    c.ntt_host_pipeline = !getenv("B200_NTT_NO_HOST_PIPELINE");
+    c.ntt_variant = env_int("B200_NTT_VARIANT", 0);
+    c.staged_copies = !getenv("B200_NO_STAGED_COPIES");
+    c.l2_fetch_granularity = env_int("B200_L2_FETCH_GRANULARITY", 0);
+    c.graphs = !getenv("B200_NO_GRAPHS");
+}
+B200Config& b200_config() {
+    static B200Config cfg;
+    static std::once_flag once;
+    std::call_once(once, [] { config_from_env(cfg); });
+    return cfg;
+}
+
+extern "C" b200_error_t b200_set_option(const char* key, const char* value) {
+    if (!key || !value) return b200_err(B200_ERR_INVALID_ARG, "set_option: null argument");
+    B200Config& c = b200_config();
+    const int v = atoi(value);
+    const std::string k(key);
+    if (k == "msm_window_bits") c.msm_c = v;
+    else if (k == "msm_glv") c.msm_glv = v != 0;
+    else if (k == "msm_affine_rounds") c.msm_affine_rounds = v;
+    else if (k == "msm_slices") c.msm_slices = v;
+    else if (k == "msm_chunk") c.msm_chunk = v;
+    else if (k == "msm_host_pipeline") c.msm_host_pipeline = v != 0;
+    else if (k == "msm_host_first_log") c.msm_host_first_log = v;
+    else if (k == "msm_auto_table") c.msm_auto_table = v != 0;
+    else if (k == "msm_list_budget_bytes") c.msm_list_budget = strtoull(value, nullptr, 0);
+    else if (k == "msm_fuse_denoms") c.msm_fuse_denoms = v;
+    else if (k == "msm_queue_threshold") c.msm_queue_threshold = v;
+    else if (k == "ntt_plan") { strncpy(c.ntt_plan, value, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
+    else if (k == "ntt_tile_log") c.ntt_tile_log = v;
+    else if (k == "ntt_radix4") c.ntt_radix4 = v != 0;
+    else if (k == "ntt_boundary_tables") c.ntt_boundary_tables = v != 0;
+    else if (k == "ntt_host_pipeline") c.ntt_host_pipeline = v != 0;
+    else if (k == "ntt_variant") c.ntt_variant = v;
+    else if (k == "staged_copies") c.staged_copies = v != 0;
+    else if (k == "graphs") c.graphs = v != 0;
+    else return b200_err(B200_ERR_INVALID_ARG, "set_option: unknown key");
+    return b200_ok();
+}
+
+extern "C" b200_error_t b200_get_counter(const char* name, uint64_t* out) {
+    if (!name || !out) return b200_err(B200_ERR_INVALID_ARG, "get_counter: null argument");
+    const std::string k(name);
+    if (k == "kernel_launches") *out = g_kernel_launches.load();
+    else if (k == "msm_xyzz_fallbacks") *out = g_counters.msm_xyzz_fallbacks.load();
+    else if (k == "queue_submits") *out = g_counters.queue_submits.load();
+    else if (k == "queue_batches") *out = g_counters.queue_batches.load();
+    else if (k == "graph_replays") *out = g_counters.graph_replays.load();
+    else if (k == "graph_captures") *out = g_counters.graph_captures.load();
+    else return b200_err(B200_ERR_INVALID_ARG, "get_counter: unknown counter");
+    return b200_ok();
 }
 
 b200_error_t b200_require_device() {
@@ -73,12 +156,17 @@ b200_error_t b200_require_device() {
     return b200_init(-1);
 }
 
-extern "C" uint32_t b200_abi_version(void) { return 1; }
+extern "C" uint32_t b200_abi_version(void) { return 2; }
 extern "C" uint64_t b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 extern "C" b200_error_t b200_init(int device) {
     std::lock_guard<std::mutex> lock(g_api.mu);
-    if (g_api.initialized && (device < 0 || device == g_api.device)) return b200_ok();
+    if (g_api.initialized) {
+        // One process drives ONE GPU: every cache of this library (registered bases, NTT tables, constant memory,
+        // per-thread streams and staging slots) lives on g_api.device.  Re-binding needs b200_shutdown first.
+        if (device < 0 || device == g_api.device) return b200_ok();
+        return b200_err(B200_ERR_INVALID_ARG, "b200_init: already bound to another device; call b200_shutdown first");
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -98,20 +186,23 @@ extern "C" b200_error_t b200_init(int device) {
         uint64_t threshold = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
-    if (const char* e = getenv("B200_L2_FETCH_GRANULARITY")) {
+    const B200Config& cfg = b200_config();
+    if (cfg.l2_fetch_granularity) {
         size_t before = 0, after = 0;
         cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-        cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+        cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)cfg.l2_fetch_granularity);
         cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
         fprintf(stderr, "[b200] L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(le));
         (void)cudaGetLastError();
     }
     g_api.device = device;
+    g_api.generation++;
     g_api.initialized = true;
     return b200_ok();
 }
 
 extern "C" void b200_shutdown(void) {
+    b200_queue_shutdown();                        // drains and joins the submit/wait dispatcher (queue.cu)
     std::lock_guard<std::mutex> lock(g_api.mu);
     if (!g_api.initialized) return;
     cudaSetDevice(g_api.device);
@@ -119,8 +210,31 @@ extern "C" void b200_shutdown(void) {
     for (auto& kv : g_api.bases) cudaFree(kv.second.d_packed);
     g_api.bases.clear();
     ntt_release_tables();
+    msm_release_graphs();
+    hostcopy_release();
+    // per-thread streams: the owning threads notice the new generation and create fresh ones on their next call
+    for (cudaStream_t s : g_api.streams) cudaStreamDestroy(s);
+    g_api.streams.clear();
+    g_api.generator_uploaded = false;
     g_api.initialized = false;
+    g_api.device = -1;
 }
+
+// ---------------------------------------------------------------------------------------------
+// NVTX ranges
+// ---------------------------------------------------------------------------------------------
+static thread_local bool t_nvtx_stage_open = false;
+void b200_nvtx_stage(const char* name) {
+    if (t_nvtx_stage_open) nvtxRangePop();
+    nvtxRangePushA(name);
+    t_nvtx_stage_open = true;
+}
+void b200_nvtx_stage_end() {
+    if (t_nvtx_stage_open) nvtxRangePop();
+    t_nvtx_stage_open = false;
+}
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 // ---------------------------------------------------------------------------------------------
 // per-stage profiling (thread-local)
@@ -132,9 +246,12 @@ static thread_local bool t_prof_open = false;
 
 bool& StageTimer::enabled() { return t_prof_on; }
 void StageTimer::mark(const char* name, cudaStream_t stream) {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, stream);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess || cudaEventRecord(e, stream) != cudaSuccess) {
+        (void)cudaGetLastError();                  // profiling is best effort: a stage without events reports 0 ms
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
     if (t_prof_open) t_prof.back().stop = e;
     cudaEvent_t e2 = e;
     t_prof.push_back(StageRec{name, e2, nullptr});
@@ -142,9 +259,12 @@ void StageTimer::mark(const char* name, cudaStream_t stream) {
 }
 void StageTimer::finish(cudaStream_t stream) {
     if (!t_prof_open) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, stream);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess || cudaEventRecord(e, stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
     t_prof.back().stop = e;
     t_prof_open = false;
 }
@@ -192,33 +312,14 @@ extern "C" b200_error_t b200_msm_g1_bls12_377_device(void* d_out, const void* d_
 
 // Second per-thread stream: host->device copies of the next point range overlap the MSM of the current one.
 static thread_local ThreadStream t_copy_stream;
-static cudaStream_t b200_thread_copy_stream() {
-    if (!t_copy_stream.s) {
-        cudaStream_t s = nullptr;
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        t_copy_stream.s = s;
-        std::lock_guard<std::mutex> lock(g_api.mu);
-        g_api.streams.push_back(s);
-    }
-    return t_copy_stream.s;
-}
+cudaStream_t b200_thread_copy_stream() { return thread_stream_get(t_copy_stream, false); }
 
 // host-buffer calls with >= 2^23 points stream the inputs in point ranges that grow geometrically: 2^20, 2^20, 2^21,
 // ... capped at 2^23.  Only the first (small) range crosses PCIe with nothing to overlap; every later range is twice the
 // one being accumulated, and a range takes about twice as long to accumulate as to transfer (~5 vs ~2.5 ns per point).
 static thread_local ThreadStream t_copy_stream2;
-static cudaStream_t b200_thread_copy_stream2() {
-    if (!t_copy_stream2.s) {
-        cudaStream_t s = nullptr;
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        t_copy_stream2.s = s;
-        std::lock_guard<std::mutex> lock(g_api.mu);
-        g_api.streams.push_back(s);
-    }
-    return t_copy_stream2.s;
-}
+cudaStream_t b200_thread_copy_stream2() { return thread_stream_get(t_copy_stream2, false); }
 
-#define MSM_HOST_FIRST_LOG 20
 #define MSM_HOST_CHUNK_LOG 23
 
 extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, size_t n, const void* scalars,
@@ -226,10 +327,16 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     B200_TRY(b200_require_device());
     if (!out) return b200_err(B200_ERR_INVALID_ARG, "msm: null output pointer");
     if (n && (!points || !scalars)) return b200_err(B200_ERR_INVALID_ARG, "msm: null input pointer");
+    if (n && n <= (size_t)b200_config().msm_queue_threshold && stride >= 104 && !(stride & 7)) {
+        // small call while many threads verify in parallel (configs[3]): coalesced with its neighbours (queue.cu)
+        uint64_t ticket = 0;
+        B200_TRY(b200_msm_submit(points, n, scalars, stride, &ticket));
+        return b200_msm_wait(ticket, out);
+    }
     cudaStream_t s = b200_thread_stream();
     if (!s) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
     const size_t chunk = (size_t)1 << MSM_HOST_CHUNK_LOG;
-    if (n < chunk || getenv("B200_MSM_NO_HOST_PIPELINE")) {
+    if (n < chunk || !b200_config().msm_host_pipeline) {
         DevBuf d_pts, d_sc, d_out;
         CUDA_TRY(d_pts.alloc(n * stride, s));
         CUDA_TRY(d_sc.alloc(n * 32, s));
@@ -249,8 +356,7 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     cudaStream_t cs = b200_thread_copy_stream();
     if (!cs) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
     std::vector<size_t> range_off, range_cnt;
-    uint32_t first_log = MSM_HOST_FIRST_LOG;
-    if (const char* e = getenv("B200_MSM_HOST_FIRST_LOG")) first_log = (uint32_t)atoi(e);
+    uint32_t first_log = (uint32_t)b200_config().msm_host_first_log;
     if (first_log < 16) first_log = 16;
     if (first_log > MSM_HOST_CHUNK_LOG) first_log = MSM_HOST_CHUNK_LOG;
     for (size_t done = 0, cur = (size_t)1 << first_log; done < n;) {
@@ -269,15 +375,18 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     CUDA_TRY(d_out.alloc(144, s));
     void* session = nullptr;
     B200_TRY(msm_stream_begin(&session, n, s));
-    std::vector<cudaEvent_t> copied(nchunks), computed(nchunks);
-    cudaEvent_t ready;
-    cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-    for (size_t i = 0; i < nchunks; i++) {
-        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming);
-    }
+    std::vector<cudaEvent_t> copied(nchunks, nullptr), computed(nchunks, nullptr);
+    cudaEvent_t ready = nullptr;
     b200_error_t rc = b200_ok();
     {
+        cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+        for (size_t i = 0; i < nchunks && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) rc = b200_cuda_err(e);
+    }
+    if (rc.code == 0) {
         cudaError_t e = cudaEventRecord(ready, s);                 // staging buffers exist from here on in stream order
         if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ready, 0);
         if (e != cudaSuccess) rc = b200_cuda_err(e);
@@ -310,8 +419,11 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     cudaStreamSynchronize(cs);
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (rc.code == 0 && e2 != cudaSuccess) rc = b200_cuda_err(e2);
-    cudaEventDestroy(ready);
-    for (size_t i = 0; i < nchunks; i++) { cudaEventDestroy(copied[i]); cudaEventDestroy(computed[i]); }
+    if (ready) cudaEventDestroy(ready);
+    for (size_t i = 0; i < nchunks; i++) {
+        if (copied[i]) cudaEventDestroy(copied[i]);
+        if (computed[i]) cudaEventDestroy(computed[i]);
+    }
     return rc;
 }
 
@@ -364,7 +476,7 @@ extern "C" b200_error_t b200_msm_register_bases_device(const void* d_points, siz
     // Sets of the size a Varuna circuit commits against (2^10 .. 2^20 powers) get their window table right away:
     // 16 x the memory (2 GiB at 2^20) buys MSMs with one bucket set and NO window fold -- the 253 - c dependent
     // doublings that are half of a small call (2^16: 4.4 -> 2.6 ms per commit, 2^18: 7.3 -> 3.3 ms).
-    if (n >= ((size_t)1 << 10) && n <= ((size_t)1 << 20) && !getenv("B200_MSM_NO_AUTO_TABLE"))
+    if (n >= ((size_t)1 << 10) && n <= ((size_t)1 << 20) && b200_config().msm_auto_table)
         return b200_msm_register_bases_tabulated_device(d_points, n, stride, 0, stream, out_handle);
     void* d_packed = nullptr;
     const bool glv = msm_glv_enabled();                 // larger sets: both P_i and phi(P_i) resident (2 x 128 B per point)
@@ -559,7 +671,7 @@ extern "C" b200_error_t b200_ntt_fr_bls12_377(void* inout, uint32_t log_n, size_
     // and download of group g - 1 run together (PCIe is full duplex), so a large batch costs about one direction of the
     // transfer instead of both plus the compute (2^20 x 16: the call is PCIe-bound either way).
     size_t ngroups = 1;
-    if (batch >= 2 && !getenv("B200_NTT_NO_HOST_PIPELINE")) {
+    if (batch >= 2 && b200_config().ntt_host_pipeline) {
         ngroups = bytes / ((size_t)32 << 20);                     // groups of >= 32 MiB
         if (ngroups > batch) ngroups = batch;
         if (ngroups > 8) ngroups = 8;
@@ -670,13 +782,11 @@ __global__ void __launch_bounds__(128) synthetic_bases_kernel(uint8_t* out, size
 }
 
 static b200_error_t upload_generator() {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
-        err = cudaMemcpyToSymbol(c_gen_x, G1_GEN_X, sizeof(G1_GEN_X));
-        if (err == cudaSuccess) err = cudaMemcpyToSymbol(c_gen_y, G1_GEN_Y, sizeof(G1_GEN_Y));
-    });
-    if (err != cudaSuccess) return b200_cuda_err(err);
+    std::lock_guard<std::mutex> lock(g_api.mu);
+    if (g_api.generator_uploaded) return b200_ok();      // per bound device: b200_shutdown clears the flag
+    CUDA_TRY(cudaMemcpyToSymbol(c_gen_x, G1_GEN_X, sizeof(G1_GEN_X)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_gen_y, G1_GEN_Y, sizeof(G1_GEN_Y)));
+    g_api.generator_uploaded = true;
     return b200_ok();
 }
 

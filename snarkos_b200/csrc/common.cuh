@@ -33,6 +33,44 @@ static inline b200_error_t b200_cuda_err(cudaError_t e) { return b200_error_t{(i
         if (_e != cudaSuccess) return b200_cuda_err(_e);  \
     } while (0)
 
+// Tuning knobs.  The B200_* environment variables are read ONCE, when the library is first used (b200_init or the first
+// compute call); afterwards b200_set_option changes them at run time (sweep tools, tests).  Nothing on the call path calls
+// getenv.
+struct B200Config {
+    int msm_c = 0;                   // msm_window_bits          B200_MSM_C             0 = automatic
+    bool msm_glv = true;             // msm_glv                  B200_MSM_NO_GLV
+    int msm_affine_rounds = -1;      // msm_affine_rounds        B200_MSM_AFFINE_ROUNDS -1 = automatic
+    int msm_slices = 1;              // msm_slices               B200_MSM_SLICES
+    int msm_chunk = 0;               // msm_chunk                B200_MSM_CHUNK         0 = automatic
+    bool msm_host_pipeline = true;   // msm_host_pipeline        B200_MSM_NO_HOST_PIPELINE
+    int msm_host_first_log = 20;     // msm_host_first_log       B200_MSM_HOST_FIRST_LOG
+    bool msm_auto_table = true;      // msm_auto_table           B200_MSM_NO_AUTO_TABLE
+    unsigned long long msm_list_budget = 0;   // msm_list_budget_bytes: cap on the pair-round scratch of ONE call
+                                     //                          (0 = whatever cudaMallocAsync grants); above it the call
+                                     //                          runs the XYZZ-only path, exactly as on an allocation failure
+    int msm_queue_threshold = 0;     // msm_queue_threshold      B200_MSM_QUEUE_THRESHOLD  host MSMs of <= this many points go
+                                     //                          through the coalescing queue (queue.cu); 0 = off
+    int msm_fuse_denoms = 1;         // msm_fuse_denoms          B200_MSM_NO_FUSE_DENOMS (pair round r computes round r+1's denominators)
+    char ntt_plan[32] = {0};         // ntt_plan "a,b,c"         B200_NTT_PLAN
+    int ntt_tile_log = 11;           // ntt_tile_log             B200_NTT_TILE_LOG
+    bool ntt_radix4 = true;          // ntt_radix4               B200_NTT_RADIX2
+    bool ntt_boundary_tables = true; // ntt_boundary_tables      B200_NTT_NO_BOUNDARY_TABLES
+    bool ntt_host_pipeline = true;   // ntt_host_pipeline        B200_NTT_NO_HOST_PIPELINE
+    int ntt_variant = 0;             // ntt_variant              B200_NTT_VARIANT       0 = default kernel selection
+    bool staged_copies = true;       // staged_copies            B200_NO_STAGED_COPIES
+    int l2_fetch_granularity = 0;    // (init only)              B200_L2_FETCH_GRANULARITY
+    bool graphs = true;              // graphs                   B200_NO_GRAPHS         CUDA-graph replay of small calls
+};
+B200Config& b200_config();           // loaded from the environment on first use
+
+// fallbacks and queue activity the caller can observe (b200_get_counter)
+struct B200Counters {
+    std::atomic<uint64_t> msm_xyzz_fallbacks{0};     // pair rounds skipped: lists did not fit (allocation failure / budget)
+    std::atomic<uint64_t> queue_submits{0}, queue_batches{0};
+    std::atomic<uint64_t> graph_replays{0}, graph_captures{0};
+};
+extern B200Counters g_counters;
+
 // stream-ordered scratch buffer (freed on the same stream when it goes out of scope)
 struct DevBuf {
     void* p = nullptr;
@@ -56,8 +94,16 @@ struct StageTimer {
     static void mark(const char* name, cudaStream_t stream);     // start of stage `name` (ends the previous one)
     static void finish(cudaStream_t stream);                      // end of the last stage of a call
 };
-#define STAGE(name, stream) do { if (StageTimer::enabled()) StageTimer::mark(name, stream); } while (0)
-#define STAGE_END(stream) do { if (StageTimer::enabled()) StageTimer::finish(stream); } while (0)
+// NVTX ranges (header-only nvtx3: a no-op costing one pointer check unless a profiler is attached) around every stage
+// of a call and around the host <-> device copies, so nsys / ncu timelines read H2D | stage | stage | ... | D2H.
+void b200_nvtx_stage(const char* name);                          // closes the calling thread's open stage range, opens `name`
+void b200_nvtx_stage_end();
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+#define STAGE(name, stream) do { b200_nvtx_stage(name); if (StageTimer::enabled()) StageTimer::mark(name, stream); } while (0)
+#define STAGE_END(stream) do { b200_nvtx_stage_end(); if (StageTimer::enabled()) StageTimer::finish(stream); } while (0)
 
 // internal entry points (device pointers, caller-provided stream)
 b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction,
@@ -84,6 +130,11 @@ b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t 
 b200_error_t b200_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream);
 b200_error_t b200_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream);
 void ntt_release_tables();
+void msm_release_graphs();           // cached CUDA graphs of small MSMs (msm.cu)
+void hostcopy_release();             // pinned staging slots (hostcopy.cu)
+void b200_queue_shutdown();          // submit / wait dispatcher (queue.cu)
+cudaStream_t b200_thread_copy_stream();
+cudaStream_t b200_thread_copy_stream2();
 b200_error_t b200_require_device();
 cudaStream_t b200_thread_stream();
 cudaStream_t b200_thread_aux_stream();

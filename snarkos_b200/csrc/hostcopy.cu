@@ -10,6 +10,7 @@
 // ordered inside the caller's stream: the uploads start after everything already queued on it and the stream resumes
 // when the last slice has landed.
 #include <cstring>
+#include <system_error>
 #include <thread>
 
 #include "common.cuh"
@@ -24,18 +25,37 @@ struct HcWorker {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;
 };
-// one staging set per calling thread (the ABI is re-entrant: concurrent callers must not share slots)
+// One staging set = 8 workers x 2 pinned 4 MiB slots (64 MiB), 8 streams, 25 events.  Sets live in a small PROCESS-WIDE
+// pool: a call checks one out under the mutex and returns it when its copies are queued, so short-lived caller threads
+// (tokio's blocking pool creates and retires threads) neither leak pinned memory nor pay the pinning again, and
+// b200_shutdown releases everything.  Concurrent callers never share a set; at most HC_MAX_SETS exist, a caller that
+// finds none free takes the driver's own pageable path for that copy (slower, never wrong).
 struct HcPool {
     HcWorker w[HC_WORKERS];
     cudaEvent_t start = nullptr;
     bool ready = false;
-    bool failed = false;
+    bool busy = false;
 };
-static thread_local HcPool t_pool;
+#define HC_MAX_SETS 4
+static std::mutex g_hc_mu;
+static HcPool g_hc_sets[HC_MAX_SETS];
+
+static void hc_destroy(HcPool& p) {
+    if (p.start) cudaEventDestroy(p.start);
+    for (int k = 0; k < HC_WORKERS; k++) {
+        HcWorker& w = p.w[k];
+        if (w.st) cudaStreamDestroy(w.st);
+        if (w.done) cudaEventDestroy(w.done);
+        for (int s = 0; s < 2; s++) {
+            if (w.slot[s]) cudaFreeHost(w.slot[s]);
+            if (w.ev[s]) cudaEventDestroy(w.ev[s]);
+        }
+    }
+    p = HcPool();
+}
 
 static bool hc_prepare(HcPool& p) {
     if (p.ready) return true;
-    if (p.failed) return false;
     bool ok = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < HC_WORKERS && ok; k++) {
         HcWorker& w = p.w[k];
@@ -47,11 +67,33 @@ static bool hc_prepare(HcPool& p) {
     }
     if (!ok) {
         (void)cudaGetLastError();
-        p.failed = true;                       // fall back to the driver's pageable path, never to a CPU computation
+        hc_destroy(p);                         // fall back to the driver's pageable path, never to a CPU computation
         return false;
     }
     p.ready = true;
     return true;
+}
+
+// a free staging set, or nullptr (all in use / pinning failed)
+static HcPool* hc_checkout() {
+    std::lock_guard<std::mutex> lock(g_hc_mu);
+    for (int i = 0; i < HC_MAX_SETS; i++) {
+        HcPool& p = g_hc_sets[i];
+        if (p.busy) continue;
+        if (!hc_prepare(p)) return nullptr;
+        p.busy = true;
+        return &p;
+    }
+    return nullptr;
+}
+static void hc_return(HcPool* p) {
+    std::lock_guard<std::mutex> lock(g_hc_mu);
+    p->busy = false;
+}
+void hostcopy_release() {
+    std::lock_guard<std::mutex> lock(g_hc_mu);
+    for (int i = 0; i < HC_MAX_SETS; i++)
+        if (!g_hc_sets[i].busy) hc_destroy(g_hc_sets[i]);
 }
 
 static bool hc_is_pageable(const void* host) {
@@ -64,8 +106,7 @@ static bool hc_is_pageable(const void* host) {
 }
 
 // direction 0: host -> device, 1: device -> host
-static b200_error_t hc_staged(void* dst, const void* src, size_t bytes, int direction, cudaStream_t stream) {
-    HcPool& p = t_pool;
+static b200_error_t hc_staged(HcPool& p, void* dst, const void* src, size_t bytes, int direction, cudaStream_t stream) {
     int device = 0;
     CUDA_TRY(cudaGetDevice(&device));
     CUDA_TRY(cudaEventRecord(p.start, stream));
@@ -73,9 +114,11 @@ static b200_error_t hc_staged(void* dst, const void* src, size_t bytes, int dire
     const int nworkers = nslices < HC_WORKERS ? (int)nslices : HC_WORKERS;
     cudaError_t errs[HC_WORKERS];
     std::thread th[HC_WORKERS];
+    int started = 0;
+    bool spawn_failed = false;
     for (int k = 0; k < nworkers; k++) {
         errs[k] = cudaSuccess;
-        th[k] = std::thread([&, k]() {
+        auto body = [&, k]() {
             HcWorker& w = p.w[k];
             cudaError_t e = cudaSetDevice(device);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(w.st, p.start, 0);
@@ -107,9 +150,20 @@ static b200_error_t hc_staged(void* dst, const void* src, size_t bytes, int dire
             }
             if (e == cudaSuccess) e = cudaEventRecord(w.done, w.st);
             errs[k] = e;
-        });
+        };
+        // nothing may throw across the extern "C" boundary: if the OS refuses a thread, this worker's share runs here
+        if (!spawn_failed) {
+            try {
+                th[k] = std::thread(body);
+                started = k + 1;
+                continue;
+            } catch (const std::system_error&) {
+                spawn_failed = true;
+            }
+        }
+        body();
     }
-    for (int k = 0; k < nworkers; k++) th[k].join();
+    for (int k = 0; k < started; k++) th[k].join();
     for (int k = 0; k < nworkers; k++)
         if (errs[k] != cudaSuccess) return b200_cuda_err(errs[k]);
     for (int k = 0; k < nworkers; k++) CUDA_TRY(cudaStreamWaitEvent(stream, p.w[k].done, 0));
@@ -120,8 +174,14 @@ static b200_error_t hc_staged(void* dst, const void* src, size_t bytes, int dire
 // stream reaches the copy (pinned path, as with cudaMemcpyAsync).
 b200_error_t b200_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
     if (bytes == 0) return b200_ok();
-    if (bytes >= HC_MIN_STAGED && !getenv("B200_NO_STAGED_COPIES") && hc_is_pageable(h_src) && hc_prepare(t_pool))
-        return hc_staged(d_dst, h_src, bytes, 0, stream);
+    NvtxRange range("b200_h2d");
+    if (bytes >= HC_MIN_STAGED && b200_config().staged_copies && hc_is_pageable(h_src)) {
+        if (HcPool* p = hc_checkout()) {
+            const b200_error_t r = hc_staged(*p, d_dst, h_src, bytes, 0, stream);
+            hc_return(p);
+            return r;
+        }
+    }
     CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
     return b200_ok();
 }
@@ -130,8 +190,14 @@ b200_error_t b200_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t
 // destination: as with cudaMemcpyAsync (synchronise the stream before reading).
 b200_error_t b200_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream) {
     if (bytes == 0) return b200_ok();
-    if (bytes >= HC_MIN_STAGED && !getenv("B200_NO_STAGED_COPIES") && hc_is_pageable(h_dst) && hc_prepare(t_pool))
-        return hc_staged(h_dst, d_src, bytes, 1, stream);
+    NvtxRange range("b200_d2h");
+    if (bytes >= HC_MIN_STAGED && b200_config().staged_copies && hc_is_pageable(h_dst)) {
+        if (HcPool* p = hc_checkout()) {
+            const b200_error_t r = hc_staged(*p, h_dst, d_src, bytes, 1, stream);
+            hc_return(p);
+            return r;
+        }
+    }
     CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream));
     return b200_ok();
 }

@@ -70,8 +70,9 @@ __global__ void msm_glv_split_kernel(uint4* __restrict__ half, const uint4* __re
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
-    const uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t k[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t k1[4], k2[4];
+    msm_scalar_reduce(k);
     msm_glv_split(k, k1, k2);
     half[2 * i] = make_uint4(k1[0], k1[1], k1[2], k1[3]);
     half[2 * i + 1] = make_uint4(k2[0], k2[1], k2[2], k2[3]);
@@ -128,6 +129,7 @@ __device__ __forceinline__ void msm_load_scalar(uint32_t* s, const uint4* __rest
     } else {
         const uint4 a = scalars[2 * i], b = scalars[2 * i + 1];
         s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+        msm_scalar_reduce(s);
     }
 }
 
@@ -572,8 +574,8 @@ b200_error_t msm_build_window_table_device(void* d_table, size_t n, uint32_t c, 
 // launcher
 // ---------------------------------------------------------------------------------------------
 extern "C" uint32_t b200_msm_window_bits(size_t n) {
-    if (const char* e = getenv("B200_MSM_C")) {
-        int c = atoi(e);
+    {
+        const int c = b200_config().msm_c;
         if (c >= 2 && c <= 22) return (uint32_t)c;
     }
     uint32_t lg = 0;
@@ -617,7 +619,7 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
     return msm_run_batch_device(d_out, d_points, n, d_scalars, stride, d_packed, nullptr, 1, stream, 0, 0, packed_glv);
 }
 
-bool msm_glv_enabled() { return !getenv("B200_MSM_NO_GLV"); }
+bool msm_glv_enabled() { return b200_config().msm_glv; }
 
 // resident sets stored in GLV form: 2n records (P_i, phi(P_i))
 b200_error_t msm_pack_bases_glv_device(void* d_packed_2n, const void* d_points, size_t n, size_t stride, cudaStream_t stream) {
@@ -653,14 +655,14 @@ struct MsmPlan {
 // GLV applies where the call packs its own points (VariableBase::msm proper, the streamed host path, the batched
 // verifier MSMs); resident sets keep their stored form (tabulated sets have no fold to shorten anyway).
 static bool msm_use_glv(const void* d_packed, size_t n_reg) {
-    return !d_packed && !n_reg && !getenv("B200_MSM_NO_GLV");
+    return !d_packed && !n_reg && b200_config().msm_glv;
 }
 
 // window width for 2n points with 127-bit scalars: the usual log2 - 5, then the narrowest window with the same
 // number of windows (127 / c + 1 is a step function: 19 bits already give the 7 windows of 20 and 21)
 static uint32_t msm_glv_window_bits(size_t n_eff) {
-    if (const char* e = getenv("B200_MSM_C")) {
-        int c = atoi(e);
+    {
+        const int c = b200_config().msm_c;
         if (c >= 2 && c <= 22) return (uint32_t)c;
     }
     uint32_t lg = 0;
@@ -714,9 +716,9 @@ static size_t msm_halved_bound(size_t E, size_t K) { return (E + (K < E ? K : E)
 // Number of batched-affine rounds before the XYZZ finish: enough to leave lists of 2..4 points.  Small calls are
 // launch-bound (every round is ~10 launches and one serial Fermat inversion), they keep the one-kernel path.
 static uint32_t msm_affine_rounds(size_t E, size_t K) {
-    if (const char* e = getenv("B200_MSM_AFFINE_ROUNDS")) {
-        int r = atoi(e);
-        return r < 0 ? 0u : (r > 30 ? 30u : (uint32_t)r);
+    {
+        const int r = b200_config().msm_affine_rounds;
+        if (r >= 0) return r > 30 ? 30u : (uint32_t)r;
     }
     // round r adds E / 2^(r+1) pairs at ~0.29 ns instead of ~0.40 ns each and costs ~0.4 ms of launches and the
     // latency-bound inversion chain: worth it above ~3.5 M pairs (measured optimum: 0 rounds at 2^18, 2 at 2^20,
@@ -799,7 +801,10 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     const size_t e1 = msm_halved_bound(E, K), e2 = msm_halved_bound(e1, K);
     if (rounds) {
         const size_t t1 = (e1 + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD;
-        cudaError_t e = list_a.alloc(e1 * sizeof(g1_packed_t), stream);
+        const unsigned long long need = (unsigned long long)e1 * sizeof(g1_packed_t) + (rounds > 1 ? (unsigned long long)e2 * sizeof(g1_packed_t) : 0) +
+                                        (unsigned long long)e1 * 48 + (unsigned long long)t1 * 48 + 3ull * (K + 1) * 4;
+        const unsigned long long budget = b200_config().msm_list_budget;
+        cudaError_t e = (budget && need > budget) ? cudaErrorMemoryAllocation : list_a.alloc(e1 * sizeof(g1_packed_t), stream);
         if (e == cudaSuccess && rounds > 1) e = list_b.alloc(e2 * sizeof(g1_packed_t), stream);
         if (e == cudaSuccess) e = pre.alloc(e1 * 48, stream);
         if (e == cudaSuccess) e = partial.alloc(t1 * 48, stream);
@@ -811,6 +816,7 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
             (void)cudaGetLastError();                                 // not enough HBM for the lists: XYZZ path only
             list_a.release(); list_b.release(); pre.release(); partial.release(); half.release(); off_a.release(); off_b.release();
             rounds = 0;
+            g_counters.msm_xyzz_fallbacks.fetch_add(1, std::memory_order_relaxed);     // observable: b200_get_counter
         }
     }
     // A round CAN be issued in slices of its output range (B200_MSM_SLICES > 1): denominators + inversion of a slice
@@ -818,8 +824,7 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     // first half of slice i + 1 runs under the multiplier-bound second half of slice i.  Measured at 2^24: 84.4 ms
     // with 1 slice, 85.6 / 86.9 / 89.2 ms with 2 / 3 / 4 -- both halves gather at random and the memory system is what
     // they share, while every extra slice adds one latency-bound inversion chain.  Default: one slice, one stream.
-    uint32_t max_slices = 1;
-    if (const char* e = getenv("B200_MSM_SLICES")) max_slices = (uint32_t)atoi(e);
+    const uint32_t max_slices = b200_config().msm_slices > 1 ? (uint32_t)b200_config().msm_slices : 1u;
     cudaStream_t aux = rounds && max_slices > 1 ? b200_thread_aux_stream() : nullptr;
     EventPool events;
     for (uint32_t r = 0; r < rounds; r++) {
@@ -838,8 +843,6 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
         rd.off = acc_off;
         rd.noff = noff;
         rd.K = (uint32_t)K;
-        rd.idx_mask = 0x7fffffffu;
-        if (const char* e = getenv("B200_DEBUG_IDX_MASK")) rd.idx_mask = (uint32_t)strtoul(e, nullptr, 0);
         const uint32_t nthr = (uint32_t)((e_out + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD);
         uint32_t nslices = aux ? nthr / (1u << 17) : 1;
         if (nslices < 1) nslices = 1;
@@ -882,7 +885,7 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     // are a latency problem (a thread's additions are one dependent chain), shorter chunks put more threads to work
     // (2^14 points: 1.29 ms at 128, 0.18 ms at 16; 2^16: 1.36 -> 0.50 ms at 32; from 2^22 entries on 128 wins: 1.91 vs 2.30 ms at 64)
     uint32_t chunk = acc_E >= ((size_t)1 << 22) ? 128 : acc_E >= ((size_t)1 << 21) ? 64 : acc_E >= ((size_t)1 << 19) ? 32 : 16;
-    if (const char* e = getenv("B200_MSM_CHUNK")) chunk = (uint32_t)atoi(e);
+    if (b200_config().msm_chunk > 0) chunk = (uint32_t)b200_config().msm_chunk;
     if (chunk < 8) chunk = 8;
     const size_t t_max = (acc_E + chunk - 1) / chunk;
     CUDA_TRY(heads.alloc((t_max + 1) * sizeof(g1_xyzz_mem_t), stream));
@@ -905,7 +908,10 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
             tail_bucket.as<uint32_t>(), pts, nullptr, entries.as<uint32_t>(), acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
     KERNEL_CHECK();
     STAGE("msm_combine", stream);
-    const size_t max_span = (n + chunk - 1) / chunk + 1;            // a bucket holds at most n entries
+    // longest possible run of heads: a bucket holds at most all acc_E entries of the stream (with tabulated bases every
+    // window of every point lands in ONE bucket set, so "at most n" does not hold: n * nwin equal digits are possible).
+    // Rounds above the device-side maximum return at once, so the extra launches of the bound are cheap.
+    const size_t max_span = (acc_E + chunk - 1) / chunk + 1;
     for (uint32_t stride2 = 1; stride2 < max_span; stride2 <<= 1) {
         msm_combine_heads_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(heads.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
                                                                          acc_off, max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride2);
@@ -1007,7 +1013,7 @@ b200_error_t msm_stream_begin(void** session, size_t n_total, cudaStream_t strea
     // is merged, so fewer, fuller buckets win (2^24 in 2^22 ranges: c = 19)
     const bool glv = msm_use_glv(nullptr, 0);
     uint32_t c = glv ? msm_glv_window_bits(2 * n_total) : b200_msm_window_bits(n_total);
-    if (!glv && !getenv("B200_MSM_C") && c > 6) c -= 1;
+    if (!glv && !(b200_config().msm_c >= 2 && b200_config().msm_c <= 22) && c > 6) c -= 1;
     b200_error_t r = msm_make_plan(&st->plan, n_total, 1, 0, c, glv);
     if (r.code == 0) {
         cudaError_t e = st->total.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);
@@ -1049,6 +1055,8 @@ b200_error_t msm_stream_finish(void* session, void* d_out, cudaStream_t stream) 
     delete st;          // stream-ordered frees
     return r;
 }
+
+void msm_release_graphs() {}
 
 void msm_stream_abort(void* session) { delete reinterpret_cast<MsmStream*>(session); }
 

@@ -40,7 +40,6 @@ struct PairRound {
     const uint32_t* off;         // K + 1 offsets of the input lists
     const uint32_t* noff;        // K + 1 offsets of the output lists, noff[b+1] - noff[b] = ceil(count_b / 2)
     uint32_t K;
-    uint32_t idx_mask;           // 0x7fffffff (a smaller mask is a TIMING experiment: gathers confined to a region)
 };
 
 enum { PAIR_ADD = 0, PAIR_DBL = 1, PAIR_COPY_A = 2, PAIR_COPY_B = 3, PAIR_INF = 4 };
@@ -68,7 +67,7 @@ B200_HD PairSlot pair_slot(const PairRound& rd, uint32_t i) {
     if (rd.entries) {
         const uint32_t id = rd.entries[i];
         s.neg = id >> 31;
-        s.x = rd.src + (size_t)(id & rd.idx_mask) * G1_BASE_U4;
+        s.x = rd.src + (size_t)(id & 0x7fffffffu) * G1_BASE_U4;
         s.y = s.x + 3;
     } else {
         s.neg = 0;

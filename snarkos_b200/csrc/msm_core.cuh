@@ -24,6 +24,25 @@ B200_HOSTDEV MsmShape msm_shape(uint32_t c, uint32_t bits = MSM_SCALAR_BITS) {
     return s;
 }
 
+// Scalars cross the ABI canonical (< r), which is what snarkVM's to_bigint() produces.  A non-canonical 256-bit k >= r
+// still denotes (k mod r) * P on a point of order r, and both the window count (253 bits) and the GLV split (127-bit
+// halves) assume k < r -- so k is reduced here instead of being silently truncated: at most 13 subtractions
+// (2^256 / r < 14), none for canonical input (one compare of the top limb).
+B200_HD void msm_scalar_reduce(uint32_t* s) {
+    if (s[7] < FrP::mod(7)) return;
+    for (int it = 0; it < 14; it++) {
+        uint32_t d[8];
+        uint32_t borrow = 0;
+        for (int i = 0; i < 8; i++) {
+            const unsigned long long t = (unsigned long long)s[i] - FrP::mod(i) - borrow;
+            d[i] = (uint32_t)t;
+            borrow = (uint32_t)(t >> 32) & 1u;
+        }
+        if (borrow) return;                            // s < r
+        for (int i = 0; i < 8; i++) s[i] = d[i];
+    }
+}
+
 // bits [lo, lo + c) of a 256-bit little-endian scalar held as 8 x u32 (c <= 24)
 B200_HD uint32_t msm_window_bits(const uint32_t* s, uint32_t lo, uint32_t c) {
     uint32_t limb = lo >> 5, off = lo & 31;

@@ -178,7 +178,7 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         CUDA_TRY(cudaFree(d_inv));
         it = g_ntt.domains.emplace(key, t).first;
     }
-    if (plan && plan->npasses > 1 && !getenv("B200_NTT_NO_BOUNDARY_TABLES")) {
+    if (plan && plan->npasses > 1 && b200_config().ntt_boundary_tables) {
         NttDomainTables& t = it->second;
         bool same = t.boundary_npasses == plan->npasses;
         for (uint32_t i = 0; same && i < plan->npasses; i++) same = (t.boundary_plan[i] == plan->log_len[i]);
@@ -417,7 +417,7 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
     if (log_n == 0) return b200_ok();
 
     NttPlan plan;
-    if (!ntt_make_plan(log_n, &plan)) return b200_err(B200_ERR_INVALID_ARG, "ntt: no valid pass plan");
+    if (!ntt_make_plan(log_n, &plan, (uint32_t)b200_config().ntt_tile_log, b200_config().ntt_plan)) return b200_err(B200_ERR_INVALID_ARG, "ntt: no valid pass plan");
     NttDomainTables tabs;
     const uint4* tile_tw = nullptr;
     B200_TRY(get_tables(log_n, direction, stream, &tabs, &tile_tw, &plan));
@@ -447,7 +447,7 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         p.coset_pre = (first && coset && direction == 0) ? 1 : 0;
         p.scale_post = (last && direction == 1) ? 1 : 0;
         p.coset_post = (last && coset && direction == 1) ? 1 : 0;
-        p.radix4 = getenv("B200_NTT_RADIX2") ? 0 : 1;
+        p.radix4 = b200_config().ntt_radix4 ? 1 : 0;
         const uint32_t tile_log = plan.log_len[i] + plan.log_cw[i];
         const uint32_t tile_elems = 1u << tile_log;
         uint32_t threads = tile_elems / 2;

@@ -18,15 +18,14 @@ struct NttPlan {
     uint32_t log_cw[NTT_MAX_PASSES];
 };
 
-// B200_NTT_PLAN="a,b,c" overrides the pass lengths; B200_NTT_TILE_LOG the tile size used when splitting.
-static bool ntt_make_plan(uint32_t log_n, NttPlan* plan) {
+// plan_override "a,b,c" (option ntt_plan) fixes the pass lengths; tile_log (option ntt_tile_log, default 11: 2048
+// elements = 64 KB -> 3 CTAs per SM) is the tile size used when splitting.
+static bool ntt_make_plan(uint32_t log_n, NttPlan* plan, uint32_t tile_log = 11, const char* plan_override = nullptr) {
     memset(plan, 0, sizeof(*plan));
-    uint32_t tile_log = 11;                            // 2048 elements = 64 KB -> 3 CTAs per SM
-    if (const char* e = getenv("B200_NTT_TILE_LOG")) tile_log = (uint32_t)atoi(e);
     if (tile_log > NTT_MAX_TILE_LOG) tile_log = NTT_MAX_TILE_LOG;
     if (tile_log < 4) tile_log = 4;
     bool have = false;
-    if (const char* e = getenv("B200_NTT_PLAN")) {
+    if (const char* e = (plan_override && *plan_override) ? plan_override : nullptr) {
         uint32_t sum = 0, k = 0;
         const char* q = e;
         while (*q && k < NTT_MAX_PASSES) {

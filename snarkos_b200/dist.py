@@ -136,9 +136,12 @@ def ntt_distributed(block: torch.Tensor, log_n: int, direction: int = 0, coset: 
         raise ValueError("both matrix sides must be divisible by the world size")
     if block.shape[0] * world != n:
         raise ValueError("block must hold 2^log_n / world elements")
+    if coset and direction == 1 and not natural_out:               # checked before anything is enqueued
+        raise ValueError("inverse coset scaling needs natural order out")
     block = block.contiguous()
     per = n // world
     if coset and direction == 0:                                   # distribute_powers(coeffs, g) on the natural-order input
+        block = block.clone()                                      # `block` is an input: the caller's tensor is not modified
         ops.mul_powers(block, log_n, 0, 1, per, 1, rank * per, 0)
     a = block.view(n1 // world, n2, FR_LIMBS)                      # rows j1 of my slab
     c = _exchange_transpose(a, world, group)                       # [N2/world, N1]: my columns j2, all j1
@@ -147,8 +150,6 @@ def ntt_distributed(block: torch.Tensor, log_n: int, direction: int = 0, coset: 
     e = _exchange_transpose(c, world, group)                       # [N1/world, N2]: my k1, all j2
     ops.ntt_rows(e, n2_log, direction)                             # over j2 -> k2 : e[k1, k2] = X[k1 + N1*k2]
     if not natural_out:
-        if coset and direction == 1:
-            raise ValueError("inverse coset scaling needs natural order out")
         return e
     f = _exchange_transpose(e, world, group)                       # [N2/world, N1]: my k2 range, all k1 = natural block
     out = f.view(per, FR_LIMBS)
@@ -284,6 +285,8 @@ def ntt_distributed_overlapped(block: torch.Tensor, log_n: int, fabric: PeerExch
     per = n // world
     if block.shape[0] != per or fabric.per != per:
         raise ValueError("block and fabric must hold 2^log_n / world elements")
+    if coset and direction == 1 and not natural_out:               # checked before anything is enqueued
+        raise ValueError("inverse coset scaling needs natural order out")
     if cta_limit is None:                                           # two exchange CTAs per SM leave room for the transforms
         cta_limit = 2 * torch.cuda.get_device_properties(block.device).multi_processor_count
     rb, rc = n2 // world, n1 // world                               # rows of my B slab / of my C slab
@@ -295,6 +298,7 @@ def ntt_distributed_overlapped(block: torch.Tensor, log_n: int, fabric: PeerExch
     xs = fabric.exchange_stream()                                   # exchanges + barriers: HIGH priority, so that their CTAs
     ts = fabric.transform_stream()                                  # get SM slots while the (compute-bound) transforms run
     if coset and direction == 0:
+        block = block.clone()                                       # the caller's tensor is not modified
         ops.mul_powers(block, log_n, 0, 1, per, 1, rank * per, 0)
     B, C = fabric.local(0), fabric.local(1)
     Bm, Cm = B.view(rb, n1, FR_LIMBS), C.view(rc, n2, FR_LIMBS)
@@ -333,8 +337,6 @@ def ntt_distributed_overlapped(block: torch.Tensor, log_n: int, fabric: PeerExch
             ev.record(ts)
             done_c.append(ev)
     if not natural_out:
-        if coset and direction == 1:
-            raise ValueError("inverse coset scaling needs natural order out")
         cur.wait_event(done_c[-1])
         return Cm
     fin = torch.cuda.Event()
@@ -366,8 +368,11 @@ def ntt_distributed_fused(block: torch.Tensor, log_n: int, fabric: PeerExchange,
     per = n // world
     if block.shape[0] != per or fabric.per != per:
         raise ValueError("block and fabric must hold 2^log_n / world elements")
+    if coset and direction == 1 and not natural_out:               # checked before anything is enqueued
+        raise ValueError("inverse coset scaling needs natural order out")
     block = block.contiguous()
     if coset and direction == 0:
+        block = block.clone()                                      # the caller's tensor is not modified
         ops.mul_powers(block, log_n, 0, 1, per, 1, rank * per, 0)
     B, C = fabric.local(0), fabric.local(1)
     fabric.barrier()                                               # every rank is done with the slabs of the previous call
@@ -378,8 +383,6 @@ def ntt_distributed_fused(block: torch.Tensor, log_n: int, fabric: PeerExchange,
     fabric.barrier()                                               # C = [N1/world, N2]: my k1, all j2, twiddled
     ops.ntt_rows(C.view(n1 // world, n2, FR_LIMBS), n2_log, direction)
     if not natural_out:
-        if coset and direction == 1:
-            raise ValueError("inverse coset scaling needs natural order out")
         return C.view(n1 // world, n2, FR_LIMBS)
     exchange_transpose(C, fabric.dst_array(0), world, rank, n1 // world, n2, log_n, direction, False)
     fabric.barrier()                                               # B = [N2/world, N1]: my k2 range = natural block

@@ -69,7 +69,6 @@ extern "C" int host_msm_affine(uint8_t* out_jac, const uint8_t* pts, size_t n, s
         rd.off = off.data();
         rd.noff = noff.data();
         rd.K = K;
-        rd.idx_mask = 0x7fffffffu;
         const uint32_t T = (tot + MSM_PAIRS_PER_THREAD - 1) / MSM_PAIRS_PER_THREAD + 2;     // + idle threads past the end
         std::vector<uint4> pre(3 * (size_t)(tot ? tot : 1)), partial(3 * (size_t)T);
         std::vector<uint4> next_x(3 * (size_t)(tot ? tot : 1)), next_y(3 * (size_t)(tot ? tot : 1));

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/snarkos_b200.h but not exported: {missing}"
     unbound = [n for n in names if n not in _lib.SYMBOLS]
     assert not unbound, f"declared but without a ctypes signature in snarkos_b200/_lib.py: {unbound}"
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -46,3 +46,19 @@ def test_no_cpu_fallback_without_a_device():
     assert e.code != 0
     with pytest.raises(_lib.B200Error):
         _lib.check(lib.b200_init(-1))
+
+
+def test_options_and_counters_need_no_device():
+    """tuning knobs are plain process state (environment read once, b200_set_option afterwards)"""
+    from snarkos_b200 import _lib
+    import snarkos_b200 as S
+    S.set_option("msm_window_bits", 17)
+    S.set_option("msm_window_bits", 0)
+    S.set_option("ntt_plan", "8,8,8")
+    S.set_option("ntt_plan", "")
+    with pytest.raises(_lib.B200Error):
+        S.set_option("no_such_knob", 1)
+    assert S.counter("kernel_launches") >= 0
+    assert S.counter("msm_xyzz_fallbacks") >= 0
+    with pytest.raises(_lib.B200Error):
+        S.counter("no_such_counter")

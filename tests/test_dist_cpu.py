@@ -88,9 +88,11 @@ def _worker(rank, world, port, q):
             d = O.EvaluationDomain(N)
             for direction, coset, f in ((0, 0, d.fft), (1, 0, d.ifft), (0, 1, d.coset_fft), (1, 1, d.coset_ifft)):
                 blk = torch.from_numpy(H.fr_mont_array(x[rank * per:(rank + 1) * per]).view(np.int64))
+                keep = blk.clone()
                 out = D.ntt_distributed(blk, log_n, direction, coset, natural_out=True, ops=ops, log_n1=log_n1)
                 want = f(x)[rank * per:(rank + 1) * per]
                 assert H.fr_from_mont_array(out.numpy().view(np.uint64)) == want, (log_n, direction, coset)
+                assert torch.equal(blk, keep), "the input block is an input: coset scaling must not modify it"
             blk = torch.from_numpy(H.fr_mont_array(x[rank * per:(rank + 1) * per]).view(np.int64))
             slab = D.ntt_distributed(blk, log_n, 0, 0, natural_out=False, ops=ops, log_n1=log_n1)
             n1 = 1 << log_n1
@@ -100,6 +102,11 @@ def _worker(rank, world, port, q):
             n2 = N // n1
             want = [full[(rank * rows + r) + n1 * k2] for r in range(rows) for k2 in range(n2)]
             assert got == want, "k1-slab layout mismatch"
+            try:                                               # refused before any exchange is enqueued (both ranks raise)
+                D.ntt_distributed(blk, log_n, 1, 1, natural_out=False, ops=ops, log_n1=log_n1)
+                raise AssertionError("inverse coset with slab output must be refused")
+            except ValueError:
+                pass
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

@@ -239,15 +239,15 @@ def test_host_buffer_streaming_path():
 
 
 # ---------------------------------------------------------------------------------------------
-# batched-affine pair rounds (msm_affine.cuh), forced on at small sizes through B200_MSM_AFFINE_ROUNDS
+# batched-affine pair rounds (msm_affine.cuh), forced on at small sizes through the msm_affine_rounds option
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("rounds", [1, 3, 8])
 @pytest.mark.parametrize("n,c", [(1, 4), (33, 4), (1000, 6), (5000, 8)])
-def test_affine_rounds_vs_oracle(monkeypatch, rounds, n, c):
+def test_affine_rounds_vs_oracle(b200_opt, rounds, n, c):
     """snarkVM batched::batch_add counterpart: pairwise affine additions with one batch inversion per round;
     narrow windows make buckets of tens to hundreds of points, `rounds` beyond log2(bucket size) must be no-ops."""
-    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", str(rounds))
-    monkeypatch.setenv("B200_MSM_C", str(c))
+    b200_opt("msm_affine_rounds", rounds)
+    b200_opt("msm_window_bits", c)
     rng = O.SplitMix64(1500 + n + rounds)
     pts = O.random_points(rng, min(n, 64))
     pts = [pts[i % len(pts)] for i in range(n)]               # repeated points: doublings appear in later rounds
@@ -258,9 +258,9 @@ def test_affine_rounds_vs_oracle(monkeypatch, rounds, n, c):
 
 
 @pytest.mark.parametrize("rounds", [2, 7])
-def test_affine_rounds_edge_cases(monkeypatch, rounds):
-    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", str(rounds))
-    monkeypatch.setenv("B200_MSM_C", "4")
+def test_affine_rounds_edge_cases(b200_opt, rounds):
+    b200_opt("msm_affine_rounds", rounds)
+    b200_opt("msm_window_bits", 4)
     rng = O.SplitMix64(81)
     n = 64
     pts = O.random_points(rng, n)
@@ -280,11 +280,11 @@ def test_affine_rounds_edge_cases(monkeypatch, rounds):
 
 
 @pytest.mark.parametrize("kind", ["all_equal", "two_values", "tiny", "top_heavy", "uniform"])
-def test_affine_rounds_skewed_distributions(monkeypatch, kind):
+def test_affine_rounds_skewed_distributions(b200_opt, kind):
     """2^16 points, 4 rounds: a bucket holding every point is halved four times and finished by the XYZZ chunks."""
     import torch
     import snarkos_b200 as S
-    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", "4")
+    b200_opt("msm_affine_rounds", 4)
     n, seed = 1 << 16, 23
     dbases = _synthetic(n, seed)
     rng = np.random.default_rng(5)
@@ -305,13 +305,13 @@ def test_affine_rounds_skewed_distributions(monkeypatch, kind):
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
 
 
-def test_affine_rounds_sliced_on_helper_stream(monkeypatch):
-    """B200_MSM_SLICES > 1: denominators + inversion of slice i + 1 on the thread's high-priority helper stream under
+def test_affine_rounds_sliced_on_helper_stream(b200_opt):
+    """msm_slices > 1: denominators + inversion of slice i + 1 on the thread's high-priority helper stream under
     the additions of slice i (kept as a measured alternative, default off) -- same result"""
     import torch
     import snarkos_b200 as S
-    monkeypatch.setenv("B200_MSM_AFFINE_ROUNDS", "3")
-    monkeypatch.setenv("B200_MSM_SLICES", "3")
+    b200_opt("msm_affine_rounds", 3)
+    b200_opt("msm_slices", 3)
     n, seed = 1 << 20, 31
     dbases = _synthetic(n, seed)
     sc = H.random_scalars_np(np.random.default_rng(6), n)
@@ -322,9 +322,9 @@ def test_affine_rounds_sliced_on_helper_stream(monkeypatch):
 
 
 @pytest.mark.parametrize("n", [1, 3, 100, 4097])
-def test_glv_split_path_equals_plain_path(monkeypatch, n):
+def test_glv_split_path_equals_plain_path(b200_opt, n):
     """VariableBase::msm splits every scalar by the endomorphism (k = k1 + k2 * lambda, phi(P) = (beta x, y): 2n points,
-    127-bit scalars, half the windows); with B200_MSM_NO_GLV the same call runs on the 253-bit scalars -- both must give
+    127-bit scalars, half the windows); with msm_glv = 0 the same call runs on the 253-bit scalars -- both must give
     the oracle's point, including infinity among the bases and the extreme scalars"""
     rng = O.SplitMix64(3100 + n)
     pts = O.random_points(rng, min(n, 32))
@@ -336,11 +336,11 @@ def test_glv_split_path_equals_plain_path(monkeypatch, n):
     bases, scal = H.bases_array(pts), H.scalars_array(sc)
     want = O.msm_naive(pts, sc) if n <= 100 else oracle_msm(bases, scal)
     assert gpu_msm(bases, scal) == want
-    monkeypatch.setenv("B200_MSM_NO_GLV", "1")
+    b200_opt("msm_glv", 0)
     assert gpu_msm(bases, scal) == want
 
 
-def test_resident_set_in_glv_form(monkeypatch):
+def test_resident_set_in_glv_form(b200_opt):
     """resident sets above 2^20 points (and smaller ones with the window table switched off) are stored as
     (P_i, phi(P_i)) pairs and every MSM against them runs on the GLV halves: exact identity at 2^20 + 77 points, a
     prefix call against the oracle, KZG commit on a small GLV-resident set"""
@@ -358,7 +358,97 @@ def test_resident_set_in_glv_form(monkeypatch):
     hb = dbases[:600 * 104].cpu().numpy()
     assert H.jac_bytes_to_affine(rb.msm(sc[:600])) == oracle_msm(hb, sc[:600])
     rb.release()
-    monkeypatch.setenv("B200_MSM_NO_AUTO_TABLE", "1")
+    b200_opt("msm_auto_table", 0)
     small = S.ResidentBases(dbases[:4096 * 104])
     assert H.jac_bytes_to_affine(small.msm(sc[:4096])) == oracle_msm(dbases[:4096 * 104].cpu().numpy(), sc[:4096])
     small.release()
+
+
+# ---------------------------------------------------------------------------------------------
+# round-2 regressions: head-combine bound with tabulated bases, non-canonical scalars, forced XYZZ fallback, 2^26
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["all_equal", "repeated_digit", "three_digits"])
+@pytest.mark.parametrize("api", ["registered", "kzg_commit"])
+def test_tabulated_structured_scalars(kind, api):
+    """With tabulated bases every window of every point lands in ONE bucket set, so a bucket can hold n * nwin entries:
+    structured scalars (every 16-bit digit equal) pile 3n .. 16n entries on one bucket and need head-combine strides far
+    above n / chunk (the loop bound assumed at most n entries per bucket and dropped partial sums)."""
+    import snarkos_b200 as S
+    n = 1 << 10                                            # auto-tabulated, c = 16, chunk = 16
+    dbases = _synthetic(n, 123)
+    hb = dbases.cpu().numpy()
+    if kind == "all_equal":
+        vals = [0x0001000100010001000100010001000100010001000100010001000100010001 % O.R_MOD] * n
+    elif kind == "repeated_digit":
+        vals = [0x000100010001] * n                        # the advisor's example: 3n entries in bucket 0
+    else:
+        vals = [(1 << 32) + (1 << 16) + 1 + ((i % 2) << 48) for i in range(n)]
+    sc = H.scalars_array(vals)
+    want = O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, H.splitmix64_at(123, np.arange(n))))
+    if api == "registered":
+        rb = S.ResidentBases(hb)                           # 2^10 points: tabulated automatically
+        assert H.jac_bytes_to_affine(rb.msm(sc)) == want
+        rb.release()
+    else:
+        powers = S.Powers(dbases, None)
+        assert H.jac_bytes_to_affine(S.KZG10.commit(powers, C.fr_to_mont(sc))) == want
+        powers.release()
+
+
+def test_non_canonical_scalars_are_reduced(b200_opt):
+    """scalars cross the ABI canonical (< r); a 256-bit k >= r still means (k mod r) * P and must not be truncated by
+    the 127-bit GLV halves or the 253-bit window count"""
+    rng = O.SplitMix64(4242)
+    n = 40
+    pts = O.random_points(rng, n)
+    vals = O.random_fr(rng, n)
+    vals[0], vals[1], vals[2], vals[3] = O.R_MOD, O.R_MOD + 1, (1 << 256) - 1, 13 * O.R_MOD + 5
+    vals[4] = (1 << 255) + 12345
+    want = O.msm_naive(pts, [v % O.R_MOD for v in vals])
+    bases, scal = H.bases_array(pts), H.scalars_array(vals)
+    assert gpu_msm(bases, scal) == want
+    b200_opt("msm_glv", 0)
+    assert gpu_msm(bases, scal) == want
+
+
+def test_forced_xyzz_fallback_when_lists_do_not_fit(b200_opt):
+    """the pair-round lists of a large call are ~25 GiB at 2^24; when they cannot be allocated the call must run the
+    XYZZ-only accumulation, say so through a counter, and return the same point.  The allocation failure is forced
+    through the msm_list_budget_bytes option."""
+    import torch
+    import snarkos_b200 as S
+    n, seed = 1 << 20, 77
+    dbases = _synthetic(n, seed)
+    sc = H.random_scalars_np(np.random.default_rng(31), n)
+    dsc = torch.from_numpy(sc.view(np.int64)).cuda()
+    want = O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, H.splitmix64_at(seed, np.arange(n))))
+    b200_opt("msm_affine_rounds", 3)
+    before = S.counter("msm_xyzz_fallbacks")
+    out = S.VariableBase.msm(dbases, dsc)
+    torch.cuda.synchronize()
+    assert S.counter("msm_xyzz_fallbacks") == before
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == want
+    b200_opt("msm_list_budget_bytes", 1 << 20)
+    out = S.VariableBase.msm(dbases, dsc)
+    torch.cuda.synchronize()
+    assert S.counter("msm_xyzz_fallbacks") == before + 1
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == want
+
+
+def test_single_gpu_2_26_exact_identity():
+    """north_star upper size on ONE GPU: 2^26 points (6.5 GiB of bases, 2 GiB of scalars, ~60 GiB of pair-round lists)"""
+    import torch
+    import snarkos_b200 as S
+    n, seed = 1 << 26, 2026
+    dbases = _synthetic(n, seed)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    dsc = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda", generator=gen)
+    dsc[:, 3] &= (1 << 60) - 1
+    out = S.VariableBase.msm(dbases, dsc)
+    torch.cuda.synchronize()
+    sc = dsc.cpu().numpy().view(np.uint64)
+    del dbases, dsc
+    torch.cuda.empty_cache()
+    k = H.splitmix64_at(seed, np.arange(n))
+    assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))

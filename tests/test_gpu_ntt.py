@@ -112,7 +112,7 @@ def test_full_size_properties(log_n, batch):
         assert H.fr_from_mont_array(out[k:k + 1])[0] == pow(w, k, O.R_MOD)
 
 
-def test_pageable_host_buffers_staged_copies(monkeypatch):
+def test_pageable_host_buffers_staged_copies(b200_opt):
     """Ordinary (pageable) caller memory, as a Rust Vec is: uploads and downloads above 8 MiB go through the library's
     pinned staging slots on worker threads (hostcopy.cu) -- several slices per worker, both directions; the result must
     equal the driver's own pageable path bit for bit, and the round trip must be the identity."""
@@ -121,15 +121,15 @@ def test_pageable_host_buffers_staged_copies(monkeypatch):
     data = H.random_fr_mont_np(np.random.default_rng(77), (batch, n))
     d = dom(n)
     staged = d.fft_in_place(data.copy())
-    monkeypatch.setenv("B200_NO_STAGED_COPIES", "1")
+    b200_opt("staged_copies", 0)
     plain = d.fft_in_place(data.copy())
-    monkeypatch.delenv("B200_NO_STAGED_COPIES")
+    b200_opt("staged_copies", 1)
     assert np.array_equal(staged, plain)
     assert np.array_equal(staged[3], C.ntt(data[3], log_n))
     assert np.array_equal(d.ifft_in_place(staged.copy()), data)
 
 
-def test_host_batch_pipeline_matches_single_shot(monkeypatch):
+def test_host_batch_pipeline_matches_single_shot(b200_opt):
     """Host batches above 64 MiB are pipelined in groups over three streams (upload / transforms / download); ragged
     groups (7 polynomials), a padded batch stride and pinned memory: same bytes as the single-shot path, padding
     between the polynomials untouched."""
@@ -149,7 +149,7 @@ def test_host_batch_pipeline_matches_single_shot(monkeypatch):
         return t.numpy().view(np.uint64).copy()
 
     piped = run(flat)
-    monkeypatch.setenv("B200_NTT_NO_HOST_PIPELINE", "1")
+    b200_opt("ntt_host_pipeline", 0)
     single = run(flat)
     assert np.array_equal(piped, single)
     for b in (0, 3, 6):

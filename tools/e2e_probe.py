@@ -13,7 +13,7 @@ sc[:, 3] &= (1 << 60) - 1
 hb, hs = bases.cpu().pin_memory(), sc.cpu().pin_memory()
 for c in [int(x) for x in os.environ.get("CS", "0,17,18,19").split(",")]:
     if c:
-        os.environ["B200_MSM_C"] = str(c)
+        S.set_option("msm_window_bits", c)
     S.VariableBase.msm(hb, hs)
     t0 = time.perf_counter()
     for _ in range(3):

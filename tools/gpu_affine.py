@@ -19,9 +19,9 @@ ref = None
 for c in [int(x) for x in os.environ.get("CS", "20").split(",")]:
     for r in [int(x) for x in os.environ.get("ROUNDS", "0,3,4,5").split(",")]:
         if c > 0:
-            os.environ["B200_MSM_C"] = str(c)
+            S.set_option("msm_window_bits", c)
         if r >= 0:
-            os.environ["B200_MSM_AFFINE_ROUNDS"] = str(r)
+            S.set_option("msm_affine_rounds", r)
         out = call(); torch.cuda.synchronize()
         best = None
         for _ in range(2):

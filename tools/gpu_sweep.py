@@ -65,13 +65,13 @@ if "msm" in what:
         rb = S.ResidentBases(bases)
         for c in cs:
             for ch in chunks:
-                os.environ["B200_MSM_C"] = str(c)
-                os.environ["B200_MSM_CHUNK"] = str(ch)
+                S.set_option("msm_window_bits", c)
+                S.set_option("msm_chunk", ch)
                 tot, st = staged(lambda: rb.msm(sc), reps=2)
                 res["msm"][f"2^{log_n} c={c} chunk={ch}"] = {"total_ms": tot, **st}
                 print(f"msm 2^{log_n} c={c} chunk={ch}: total {tot:8.3f} ms  " + " ".join(f"{k[4:]}={v:.3f}" for k, v in st.items()), flush=True)
-        os.environ.pop("B200_MSM_C", None)
-        os.environ.pop("B200_MSM_CHUNK", None)
+        S.set_option("msm_window_bits", 0)
+        S.set_option("msm_chunk", 0)
         rb.release()
         del bases, sc
 
@@ -91,14 +91,14 @@ if "ntt" in what:
                 lens = [int(x) for x in plan.split(",")]
                 if max(lens) > tile:
                     continue
-                os.environ["B200_NTT_PLAN"] = plan
-                os.environ["B200_NTT_TILE_LOG"] = str(tile)
+                S.set_option("ntt_plan", plan)
+                S.set_option("ntt_tile_log", tile)
                 tot, st = staged(lambda: d.fft_in_place(t))
                 key = f"2^{log_n}x{batch} plan={plan} tile=2^{tile}"
                 res["ntt"][key] = {"total_ms": tot, **st}
                 print(f"ntt {key}: total {tot:8.3f} ms  " + " ".join(f"{k[4:]}={v:.3f}" for k, v in st.items()), flush=True)
-        os.environ.pop("B200_NTT_PLAN", None)
-        os.environ.pop("B200_NTT_TILE_LOG", None)
+        S.set_option("ntt_plan", "")
+        S.set_option("ntt_tile_log", 11)
         del t
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

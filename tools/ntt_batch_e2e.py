@@ -10,7 +10,7 @@ d = S.EvaluationDomain(n)
 t = torch.randint(0, 1 << 59, (batch, n, 4), dtype=torch.int64).pin_memory()
 for mode in ("pipelined", "single"):
     if mode == "single":
-        os.environ["B200_NTT_NO_HOST_PIPELINE"] = "1"
+        S.set_option("ntt_host_pipeline", 0)
     d.fft_in_place(t)
     t0 = time.perf_counter()
     for _ in range(5):
