@@ -7,9 +7,11 @@ A "step" is one pass of the hot path over one batch of synthetic input: one Vari
   ntt.value    : NTT Gelem/s, same rules
   e2e          : the same MSM metric through the public host-buffer API (pinned host bases + scalars copied H2D and the
                  144-byte result copied D2H inside the timed region, every step)
-  roofline     : dominant kernel of the step (msm_accumulate) against the measured HBM peak, as the contract asks;
-                 roofline_int puts the same kernel against the integer-multiply pipe (the bound that actually binds)
-  cpu_baseline : the CPU oracle (restated snarkVM algorithm, "port") on the box's host cores, bounded sample
+  roofline     : dominant kernel of the step (msm_pair_add_kernel) against the integer-multiply pipe -- the bound
+                 SURVEY 8d names for the MSM; roofline_hbm keeps the same kernel against the measured HBM peak
+  cpu_baseline : the CPU oracle (snarkVM batched::msm restated, "port") on the box's host cores, same 2^24 inputs
+  strong_2^26  : BASELINE configs[4] at every N: ONE 2^26-point MSM sharded by point range (2^26 / N points per rank)
+                 and ONE 2^26-element four-step NTT (fused peer-store exchange and NCCL all-to-all), natural order out
 `--impl reference` times that CPU port alone (the reference's hot path is Rust in an un-vendored dependency and no Rust
 toolchain exists in the image, so there is no oracle/_ref to run).
 """
@@ -35,7 +37,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=24, help="log2 of MSM points and NTT elements per GPU")
-    ap.add_argument("--cpu-msm-log-n", type=int, default=22, help="bounded CPU-baseline MSM sample")
+    ap.add_argument("--cpu-msm-log-n", type=int, default=24, help="CPU-baseline MSM size (default: the full workload)")
+    ap.add_argument("--strong-log-n", type=int, default=26, help="configs[4]: total size of the sharded MSM / four-step NTT")
+    ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--cpu-ntt-log-n", type=int, default=24, help="bounded CPU-baseline NTT sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -114,18 +118,12 @@ class ClockSampler:
 # CPU arm (oracle port).  The ONLY place bench.py touches oracle/.
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_inputs(msm_log_n, ntt_log_n):
-    """Bounded sample built without any GPU code: 2^12 distinct oracle-generated points tiled up to 2^msm_log_n
-    (MSM cost does not depend on the point values), uniform scalars / Fr data < 2^252."""
+    """Inputs built without any GPU code: 2^msm_log_n DISTINCT points (k0 + i) * G from the oracle's point sequence
+    (one mixed addition per point), uniform scalars / Fr data < 2^252."""
     import numpy as np
-    from oracle import bls12_377 as O
     from oracle import c_oracle as C
     rng = np.random.default_rng(2024)
-    g = np.frombuffer(O.affine_bytes(O.G1_GEN), dtype=np.uint8)
-    distinct = min(1 << 12, 1 << msm_log_n)
-    k = rng.integers(1, 1 << 62, size=distinct, dtype=np.uint64)
-    pts = C.g1_mul_u64(g, k)                                     # [distinct, 104]
-    reps = (1 << msm_log_n) // distinct
-    bases = np.tile(pts, (reps, 1)).reshape(-1)
+    bases = C.g1_sequence(0x9E3779B97F4A7C15, 1 << msm_log_n, nthreads=host_threads()).reshape(-1)
 
     def rnd(n):
         s = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
@@ -146,7 +144,7 @@ def cpu_time_once(bases, scalars, ntt_data, ntt_log_n):
     from oracle import c_oracle as C
     nt = host_threads()
     t0 = time.perf_counter()
-    C.msm(bases, scalars, nthreads=nt)
+    C.msm_batched(bases, scalars, nthreads=nt)              # snarkVM batched::msm: what BLS12-377 G1 is dispatched to
     t1 = time.perf_counter()
     C.ntt(ntt_data, ntt_log_n, nthreads=nt)
     t2 = time.perf_counter()
@@ -161,7 +159,7 @@ def run_reference(args):
     C.build()
     cores = host_threads()
     bases, scalars, ntt_data = cpu_inputs(args.cpu_msm_log_n, args.cpu_ntt_log_n)
-    for _ in range(max(1, min(args.warmup, 1))):
+    for _ in range(max(1, min(args.warmup, 1))):            # one warm-up step: builds the cached FFT precomputation
         cpu_time_once(bases, scalars, ntt_data, args.cpu_ntt_log_n)
     tm, tn = 0.0, 0.0
     for _ in range(args.steps):
@@ -170,8 +168,9 @@ def run_reference(args):
         tn += b
     npts, nel = 1 << args.cpu_msm_log_n, 1 << args.cpu_ntt_log_n
     value = npts * args.steps / tm / 1e6
-    sample = (f"MSM 2^{args.cpu_msm_log_n} points (2^12 distinct, tiled) + NTT 2^{args.cpu_ntt_log_n} per step; "
-              f"C restatement of snarkVM standard::msm / in-order radix-2 FFT, OpenMP {cores} threads")
+    sample = (f"MSM 2^{args.cpu_msm_log_n} distinct points + NTT 2^{args.cpu_ntt_log_n} per step; batched::msm port "
+              f"(C restatement of snarkVM batched::msm: c = ln n + 2, one task per window, affine pair additions with one "
+              f"inversion per batch of 1500) / in-order radix-2 FFT with cached FFTPrecomputation, OpenMP {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpoints/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tm + tn) / args.steps * 1e3,
@@ -205,10 +204,8 @@ def run_b200(args):
     S.init(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if "B200_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["B200_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)          # NCCL_DEBUG=VERSION/WARN prints a banner on stdout; keep it to the JSON line
+        # NCCL_DEBUG is left exactly as the launcher set it (the driver reads the rank count from NCCL's own log); the
+        # JSON line is printed last, after the process group is gone, on a line of its own
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = 1 << args.log_n
@@ -333,7 +330,8 @@ def run_b200(args):
         e_msm, e_ntt, e_res, e_tab, d_tab = [float(x) for x in tt.cpu()]
         e2e = {"value": world * n * Ke / e_msm / 1e6, "unit": "Mpoints/s",
                "h2d_bytes_per_step": int(h_bases.numel() + h_scalars.numel() * 8), "d2h_bytes_per_step": 144,
-               "steps": Ke, "api": "snarkos_b200.VariableBase.msm(pinned host bases, pinned host scalars) -> b200_msm_g1_bls12_377",
+               "steps": Ke, "h2d_gbs_per_rank": (h_bases.numel() + h_scalars.numel() * 8) * Ke / e_msm / 1e9,
+               "api": "snarkos_b200.VariableBase.msm(pinned host bases, pinned host scalars) -> b200_msm_g1_bls12_377",
                "resident_bases": {"value": world * n * Ke / e_res / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": int(h_scalars.numel() * 8),
                                   "d2h_bytes_per_step": 144, "api": "snarkos_b200.ResidentBases.msm(pinned host scalars) -> b200_msm_registered"}}
         if tab:
@@ -369,8 +367,78 @@ def run_b200(args):
                                      "value": n * Ke / (t7 - t6) / 1e9, "unit": "Gelem/s"}
         del h_bases, h_scalars, h_ntt
 
+
+    # ---- BASELINE configs[4] at this N: ONE 2^26 MSM sharded by point range + ONE 2^26 four-step NTT -----------------
+    strong = None
+    if not args.no_strong:
+        L26 = args.strong_log_n
+        per = (1 << L26) // world
+        Ks = min(K, 3)
+        b26 = S.synthetic_bases(per, seed=26000 + rank)            # rank r holds points [r * per, (r + 1) * per)
+        s26 = rand_limbs(per)
+        torch.cuda.synchronize()
+        D.msm_sharded(b26, s26)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Ks):
+            D.msm_sharded(b26, s26)                                 # local Pippenger + all-gather of 144 B + 7 additions
+        e1.record()
+        torch.cuda.synchronize()
+        t_msm26 = e0.elapsed_time(e1) / Ks
+        del b26, s26
+        torch.cuda.empty_cache()
+        blk = rand_limbs(per)
+        times = {}
+        if world == 1:
+            d26 = S.EvaluationDomain(1 << L26)
+            d26.fft_in_place(blk)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(Ks):
+                d26.fft_in_place(blk)
+            e1.record()
+            torch.cuda.synchronize()
+            times["single_gpu"] = e0.elapsed_time(e1) / Ks
+        else:
+            fabric = D.PeerExchange(per)
+            variants = {"fused_natural": lambda: D.ntt_distributed_fused(blk, L26, fabric, natural_out=True),
+                        "fused_slab": lambda: D.ntt_distributed_fused(blk, L26, fabric, natural_out=False),
+                        "nccl_natural": lambda: D.ntt_distributed(blk, L26, natural_out=True),
+                        "nccl_slab": lambda: D.ntt_distributed(blk, L26, natural_out=False)}
+            for name, fn in variants.items():
+                fn()
+                barrier()
+                e0.record()
+                for _ in range(Ks):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                times[name] = e0.elapsed_time(e1) / Ks
+                barrier()
+            fabric.close()
+        del blk
+        keys = sorted(times)
+        tt = torch.tensor([t_msm26] + [times[k_] for k_ in keys], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        vals = [float(x) for x in tt.cpu()]
+        best_ntt = min(vals[1:])
+        strong = {"workload": f"configs[4]: one MSM of 2^{L26} points sharded by point range over {world} GPU(s) "
+                              f"(2^{L26}/{world} points per rank, partial sums all-gathered and added) + one four-step NTT of "
+                              f"2^{L26} elements (block-distributed, natural order in)",
+                  "scaling": "strong", "steps": Ks,
+                  "msm_ms": vals[0], "msm_mpoints_s": (1 << L26) / (vals[0] * 1e-3) / 1e6,
+                  "ntt_ms": {k_: v for k_, v in zip(keys, vals[1:])},
+                  "ntt_gelem_s": (1 << L26) / (best_ntt * 1e-3) / 1e9,
+                  "ntt_exchange": ("none (one GPU: the plain multi-pass transform)" if world == 1 else
+                                   "fused_*: ONE kernel per exchange storing transposed + twiddled tiles into peer HBM over "
+                                   "NVLink (CUDA IPC); nccl_*: re-tile + ncclAllToAll + re-tile; *_natural = 3 exchanges "
+                                   "(natural order out), *_slab = 2 (k1-slab out for a following pointwise stage)")}
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -386,14 +454,14 @@ def run_b200(args):
     dom_kernel, dom_ms = ("msm_pair_add_kernel", add_ms) if rounds else ("msm_accumulate_kernel", stage.get("msm_accumulate", 0.0) / K)
     bucket_ms = sum(v for k_, v in stage.items() if k_.startswith("msm_pairs") or k_ in ("msm_accumulate", "msm_combine")) / K
     alg_bytes = (104 + 32) * n                                   # (104 + 32) B per point
-    roofline = {"bound": "hbm", "kernel": dom_kernel, "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else None,
+    roofline_hbm = {"bound": "hbm", "kernel": dom_kernel, "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
                 "traffic": NCU_TRAFFIC_BYTES.get(dom_kernel + "@2^24") if args.log_n == 24 else None,
                 "traffic_note": "bytes per MSM (all launches of the kernel), ncu capture under profiles/; every round re-reads "
                                 "its operands (round 0: one 128 B line per gathered base, per window), so traffic >> (104+32) B/point",
                 "launches_per_step": max(rounds, 1), "avg_launch_ms": dom_ms / max(rounds, 1), "ms_per_step": dom_ms,
                 "algorithmic_bytes_per_step": alg_bytes, "bucket_accumulation_ms": bucket_ms}
-    roofline["frac"] = roofline["achieved"] / hbm_peak if roofline["achieved"] else None
+    roofline_hbm["frac"] = roofline_hbm["achieved"] / hbm_peak if roofline_hbm["achieved"] else None
     # integer-multiply pipe: Fq modmuls the kernel must execute vs the modmul rate of a pure fp_mul loop
     import ctypes
     ms_, ops_ = ctypes.c_float(), ctypes.c_double()
@@ -409,13 +477,21 @@ def run_b200(args):
     else:
         modmuls = 10.0 * n_eff * nwin                             # one XYZZ mixed add (8M + 2S) per non-zero digit
         per_add = "10 (XYZZ mixed addition)"
-    roofline_int = {"bound": "int_mul_pipe", "kernel": dom_kernel, "unit": "G Fq-modmul/s",
+    roofline = {"bound": "int_mul_pipe", "kernel": dom_kernel, "unit": "G Fq-modmul/s",
                     "achieved": modmuls / (dom_ms * 1e-3) / 1e9 if dom_ms else None, "peak": best / 1e9,
                     "peak_source": "fp_mul<Fq> dependent-chain microbenchmark, same run, full occupancy",
                     "modmul_per_step": modmuls, "modmul_per_addition": per_add, "window_bits": c, "windows": nwin,
                     "digits": "signed", "affine_rounds": rounds, "glv": bool(glv),
                     "entries": n_eff * nwin}
-    roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"] if roofline_int["achieved"] else None
+    roofline["frac"] = roofline["achieved"] / roofline["peak"] if roofline["achieved"] else None
+    # whole call against the same peak: every Fq product the MSM executes (denominators, inversions, XYZZ finish, reduce)
+    roofline["launches_per_step"] = max(rounds, 1)
+    roofline["avg_launch_ms"] = dom_ms / max(rounds, 1)
+    roofline["ms_per_step"] = dom_ms
+    roofline["traffic"] = roofline_hbm["traffic"]
+    roofline["note"] = ("SURVEY 8d / north_star: the MSM is bounded by the integer-multiply pipe, not HBM; 'peak' is the measured "
+                        "Fq Montgomery product rate of this GPU (276 IMAD.WIDE each, 96 % of the 31.5 IMAD.WIDE/clk/SM pipe); "
+                        "roofline_hbm keeps the HBM view the base contract asks for")
     ntt_pass_ms = sum(v for k_, v in stage.items() if k_.startswith("ntt_pass")) / K
     ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
@@ -433,13 +509,17 @@ def run_b200(args):
         hb = bases[: (1 << ml) * 104].cpu().numpy()
         hs = scalars[: 1 << ml].cpu().numpy().view(np.uint64)
         hn = ntt_data[: 1 << nl].cpu().numpy().view(np.uint64)
+        C.ntt(hn[: 1 << 10], 10)
+        C.ntt(hn, nl, nthreads=host_threads())                   # untimed: builds the cached precomputation for 2^nl
         tm, tn = cpu_time_once(hb, hs, hn, nl)
         cores = host_threads()
         cpu = {"value": (1 << ml) / tm / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
-               "sample": f"first 2^{ml} of the same bases/scalars, {tm:.2f} s; C restatement of snarkVM standard::msm "
-                         f"(c = ln n + 2, Jacobian buckets), OpenMP over windows; NOT snarkVM itself (no Rust toolchain)"}
+               "sample": f"{'the same' if ml == args.log_n else 'first'} 2^{ml} bases/scalars, {tm:.2f} s; batched::msm port (C restatement "
+                         f"of snarkVM batched::msm: c = ln n + 2 = {C.lib().oracle_msm_window_bits(1 << ml)}, one task per window, affine "
+                         f"pair additions with one inversion per 1500 pairs), OpenMP; NOT snarkVM itself (no Rust toolchain)"}
         ntt_cpu = {"value": (1 << nl) / tn / 1e9, "unit": "Gelem/s", "cores": cores, "kind": "port",
-                   "sample": f"first 2^{nl} elements as one polynomial, {tn:.2f} s; in-order radix-2 FFT with root table, OpenMP"}
+                   "sample": f"first 2^{nl} elements as one polynomial, {tn:.2f} s; in-order radix-2 FFT, FFTPrecomputation "
+                             f"(roots, size_inv) cached outside the timed call like snarkVM's, OpenMP"}
 
     # ---- config 4 shape: the small MSMs of 256 transactions' verification, batched into one call (rank 0, N = 1) -----
     batch_verify = None
@@ -456,14 +536,80 @@ def run_b200(args):
         t_gpu = (time.perf_counter() - t0) / reps
         batch_verify = {"workload": f"{n_tx} independent MSMs x {per} points (KZG10::batch_check linear combinations of a block)",
                         "e2e_ms": t_gpu * 1e3, "msms_per_s": n_tx / t_gpu, "api": "snarkos_b200.msm_batch -> b200_msm_batch_g1_bls12_377 (host buffers)"}
+        # the same 256 MSMs arriving from 64 host threads at once through the coalescing queue (b200_msm_submit / _wait):
+        # what the validator's parallel transaction checks look like at the C ABI
+        import ctypes as ct
+        import threading
+        L = S.lib()
+        outq = np.zeros((n_tx, 144), dtype=np.uint8)
+        n_thr = 64
+
+        def verify_worker(t, barrier_):
+            barrier_.wait()
+            for m in range(t, n_tx, n_thr):
+                tk = ct.c_uint64(0)
+                L.b200_msm_submit(hb[m * per * 104:].ctypes.data_as(ct.c_void_p), per, hs[m * per:].ctypes.data_as(ct.c_void_p), 104, ct.byref(tk))
+                L.b200_msm_wait(tk.value, outq[m].ctypes.data_as(ct.c_void_p))
+
+        best = None
+        b0 = S.counter("queue_batches")
+        for rep in range(4):
+            bar = threading.Barrier(n_thr + 1)
+            ths = [threading.Thread(target=verify_worker, args=(t, bar)) for t in range(n_thr)]
+            for th in ths:
+                th.start()
+            bar.wait()
+            t0 = time.perf_counter()
+            for th in ths:
+                th.join()
+            dt = time.perf_counter() - t0
+            if rep and (best is None or dt < best):
+                best = dt
+        batch_verify["queued_64_threads_ms"] = best * 1e3
+        batch_verify["queued_batches_per_block"] = (S.counter("queue_batches") - b0) / 4
+        batch_verify["queued_api"] = "b200_msm_submit + b200_msm_wait from 64 threads, 4 MSMs each (python threads: includes GIL hand-offs)"
         if not args.no_cpu_baseline:
             from oracle import c_oracle as C
+            C.msm_many(hb, hs, off, nthreads=host_threads())
             t0 = time.perf_counter()
-            for m in range(n_tx):
-                C.msm(hb[m * per * 104:(m + 1) * per * 104], hs[m * per:(m + 1) * per])
+            C.msm_many(hb, hs, off, nthreads=host_threads())
             t_cpu = time.perf_counter() - t0
             batch_verify["cpu_port_ms"] = t_cpu * 1e3
-            batch_verify["cpu_port_note"] = "the same 256 MSMs through the C oracle one after another (each parallel over its windows)"
+            batch_verify["cpu_port_note"] = (f"the same 256 MSMs through the batched::msm port, one task per MSM on {host_threads()} threads "
+                                             f"(the reference verifies a block's transactions rayon-parallel)")
+
+    # ---- BASELINE configs[0]: 2^16 random bases / scalars through VariableBase::msm (rank 0, N = 1) ----------------------
+    config0 = None
+    if world == 1:
+        n0 = 1 << 16
+        hb0 = bases[: n0 * 104].cpu().pin_memory()
+        hs0 = scalars[:n0].cpu().pin_memory()
+        S.VariableBase.msm(hb0, hs0)
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            S.VariableBase.msm(hb0, hs0)
+        t_h = (time.perf_counter() - t0) / reps
+        db0, ds0 = bases[: n0 * 104], scalars[:n0]
+        S.VariableBase.msm(db0, ds0)
+        torch.cuda.synchronize()
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        for _ in range(reps):
+            S.VariableBase.msm(db0, ds0)
+        e1_.record()
+        torch.cuda.synchronize()
+        config0 = {"workload": "configs[0]: BLS12-377 G1 MSM, 2^16 random bases / scalars", "e2e_ms": t_h * 1e3,
+                   "e2e_mpoints_s": n0 / t_h / 1e6, "device_ms": e0_.elapsed_time(e1_) / reps,
+                   "h2d_bytes": n0 * 136, "api": "VariableBase.msm(pinned host buffers) -> b200_msm_g1_bls12_377"}
+        if not args.no_cpu_baseline:
+            from oracle import c_oracle as C
+            hb0n, hs0n = hb0.numpy(), hs0.numpy().view(np.uint64)
+            C.msm_batched(hb0n, hs0n, nthreads=host_threads())
+            t0 = time.perf_counter()
+            C.msm_batched(hb0n, hs0n, nthreads=host_threads())
+            config0["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+            config0["cpu_port_note"] = f"batched::msm port, {host_threads()} threads (c = 13: 20 windows)"
 
     line = {
         "metric": METRIC, "value": world * n * K / (msm_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -477,19 +623,25 @@ def run_b200(args):
                    "bases": "k_i * G, k_i = splitmix64(seed, i), generated on the device; scalars / Fr data uniform < 2^252"},
         "msm_ms": msm_ms / K, "clocks": clocks, "gpu_launches": int(launches),
         "stage_ms_per_step": {k_: v / K for k_, v in stage.items()},
-        "roofline": roofline, "roofline_int": roofline_int,
+        "roofline": roofline, "roofline_hbm": roofline_hbm,
         "ntt": {"value": world * n * K / (ntt_ms * 1e-3) / 1e9, "unit": "Gelem/s", "ms": ntt_ms / K, "roofline": ntt_roof,
                 "e2e": ntt_e2e, "cpu_baseline": ntt_cpu},
     }
     if batch_verify is not None:
         line["batch_verify_msm"] = batch_verify
+    if config0 is not None:
+        line["config0_msm_2^16"] = config0
+    if strong is not None:
+        line["strong_2^26"] = strong
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stderr.flush()
+    print("\n" + json.dumps(line), flush=True)           # last line of stdout, whatever NCCL_DEBUG printed before
 
 
 if __name__ == "__main__":

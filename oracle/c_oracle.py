@@ -44,6 +44,12 @@ def lib() -> ctypes.CDLL:
         L.oracle_g1_is_on_curve.restype = i32
         L.oracle_msm.argtypes = [vp, vp, sz, sz, vp, i32]
         L.oracle_msm.restype = None
+        L.oracle_msm_batched.argtypes = [vp, vp, sz, sz, vp, i32]
+        L.oracle_msm_batched.restype = None
+        L.oracle_msm_many.argtypes = [vp, vp, vp, vp, sz, sz, i32]
+        L.oracle_msm_many.restype = None
+        L.oracle_g1_sequence.argtypes = [vp, ctypes.c_uint64, sz, sz, i32]
+        L.oracle_g1_sequence.restype = None
         L.oracle_msm_window_bits.argtypes = [sz]
         L.oracle_msm_window_bits.restype = i32
         L.oracle_ntt.argtypes = [vp, i32, sz, sz, i32, i32, i32]
@@ -99,6 +105,36 @@ def msm(bases: np.ndarray, scalars: np.ndarray, stride: int = 104, nthreads: int
     assert bases.size >= n * stride
     out = np.zeros(144, dtype=np.uint8)
     lib().oracle_msm(_p(out), _p(bases), n, stride, _p(scalars), nthreads)
+    return out
+
+
+def msm_batched(bases: np.ndarray, scalars: np.ndarray, stride: int = 104, nthreads: int = 0) -> np.ndarray:
+    """snarkVM batched::msm restated (affine pair additions sharing one inversion per batch) -- the variant
+    VariableBase::msm runs for BLS12-377 G1; same interface as msm()."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    n = scalars.shape[0]
+    assert bases.size >= n * stride
+    out = np.zeros(144, dtype=np.uint8)
+    lib().oracle_msm_batched(_p(out), _p(bases), n, stride, _p(scalars), nthreads)
+    return out
+
+
+def msm_many(bases: np.ndarray, scalars: np.ndarray, offsets, stride: int = 104, nthreads: int = 0) -> np.ndarray:
+    """independent MSMs over [offsets[m], offsets[m+1]), one task per MSM (the reference verifies a block's transactions
+    rayon-parallel); returns uint8 [nmsm, 144]"""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8).reshape(-1)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.zeros((off.size - 1, 144), dtype=np.uint8)
+    lib().oracle_msm_many(_p(out), _p(bases), _p(scalars), _p(off), off.size - 1, stride, nthreads)
+    return out
+
+
+def g1_sequence(k0: int, n: int, stride: int = 104, nthreads: int = 0) -> np.ndarray:
+    """(k0 + i) * G for i < n as affine images [n, stride]: n distinct points at ~1 us each"""
+    out = np.zeros((n, stride), dtype=np.uint8)
+    lib().oracle_g1_sequence(_p(out), k0, n, stride, nthreads)
     return out
 
 

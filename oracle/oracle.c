@@ -3,7 +3,9 @@
  * reaches through VM::execute / Ledger::check_* (SURVEY.md section 8a):
  *
  *   VariableBase::msm over BLS12-377 G1        [UPSTREAM snarkvm-algorithms 1.0.0 @ dea322b,
- *                                               algorithms/src/msm/variable_base/{mod,standard}.rs]
+ *                                               algorithms/src/msm/variable_base/{mod,batched,standard}.rs]
+ *       oracle_msm_batched = batched::msm (what BLS12-377 G1 is dispatched to: affine pair additions with
+ *       one inversion per batch), oracle_msm = standard::msm (Jacobian buckets; the independent cross-check)
  *   EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place over Fr
  *                                              [UPSTREAM algorithms/src/fft/domain.rs]
  *   Fp256 / Fp384 Montgomery arithmetic on 64-bit limbs
@@ -99,32 +101,28 @@ typedef uint64_t u64;
         PFX##_sub_nored(r, MOD, a);                                                             \
     }                                                                                           \
     static inline void PFX##_dbl(u64 *r, const u64 *a) { PFX##_add(r, a, a); }                  \
+    /* "no-carry" CIOS [UPSTREAM fields/src/fp_256.rs / fp_384.rs mul_assign: the modulus leaves its top bit     \
+     * spare, so product and reduction of one row run as two interleaved carry chains and t never needs an        \
+     * extra limb]; fully unrolled (N is a constant) so that t lives in registers */                              \
     static inline void PFX##_mul(u64 *r, const u64 *a, const u64 *b) {                          \
-        u64 t[N + 2];                                                                           \
-        memset(t, 0, sizeof(t));                                                                \
-        for (int i = 0; i < N; i++) {                                                           \
-            u64 c = 0;                                                                          \
-            for (int j = 0; j < N; j++) {                                                       \
-                u128 p = (u128)a[j] * b[i] + t[j] + c;                                          \
-                t[j] = (u64)p;                                                                  \
-                c = (u64)(p >> 64);                                                             \
+        u64 t[N];                                                                               \
+        _Pragma("GCC unroll 8") for (int j = 0; j < N; j++) t[j] = 0;                           \
+        _Pragma("GCC unroll 8") for (int i = 0; i < N; i++) {                                   \
+            u128 p = (u128)a[0] * b[i] + t[0];                                                  \
+            u64 c1 = (u64)(p >> 64);                                                            \
+            const u64 k = (u64)p * (u64)(INV);                                                  \
+            u128 q = (u128)k * MOD[0] + (u64)p;                                                 \
+            u64 c2 = (u64)(q >> 64);                                                            \
+            _Pragma("GCC unroll 8") for (int j = 1; j < N; j++) {                               \
+                p = (u128)a[j] * b[i] + t[j] + c1;                                              \
+                c1 = (u64)(p >> 64);                                                            \
+                q = (u128)k * MOD[j] + (u64)p + c2;                                             \
+                c2 = (u64)(q >> 64);                                                            \
+                t[j - 1] = (u64)q;                                                              \
             }                                                                                   \
-            u128 s = (u128)t[N] + c;                                                            \
-            t[N] = (u64)s;                                                                      \
-            t[N + 1] = (u64)(s >> 64);                                                          \
-            u64 m = t[0] * (u64)(INV);                                                          \
-            u128 p = (u128)m * MOD[0] + t[0];                                                   \
-            c = (u64)(p >> 64);                                                                 \
-            for (int j = 1; j < N; j++) {                                                       \
-                p = (u128)m * MOD[j] + t[j] + c;                                                \
-                t[j - 1] = (u64)p;                                                              \
-                c = (u64)(p >> 64);                                                             \
-            }                                                                                   \
-            s = (u128)t[N] + c;                                                                 \
-            t[N - 1] = (u64)s;                                                                  \
-            t[N] = t[N + 1] + (u64)(s >> 64);                                                   \
+            t[N - 1] = c1 + c2;                                                                 \
         }                                                                                       \
-        if (t[N] || PFX##_geq(t, MOD)) PFX##_sub_nored(t, t, MOD);                              \
+        if (PFX##_geq(t, MOD)) PFX##_sub_nored(t, t, MOD);                                      \
         memcpy(r, t, N * 8);                                                                    \
     }                                                                                           \
     static inline void PFX##_sqr(u64 *r, const u64 *a) { PFX##_mul(r, a, a); }                  \
@@ -452,6 +450,254 @@ void oracle_msm(uint8_t *out_jac, const uint8_t *bases, size_t n, size_t stride,
     memcpy(out_jac, &total, 144);
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * batched::msm restated -- the variant VariableBase::msm dispatches BLS12-377 G1 to
+ *   [UPSTREAM algorithms/src/msm/variable_base/batched.rs: msm / batched_window / batch_add /
+ *    batch_add_in_place, curves/.../short_weierstrass_jacobian/affine.rs: batch_add_loop_1 / batch_add_loop_2]
+ *
+ *   n < 15              bit-serial double-and-add over all bases
+ *   c = 1 (n < 32) else ln(n) + 2, unsigned c-bit windows, 2^c - 1 buckets, one task per window (rayon there,
+ *   OpenMP here -- so at most ceil(253 / c) threads are ever busy, exactly like upstream)
+ *   per window: (bucket, index) positions sorted by bucket; rounds of PAIRWISE AFFINE additions, flushed in batches of
+ *   batch_size / 2 pairs that share ONE field inversion (Montgomery's trick: ~6 Fq products per addition instead of
+ *   the ~11 of a Jacobian mixed addition); the first round reads the bases, later rounds work in place; then the
+ *   running-sum reduction in Jacobian coordinates and the fold over windows, high to low.
+ * Only the order inside a bucket may differ from upstream (stable counting sort instead of sort_unstable); the group
+ * element is the same.
+ * ---------------------------------------------------------------------------------------- */
+static size_t batched_batch_size(size_t n) { return n < 500000 ? 300 : 3000; }    /* upstream get_batch_size (x86_64) */
+
+typedef struct { u64 x[6], y[6]; } affp_t;            /* affine, (0, 0) = infinity */
+static inline int affp_is_inf(const affp_t *p) { return fq_is_zero(p->x) && fq_is_zero(p->y); }
+
+/* out[i] = a[i] + b[i] for cnt pairs with one shared inversion.  Exceptional pairs are resolved on the spot. */
+static void batched_pairs_add(affp_t *out, const affp_t *a, const affp_t *b, size_t cnt, u64 (*den)[6], u64 (*pre)[6]) {
+    u64 acc[6];
+    memcpy(acc, FQ_ONE, 48);
+    /* loop 1: denominators and running products */
+    for (size_t i = 0; i < cnt; i++) {
+        memcpy(pre[i], acc, 48);
+        if (affp_is_inf(&a[i]) || affp_is_inf(&b[i])) { memset(den[i], 0, 48); continue; }
+        if (fq_eq(a[i].x, b[i].x)) {
+            if (fq_eq(a[i].y, b[i].y) && !fq_is_zero(a[i].y)) fq_dbl(den[i], a[i].y);   /* doubling: 2 y */
+            else { memset(den[i], 0, 48); continue; }                                   /* P + (-P) */
+        } else {
+            fq_sub(den[i], b[i].x, a[i].x);
+        }
+        fq_mul(acc, acc, den[i]);
+    }
+    u64 inv[6];
+    fq_inv(inv, acc, FQ_ONE);
+    /* loop 2: walk back, peel the inverses off, finish the additions */
+    for (size_t i = cnt; i-- > 0;) {
+        if (fq_is_zero(den[i])) {
+            if (affp_is_inf(&a[i])) out[i] = b[i];
+            else if (affp_is_inf(&b[i])) out[i] = a[i];
+            else memset(&out[i], 0, sizeof(affp_t));
+            continue;
+        }
+        u64 dinv[6], lam[6], num[6], x3[6], y3[6], t[6];
+        fq_mul(dinv, inv, pre[i]);
+        fq_mul(inv, inv, den[i]);
+        if (fq_eq(a[i].x, b[i].x)) {                   /* doubling: lambda = 3 x^2 / 2 y */
+            fq_sqr(t, a[i].x);
+            fq_dbl(num, t);
+            fq_add(num, num, t);
+        } else {
+            fq_sub(num, b[i].y, a[i].y);
+        }
+        fq_mul(lam, num, dinv);
+        fq_sqr(x3, lam);
+        fq_sub(x3, x3, a[i].x);
+        fq_sub(x3, x3, b[i].x);
+        fq_sub(t, a[i].x, x3);
+        fq_mul(y3, lam, t);
+        fq_sub(y3, y3, a[i].y);
+        memcpy(out[i].x, x3, 48);
+        memcpy(out[i].y, y3, 48);
+    }
+}
+
+static void batched_window(jac_t *res, const uint8_t *bases, size_t n, size_t stride, const u64 *scalars, int w_start, int c) {
+    const size_t nb = ((size_t)1 << c) - 1;
+    const size_t batch = batched_batch_size(n) / 2;
+    /* positions sorted by bucket (counting sort): idx[off[b] .. off[b + 1]) = scalar indices of bucket b */
+    uint32_t *off = (uint32_t *)calloc(nb + 2, sizeof(uint32_t));
+    uint32_t *idx = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        unsigned d = get_window(scalars + 4 * i, w_start, c);
+        if (d) off[d + 1]++;
+    }
+    for (size_t b = 1; b <= nb + 1; b++) off[b] += off[b - 1];
+    uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * (nb + 2));
+    memcpy(cur, off, sizeof(uint32_t) * (nb + 2));
+    for (size_t i = 0; i < n; i++) {
+        unsigned d = get_window(scalars + 4 * i, w_start, c);
+        if (d) idx[cur[d]++] = (uint32_t)i;
+    }
+    const size_t total = off[nb + 1];
+    /* lists: cnt[b] points of bucket b at pts[start[b]..]; the first round builds them from the bases */
+    affp_t *pts = (affp_t *)malloc(sizeof(affp_t) * (total / 2 + nb + 1));
+    uint32_t *start = (uint32_t *)malloc(sizeof(uint32_t) * (nb + 1));
+    uint32_t *cnt = (uint32_t *)malloc(sizeof(uint32_t) * (nb + 1));
+    affp_t *pa = (affp_t *)malloc(sizeof(affp_t) * batch), *pb = (affp_t *)malloc(sizeof(affp_t) * batch);
+    affp_t *po = (affp_t *)malloc(sizeof(affp_t) * batch);
+    u64(*den)[6] = (u64(*)[6])malloc(48 * batch);
+    u64(*pre)[6] = (u64(*)[6])malloc(48 * batch);
+    size_t *dst = (size_t *)malloc(sizeof(size_t) * batch);
+    size_t pend = 0, wr = 0;
+    int all_ones = 1;
+#define FLUSH()                                                          \
+    do {                                                                 \
+        if (pend) {                                                      \
+            batched_pairs_add(po, pa, pb, pend, den, pre);               \
+            for (size_t q_ = 0; q_ < pend; q_++) pts[dst[q_]] = po[q_];  \
+            pend = 0;                                                    \
+        }                                                                \
+    } while (0)
+    for (size_t b = 1; b <= nb; b++) {                 /* round 1: bases -> lists (batch_add_write) */
+        const uint32_t lo = off[b], m = off[b + 1] - lo;
+        start[b] = (uint32_t)wr;
+        cnt[b] = (m + 1) / 2;
+        if (cnt[b] > 1) all_ones = 0;
+        for (uint32_t j = 0; j + 1 < m; j += 2) {
+            aff_t A, B;
+            load_affine(&A, bases + (size_t)idx[lo + j] * stride);
+            load_affine(&B, bases + (size_t)idx[lo + j + 1] * stride);
+            memset(&pa[pend], 0, sizeof(affp_t));
+            memset(&pb[pend], 0, sizeof(affp_t));
+            if (!A.inf) { memcpy(pa[pend].x, A.x, 48); memcpy(pa[pend].y, A.y, 48); }
+            if (!B.inf) { memcpy(pb[pend].x, B.x, 48); memcpy(pb[pend].y, B.y, 48); }
+            dst[pend++] = wr++;
+            if (pend == batch) FLUSH();
+        }
+        if (m & 1) {                                   /* the odd one out is copied through (upstream: !0u32 instruction) */
+            aff_t A;
+            load_affine(&A, bases + (size_t)idx[lo + m - 1] * stride);
+            memset(&pts[wr], 0, sizeof(affp_t));
+            if (!A.inf) { memcpy(pts[wr].x, A.x, 48); memcpy(pts[wr].y, A.y, 48); }
+            wr++;
+        }
+    }
+    FLUSH();
+    while (!all_ones) {                                /* later rounds in place (batch_add_in_place) */
+        all_ones = 1;
+        for (size_t b = 1; b <= nb; b++) {
+            const uint32_t m = cnt[b], s0 = start[b];
+            if (m < 2) continue;
+            /* results go to the front of the bucket's own range: slot j/2 <- slots j, j + 1.  The operands are copied
+             * out when the pair is queued and a queued result lands at or below the slots already consumed, so
+             * nothing still to be read in this round is overwritten; every queue is flushed before the next round */
+            for (uint32_t j = 0; j + 1 < m; j += 2) {
+                pa[pend] = pts[s0 + j];
+                pb[pend] = pts[s0 + j + 1];
+                dst[pend++] = s0 + j / 2;
+                if (pend == batch) FLUSH();
+            }
+            if (m & 1) pts[s0 + m / 2] = pts[s0 + m - 1];
+            cnt[b] = (m + 1) / 2;
+            if (cnt[b] > 1) all_ones = 0;
+        }
+        FLUSH();
+    }
+#undef FLUSH
+    /* running-sum reduction: res = sum_b b * bucket_b */
+    jac_t running, acc;
+    jac_set_inf(&running);
+    jac_set_inf(&acc);
+    for (size_t b = nb; b >= 1; b--) {
+        if (cnt[b]) {
+            aff_t q;
+            q.inf = affp_is_inf(&pts[start[b]]);
+            memcpy(q.x, pts[start[b]].x, 48);
+            memcpy(q.y, pts[start[b]].y, 48);
+            jac_add_affine(&running, &running, &q);
+        }
+        jac_add(&acc, &acc, &running);
+    }
+    *res = acc;
+    free(off); free(idx); free(cur); free(pts); free(start); free(cnt); free(pa); free(pb); free(po); free(den); free(pre); free(dst);
+}
+
+void oracle_msm_batched(uint8_t *out_jac, const uint8_t *bases, size_t n, size_t stride, const u64 *scalars, int nthreads) {
+    jac_t total;
+    jac_set_inf(&total);
+    if (n < 15) { oracle_msm(out_jac, bases, n, stride, scalars, nthreads); return; }   /* same bit-serial path */
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    const int c = oracle_msm_window_bits(n);
+    const int nwin = (253 + c - 1) / c;
+    jac_t *wsum = (jac_t *)malloc(sizeof(jac_t) * nwin);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int w = 0; w < nwin; w++) batched_window(&wsum[w], bases, n, stride, scalars, w * c, c);
+    for (int w = nwin - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) jac_double(&total, &total);
+        jac_add(&total, &total, &wsum[w]);
+    }
+    free(wsum);
+    memcpy(out_jac, &total, 144);
+}
+
+/* out[i] = (k0 + i) * G as affine images: n DISTINCT points in ~1 us each (one mixed addition per point, one shared
+ * inversion per chunk) -- inputs for the CPU arm of bench.py at full size without any GPU code. */
+void oracle_g1_sequence(uint8_t *out_affine, u64 k0, size_t n, size_t stride, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    aff_t g;
+    memcpy(g.x, G1_GEN_X, 48);
+    memcpy(g.y, G1_GEN_Y, 48);
+    g.inf = 0;
+    const size_t chunk = 4096;
+    const long nchunks = (long)((n + chunk - 1) / chunk);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (long ci = 0; ci < nchunks; ci++) {
+        const size_t lo = (size_t)ci * chunk, hi = lo + chunk < n ? lo + chunk : n, m = hi - lo;
+        jac_t *J = (jac_t *)malloc(sizeof(jac_t) * m);
+        u64(*pre)[6] = (u64(*)[6])malloc(48 * m);
+        jac_t acc;
+        jac_set_inf(&acc);
+        const u64 k = k0 + lo;
+        for (int bit = 63; bit >= 0; bit--) {
+            jac_double(&acc, &acc);
+            if ((k >> bit) & 1) jac_add_affine(&acc, &acc, &g);
+        }
+        u64 prod[6];
+        memcpy(prod, FQ_ONE, 48);
+        for (size_t i = 0; i < m; i++) {
+            J[i] = acc;
+            memcpy(pre[i], prod, 48);
+            if (!fq_is_zero(acc.z)) fq_mul(prod, prod, acc.z);
+            jac_add_affine(&acc, &acc, &g);
+        }
+        u64 inv[6];
+        fq_inv(inv, prod, FQ_ONE);
+        for (size_t i = m; i-- > 0;) {
+            aff_t a;
+            if (fq_is_zero(J[i].z)) { memset(&a, 0, sizeof(a)); a.inf = 1; }
+            else {
+                u64 zi[6], zi2[6];
+                fq_mul(zi, inv, pre[i]);
+                fq_mul(inv, inv, J[i].z);
+                fq_sqr(zi2, zi);
+                fq_mul(a.x, J[i].x, zi2);
+                fq_mul(zi2, zi2, zi);
+                fq_mul(a.y, J[i].y, zi2);
+                a.inf = 0;
+            }
+            store_affine(out_affine + stride * (lo + i), &a, stride);
+        }
+        free(J);
+        free(pre);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * EvaluationDomain over Fr: in-order radix-2 (i)FFT with a precomputed root table
  * (io_helper / oi_helper + derange restated as bit-reverse + DIT), Montgomery data in place.
@@ -474,6 +720,51 @@ static inline size_t bitrev(size_t x, int bits) {
     return r;
 }
 
+/* FFTPrecomputation restated [UPSTREAM algorithms/src/fft/domain.rs: precompute_fft / precompute_ifft]: snarkVM builds
+ * the n/2 powers of the root ONCE per domain and callers keep it (Varuna holds it in the proving key's domains), so the
+ * table -- and size_inv, and the coset powers -- are cached here per (log_n, direction) and built in parallel; a timed
+ * oracle_ntt call after the first one does transforms only. */
+typedef struct { u64 *roots; u64 *cpow; u64 size_inv[4]; int ready; } ntt_pc_t;
+static ntt_pc_t g_ntt_pc[64][2];
+
+static void powers_parallel(u64 *out, const u64 *base, size_t count, int nthreads) {
+    /* out[i] = base^i: chunk heads by square-and-multiply, then one multiplication per element */
+    const size_t chunk = 1 << 12;
+    const long nchunks = (long)((count + chunk - 1) / chunk);
+    (void)nthreads;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (long ci = 0; ci < nchunks; ci++) {
+        const size_t lo = (size_t)ci * chunk, hi = lo + chunk < count ? lo + chunk : count;
+        u64 e[1] = {lo};
+        fr_pow(out + 4 * lo, base, e, 1, FR_ONE);
+        for (size_t i = lo + 1; i < hi; i++) fr_mul(out + 4 * i, out + 4 * (i - 1), base);
+    }
+}
+
+static ntt_pc_t *ntt_precomputation(int log_n, int direction, int need_coset, int nthreads) {
+    ntt_pc_t *pc = &g_ntt_pc[log_n][direction];
+#pragma omp critical(oracle_ntt_pc)
+    {
+        const size_t n = (size_t)1 << log_n;
+        if (!pc->ready) {
+            u64 gen[4];
+            domain_group_gen(gen, log_n, direction);
+            const size_t half = n > 1 ? n / 2 : 1;
+            pc->roots = (u64 *)malloc(32 * half);
+            powers_parallel(pc->roots, gen, half, nthreads);
+            u64 nn[4] = {n, 0, 0, 0};
+            fr_mul(nn, nn, FR_R2);
+            fr_inv(pc->size_inv, nn, FR_ONE);
+            pc->ready = 1;
+        }
+        if (need_coset && !pc->cpow) {
+            pc->cpow = (u64 *)malloc(32 * n);
+            powers_parallel(pc->cpow, direction ? FR_GENERATOR_INV : FR_GENERATOR, n, nthreads);
+        }
+    }
+    return pc;
+}
+
 static void ntt_one(u64 *a, int log_n, const u64 *roots /* n/2 powers of omega */, int par,
                     int nthreads) {
     size_t n = (size_t)1 << log_n;
@@ -486,21 +777,34 @@ static void ntt_one(u64 *a, int log_n, const u64 *roots /* n/2 powers of omega *
             memcpy(t, a + 4 * i, 32); memcpy(a + 4 * i, a + 4 * j, 32); memcpy(a + 4 * j, t, 32);
         }
     }
+    /* upstream compacts the roots a layer needs into a contiguous run when the stride through the table gets large
+     * (cache behaviour of the short-distance layers); same here */
+    u64 *compact = (u64 *)malloc(32 * (n > 1 ? n / 2 : 1));
     for (int s = 0; s < log_n; s++) {
         size_t m = (size_t)1 << s;
         size_t tw_stride = n >> (s + 1);
+        const u64 *tw = roots;
+        size_t tws = tw_stride;
+        if (tw_stride > 1 && m >= 2) {
+#pragma omp parallel for schedule(static) if (par && m >= 4096) num_threads(nthreads)
+            for (long j = 0; j < (long)m; j++) memcpy(compact + 4 * j, roots + 4 * ((size_t)j * tw_stride), 32);
+            tw = compact;
+            tws = 1;
+        }
         /* butterfly q of this stage: block k = (q / m) * 2m, offset j = q % m */
 #pragma omp parallel for schedule(static) if (par) num_threads(nthreads)
         for (long q = 0; q < (long)(n / 2); q++) {
             size_t j = (size_t)q & (m - 1);
             size_t k = (((size_t)q) >> s) << (s + 1);
             u64 t[4], u[4];
-            fr_mul(t, a + 4 * (k + j + m), roots + 4 * (j * tw_stride));
+            if (j) fr_mul(t, a + 4 * (k + j + m), tw + 4 * (j * tws));
+            else memcpy(t, a + 4 * (k + j + m), 32);
             memcpy(u, a + 4 * (k + j), 32);
             fr_add(a + 4 * (k + j), u, t);
             fr_sub(a + 4 * (k + j + m), u, t);
         }
     }
+    free(compact);
 }
 
 void oracle_ntt(u64 *data, int log_n, size_t batch, size_t batch_stride_elems, int direction,
@@ -511,23 +815,8 @@ void oracle_ntt(u64 *data, int log_n, size_t batch, size_t batch_stride_elems, i
 #else
     nthreads = 1;
 #endif
-    u64 gen[4];
-    domain_group_gen(gen, log_n, direction);
-    size_t half = n > 1 ? n / 2 : 1;
-    u64 *roots = (u64 *)malloc(32 * half);
-    memcpy(roots, FR_ONE, 32);
-    for (size_t i = 1; i < half; i++) fr_mul(roots + 4 * i, roots + 4 * (i - 1), gen);
-    u64 size_inv[4], nn[4] = {n, 0, 0, 0};
-    fr_mul(nn, nn, FR_R2);
-    fr_inv(size_inv, nn, FR_ONE);
-    /* coset powers g^i (forward: before the FFT) or g^-i (inverse: after the iFFT) */
-    u64 *cpow = NULL;
-    if (coset) {
-        cpow = (u64 *)malloc(32 * n);
-        memcpy(cpow, FR_ONE, 32);
-        const u64 *g = direction ? FR_GENERATOR_INV : FR_GENERATOR;
-        for (size_t i = 1; i < n; i++) fr_mul(cpow + 4 * i, cpow + 4 * (i - 1), g);
-    }
+    const ntt_pc_t *pc = ntt_precomputation(log_n, direction, coset, nthreads);
+    const u64 *roots = pc->roots, *cpow = pc->cpow, *size_inv = pc->size_inv;
     int outer = (batch >= (size_t)nthreads) || nthreads == 1;   /* parallel over polys, else inside one */
 #pragma omp parallel for schedule(dynamic, 1) if (outer) num_threads(nthreads)
     for (long b = 0; b < (long)batch; b++) {
@@ -546,9 +835,22 @@ void oracle_ntt(u64 *data, int log_n, size_t batch, size_t batch_stride_elems, i
             for (long i = 0; i < (long)n; i++) fr_mul(a + 4 * i, a + 4 * i, cpow + 4 * i);
         }
     }
-    free(roots);
-    if (cpow) free(cpow);
     (void)fr_pow_u64;
+}
+
+/* many independent MSMs, one task per MSM (rayon over transactions in the reference's block verification) */
+void oracle_msm_many(uint8_t *out_jac, const uint8_t *bases, const u64 *scalars, const u64 *offsets, size_t nmsm,
+                     size_t stride, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (long m = 0; m < (long)nmsm; m++) {
+        const size_t lo = offsets[m], hi = offsets[m + 1];
+        oracle_msm_batched(out_jac + 144 * (size_t)m, bases + lo * stride, hi - lo, stride, scalars + 4 * lo, 1);
+    }
 }
 
 int oracle_num_threads(void) {

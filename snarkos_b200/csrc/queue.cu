@@ -53,7 +53,9 @@ struct QueueState {
     size_t d_cap = 0;
     cudaStream_t stream = nullptr;
 };
-static QueueState g_q;
+// Never destroyed: a process that exits without b200_shutdown still has the dispatcher parked on its condition
+// variable, and destroying a joinable std::thread (or a mutex a thread sleeps on) during static destruction aborts.
+static QueueState& g_q = *new QueueState();
 
 static void job_complete(QueueJob& j, b200_error_t err) {
     std::lock_guard<std::mutex> lock(j.mu);

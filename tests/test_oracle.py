@@ -162,3 +162,67 @@ def test_c_ntt_kat_and_inner_parallel():
     b = C.ntt(x, 12, nthreads=4)
     assert np.array_equal(a, b)
     assert np.array_equal(C.ntt(a, 12, direction=1), x)
+
+
+# ---------------------------------------------------------------------------------------------
+# batched::msm restated (the variant snarkVM dispatches BLS12-377 G1 to) against the other two formulations
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 14, 15, 31, 32, 100, 1000, 5000])
+def test_batched_msm_equals_standard_and_naive(n):
+    """mirrors snarkVM variable_base::tests::test_msm (naive vs standard vs batched, sizes 1..1000)"""
+    rng = np.random.default_rng(n)
+    pts = C.g1_sequence(777 + n, n)
+    sc = H.random_scalars_np(rng, n)
+    if n > 40:
+        sc[0] = 0
+        sc[1] = H.scalars_array([O.R_MOD - 1])[0]
+        pts[3] = 0
+        pts[3, 96] = 1                                   # infinity inside the bases
+        pts[7], sc[7] = pts[6], sc[6]                    # equal points in one bucket: the pair is a doubling
+    std = C.g1_to_affine(C.msm(pts.reshape(-1), sc))
+    bat = C.g1_to_affine(C.msm_batched(pts.reshape(-1), sc))
+    assert np.array_equal(std, bat)
+    if n <= 100:
+        ks = [777 + n + i for i in range(n)]
+        svals = H.limbs_to_ints(sc)
+        total = 0
+        for i in range(n):
+            if pts[i, 96] == 0:
+                k = ks[i] if not (n > 40 and i == 7) else ks[6]
+                total += svals[i] * k
+        want = O.g1_mul(O.G1_GEN, total % O.R_MOD)
+        assert H.jac_bytes_to_affine(C.msm_batched(pts.reshape(-1), sc)) == want
+    # degenerate distributions: every point in one bucket / every pair a doubling
+    same_s = np.tile(sc[n // 2:n // 2 + 1], (n, 1))
+    assert np.array_equal(C.g1_to_affine(C.msm(pts.reshape(-1), same_s)), C.g1_to_affine(C.msm_batched(pts.reshape(-1), same_s)))
+    same_p = np.tile(pts[n // 2:n // 2 + 1], (n, 1))
+    assert np.array_equal(C.g1_to_affine(C.msm(same_p.reshape(-1), sc)), C.g1_to_affine(C.msm_batched(same_p.reshape(-1), sc)))
+
+
+def test_point_sequence_and_msm_many():
+    g = np.frombuffer(O.affine_bytes(O.G1_GEN), dtype=np.uint8)
+    k0 = 99990
+    assert np.array_equal(C.g1_sequence(k0, 5000), C.g1_mul_u64(g, np.arange(k0, k0 + 5000, dtype=np.uint64)))
+    assert C.g1_sequence(0, 3)[0, 96] == 1               # 0 * G = infinity
+    rng = np.random.default_rng(3)
+    pts = C.g1_sequence(5, 300).reshape(-1)
+    sc = H.random_scalars_np(rng, 300)
+    off = np.array([0, 40, 40, 100, 300], dtype=np.uint64)
+    out = C.msm_many(pts, sc, off)
+    for m in range(4):
+        lo, hi = int(off[m]), int(off[m + 1])
+        assert np.array_equal(C.g1_to_affine(out[m]), C.g1_to_affine(C.msm(pts[lo * 104:hi * 104], sc[lo:hi])))
+
+
+def test_ntt_precomputation_is_cached_and_consistent():
+    """the oracle keeps snarkVM's FFTPrecomputation per domain; repeated calls, both directions and the coset variants
+    still agree with the big-int DFT"""
+    rng = O.SplitMix64(17)
+    x = O.random_fr(rng, 64)
+    d = O.EvaluationDomain(64)
+    a = H.fr_mont_array(x)
+    for _ in range(2):
+        assert H.fr_from_mont_array(C.ntt(a, 6)) == d.fft(x)
+        assert H.fr_from_mont_array(C.ntt(a, 6, direction=1)) == d.ifft(x)
+        assert H.fr_from_mont_array(C.ntt(a, 6, coset=1)) == d.coset_fft(x)
+        assert H.fr_from_mont_array(C.ntt(a, 6, direction=1, coset=1)) == d.coset_ifft(x)
