@@ -40,6 +40,109 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const NttPa
     ntt_phase_store(p, sm, tile, batch, tid, nt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy (TMA) variant: persistent CTAs, two tile buffers, cp.async.bulk (UBLKCP) loads of tile i + 1 completing on
+// an mbarrier while tile i is being transformed (option ntt_variant = 1; phases in ntt_core.cuh).
+// ---------------------------------------------------------------------------------------------
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// generic-proxy accesses to a buffer ordered before the async-proxy (bulk copy) writes that reuse it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}   // namespace tma
+
+#define NTT_BULK_HEADER_U4 8u          // 128 bytes: the two mbarriers
+#ifndef NTT_BULK_MIN_CTAS
+#define NTT_BULK_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, NTT_BULK_MIN_CTAS) ntt_pass_bulk_kernel(const NttPassParams p, uint32_t tiles_per_poly,
+                                                                               uint32_t total_tiles) {
+    extern __shared__ __align__(128) uint4 sm[];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const NttGeom g = ntt_geom(p);
+    const uint32_t L = g.log_len;
+    const uint32_t buf_elems = ntt_bulk_tile_elems(L, g.log_cw, g.last);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
+    uint4* sm_tw = sm + NTT_BULK_HEADER_U4;
+    uint4* bufs = sm_tw + ((size_t)1 << L);
+    if (tid == 0) {
+        tma::mbar_init(&bars[0], 1);
+        tma::mbar_init(&bars[1], 1);
+        tma::fence_barrier_init();
+    }
+    ntt_phase_stage_twiddles(p, sm_tw, tid, nt);
+    const NttTwiddles twd = ntt_shared_twiddles(sm_tw, L);
+    __syncthreads();
+    const uint32_t nruns = ntt_bulk_runs(p);
+    const uint32_t tile_bytes = g.tile_elems * 32u;
+    auto issue = [&](uint32_t gtile, uint32_t b) {
+        const uint32_t tile = gtile % tiles_per_poly, batch = gtile / tiles_per_poly;
+        const uint4* src = p.src + 2ull * batch * p.batch_stride;
+        uint4* dstb = bufs + (size_t)b * 2 * buf_elems;
+        if (tid == 0) tma::mbar_expect_tx(&bars[b], tile_bytes);
+        for (uint32_t r = tid; r < nruns; r += nt) {
+            unsigned long long se;
+            uint32_t de, cnt;
+            ntt_bulk_run(p, tile, r, se, de, cnt);
+            tma::bulk_g2s(dstb + 2 * (size_t)de, src + 2 * se, cnt * 32u, &bars[b]);
+        }
+    };
+    uint32_t it = 0;
+    if (blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+    for (uint32_t gt = blockIdx.x; gt < total_tiles; gt += gridDim.x, it++) {
+        const uint32_t b = it & 1u;
+        if (gt + gridDim.x < total_tiles) issue(gt + gridDim.x, b ^ 1u);       // next tile lands while this one is transformed
+        tma::mbar_wait(&bars[b], (it >> 1) & 1u);
+        const uint32_t tile = gt % tiles_per_poly, batch = gt / tiles_per_poly;
+        NttBulkTile T;
+        T.sm = bufs + (size_t)b * 2 * buf_elems;
+        T.last = g.last;
+        T.log_len = L;
+        T.log_cw = g.log_cw;
+        T.h = (tid >> 2) & 1u;
+        if (p.coset_pre) {
+            ntt_bulk_coset_pre(p, T, tile, tid, nt);
+            __syncthreads();
+        }
+        uint32_t s = 0;
+        for (; p.radix4 && s + 1 < L; s += 2) {
+            ntt_bulk_stage2(p, T, twd, s, tid, nt);
+            __syncthreads();
+        }
+        for (; s < L; s++) {
+            ntt_bulk_stage(p, T, twd, s, tid, nt);
+            __syncthreads();
+        }
+        ntt_bulk_store_out(p, T, tile, batch, tid, nt);
+        tma::fence_proxy_async();
+        __syncthreads();                         // buffer b is free for the bulk copies of iteration it + 1
+    }
+}
+
 // out[i] = (base^(2^nsq))^(i << shift)
 __global__ void ntt_pow_table_kernel(uint4* out, fr_t base, uint32_t nsq, uint32_t count, uint32_t shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,6 +221,7 @@ struct NttState {
     uint4* tile_tw[2] = {nullptr, nullptr};
     std::map<uint32_t, NttDomainTables> domains;     // key = log_n * 2 + direction
     bool smem_attr_set = false;
+    int sm_count = 148;
 };
 static NttState g_ntt;
 
@@ -148,6 +252,13 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         // different L1 / shared splits do not share an SM, which serialises the two streams of the overlapped
         // multi-GPU schedule (measured: NTT 4.01 ms + exchange 0.38 ms = 4.39 ms "concurrently")
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        {
+            int dev = 0;
+            CUDA_TRY(cudaGetDevice(&dev));
+            CUDA_TRY(cudaDeviceGetAttribute(&g_ntt.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        }
         CUDA_TRY(cudaFuncSetAttribute(ntt_exchange_transpose_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         g_ntt.smem_attr_set = true;
     }
@@ -455,7 +566,23 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         if (threads < 32) threads = 32;
         static const char* const kPassName[NTT_MAX_PASSES] = {"ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"};
         STAGE(kPassName[i], stream);
-        dim3 grid(1u << (log_n - tile_log), (unsigned)batch);
+        const uint32_t tiles_per_poly = 1u << (log_n - tile_log);
+        const unsigned long long total_tiles = (unsigned long long)tiles_per_poly * batch;
+        if (b200_config().ntt_variant == 1 && threads == 256 && total_tiles < (1ull << 31)) {
+            // bulk-copy (TMA) variant: persistent CTAs over all tiles of the batch, two tile buffers
+            const uint32_t buf_elems = ntt_bulk_tile_elems(plan.log_len[i], plan.log_cw[i], last ? 1u : 0u);
+            const size_t smem = NTT_BULK_HEADER_U4 * 16 + ((size_t)1 << plan.log_len[i]) * 16 + 2 * (size_t)buf_elems * 32;
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ntt_pass_bulk_kernel, 256, smem));
+            if (per_sm >= 1) {
+                unsigned long long ctas = (unsigned long long)g_ntt.sm_count * per_sm;
+                if (ctas > total_tiles) ctas = total_tiles;
+                ntt_pass_bulk_kernel<<<(unsigned)ctas, 256, smem, stream>>>(p, tiles_per_poly, (uint32_t)total_tiles);
+                KERNEL_CHECK();
+                continue;
+            }
+        }
+        dim3 grid(tiles_per_poly, (unsigned)batch);
         const size_t smem = (size_t)tile_elems * 32 + ((size_t)1 << plan.log_len[i]) * 16;   // tile + L/2 twiddles
         ntt_pass_kernel<<<grid, threads, smem, stream>>>(p);
         KERNEL_CHECK();

@@ -140,11 +140,35 @@ B200_HD void ntt_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, ui
     NttGeom g = ntt_geom(p);
     const uint4* src = p.src + 2ull * batch * p.batch_stride;
     uint32_t total = 2u * g.tile_elems;                 // 16-byte words
-    for (uint32_t u = tid; u < total; u += nthreads) {
+    // Batches of NTT_LOAD_BATCH independent global loads before their shared-memory stores: the trip count is a run-time
+    // value, so the compiler keeps ONE load in flight per thread otherwise and the phase pays the global latency once per
+    // word (ncu r02: STS.128 behind the LDG carried 8 % of all stall samples, all of them long scoreboard).
+#ifndef NTT_LOAD_BATCH
+#define NTT_LOAD_BATCH 8
+#endif
+    uint32_t u = tid;
+    for (; u + (NTT_LOAD_BATCH - 1) * nthreads < total; u += NTT_LOAD_BATCH * nthreads) {
+        uint4 v[NTT_LOAD_BATCH];
+        uint32_t dst[NTT_LOAD_BATCH];
+        B200_UNROLL
+        for (int k = 0; k < NTT_LOAD_BATCH; k++) {
+            const uint32_t uu = u + k * nthreads;
+            uint32_t half = uu & 1u, e = uu >> 1;
+            uint32_t t, cw;
+            if (!g.last) { cw = e & ((1u << g.log_cw) - 1); t = e >> g.log_cw; }      // cw fastest in memory
+            else         { t = e & ((1u << g.log_len) - 1); cw = e >> g.log_len; }    // t fastest in memory
+            unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
+            v[k] = src[2 * idx + half];
+            dst[k] = half * g.tile_elems + ((t << g.log_cw) + cw);
+        }
+        B200_UNROLL
+        for (int k = 0; k < NTT_LOAD_BATCH; k++) sm[dst[k]] = v[k];
+    }
+    for (; u < total; u += nthreads) {
         uint32_t half = u & 1u, e = u >> 1;
         uint32_t t, cw;
-        if (!g.last) { cw = e & ((1u << g.log_cw) - 1); t = e >> g.log_cw; }      // cw fastest in memory
-        else         { t = e & ((1u << g.log_len) - 1); cw = e >> g.log_len; }    // t fastest in memory
+        if (!g.last) { cw = e & ((1u << g.log_cw) - 1); t = e >> g.log_cw; }
+        else         { t = e & ((1u << g.log_len) - 1); cw = e >> g.log_len; }
         unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
         sm[half * g.tile_elems + ((t << g.log_cw) + cw)] = src[2 * idx + half];
     }
@@ -287,55 +311,257 @@ B200_HD void ntt_phase_stage2(const NttPassParams& p, uint4* sm, const NttTwiddl
 // ---------------------------------------------------------------------------------------------
 // phase 3: shared -> global with the bit reversal undone, inter-pass twiddle / final scaling
 // ---------------------------------------------------------------------------------------------
+// one element of the store phase; tw = its boundary twiddle when the caller has already fetched it (have_tw)
+// tile position (t, cw) that holds output (k, cw) of the pass: DIF leaves output k at the bit-reversed row
+B200_HD void ntt_store_source(const NttGeom& g, uint32_t e, uint32_t& t, uint32_t& cw) {
+    cw = e & ((1u << g.log_cw) - 1);
+    t = bitrev32(e >> g.log_cw, g.log_len);
+}
+B200_HD void ntt_store_element(const NttPassParams& p, const NttGeom& g, fr_t x, uint4* dst, uint32_t tile, uint32_t e,
+                               bool have_tw, const fr_t& tw) {
+    uint32_t cw = e & ((1u << g.log_cw) - 1), k = e >> g.log_cw;          // k = output index of this pass
+    unsigned long long out;
+    if (!g.last) {
+        uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
+        unsigned long long sub = tile >> log_tiles_per_sub;
+        unsigned long long m = ((unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw) + cw;
+        out = (sub << g.log_sub) + ((unsigned long long)k << g.log_stride) + m;
+        // twiddle w_{M}^(m*k): one product from the per-pass table when it exists (same offset as the output
+        // inside its sub-problem), else w_N^((m*k mod M) << (log_n - log_sub)) from the two-level tables
+        if (p.boundary_tw) {
+            if (m && k) x = fp_mul(x, have_tw ? tw : fr_load(p.boundary_tw, ((unsigned long long)k << g.log_stride) + m));
+        } else {
+            unsigned long long ex = ((m * k) & ((1ull << g.log_sub) - 1)) << (p.log_n - g.log_sub);
+            if (ex) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, ex));
+        }
+    } else if (p.npasses == 1) {
+        out = k;
+    } else {
+        // digit reversal of the row index: row = (k0, k1, .., k_{last-1}) -> k0 + L0*k1 + ...
+        uint32_t log_rows = p.log_n - g.log_len;
+        uint32_t l0 = p.log_len[0];
+        uint32_t log_k0_tiles = l0 - g.log_cw;
+        unsigned long long k0 = ((unsigned long long)(tile & ((1u << log_k0_tiles) - 1)) << g.log_cw) + cw;
+        unsigned long long rest = tile >> log_k0_tiles;            // digits k1 .. k_{last-1}, k1 most significant
+        unsigned long long acc = k0;
+        uint32_t shift = l0;
+        uint32_t rem_bits = log_rows - l0;
+        for (uint32_t i = 1; i + 1 < p.npasses; i++) {
+            rem_bits -= p.log_len[i];
+            unsigned long long digit = (rest >> rem_bits) & ((1ull << p.log_len[i]) - 1);
+            acc += digit << shift;
+            shift += p.log_len[i];
+        }
+        out = acc + ((unsigned long long)k << log_rows);
+    }
+    if (g.last) {
+        if (p.scale_post) x = fp_mul(x, p.size_inv);
+        if (p.coset_post) x = fp_mul(x, pow2level(p.coset_lo, p.coset_hi, out));
+    }
+    uint4 lo, hi;
+    fr_to_u4(x, lo, hi);
+    dst[2 * out] = lo;                             // (one 256-bit store per element: no measurable difference, L2 merges the halves)
+    dst[2 * out + 1] = hi;
+}
+
 B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
                              uint32_t nthreads) {
     NttGeom g = ntt_geom(p);
     uint4* dst = p.dst + 2ull * batch * p.batch_stride;
+    uint32_t e = tid;
+    if (!g.last && p.boundary_tw) {
+        // the boundary twiddles of NTT_STORE_BATCH elements are fetched together, ahead of the products that use them
+        // (ncu r02: the first IMAD behind the one-at-a-time twiddle load carried 7 % of all stall samples)
+#ifndef NTT_STORE_BATCH
+#define NTT_STORE_BATCH 4
+#endif
+        const uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
+        const unsigned long long m0 = (unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw;
+        for (; e + (NTT_STORE_BATCH - 1) * nthreads < g.tile_elems; e += NTT_STORE_BATCH * nthreads) {
+            fr_t tw[NTT_STORE_BATCH];
+            B200_UNROLL
+            for (int q = 0; q < NTT_STORE_BATCH; q++) {
+                const uint32_t ee = e + q * nthreads;
+                const uint32_t cw = ee & ((1u << g.log_cw) - 1), k = ee >> g.log_cw;
+                tw[q] = fr_load(p.boundary_tw, ((unsigned long long)k << g.log_stride) + m0 + cw);
+            }
+            B200_UNROLL
+            for (int q = 0; q < NTT_STORE_BATCH; q++) {
+                uint32_t t, cw;
+                ntt_store_source(g, e + q * nthreads, t, cw);
+                ntt_store_element(p, g, tile_load(sm, g.tile_elems, (t << g.log_cw) + cw), dst, tile, e + q * nthreads, true, tw[q]);
+            }
+        }
+    }
+    const fr_t none = fp_zero<FrP>();
+    for (; e < g.tile_elems; e += nthreads) {
+        uint32_t t, cw;
+        ntt_store_source(g, e, t, cw);
+        ntt_store_element(p, g, tile_load(sm, g.tile_elems, (t << g.log_cw) + cw), dst, tile, e, false, none);
+    }
+}
+
+// =============================================================================================
+// Bulk-copy (TMA) variant of a pass: the tile arrives in shared memory through cp.async.bulk (SASS UBLKCP) -- one
+// asynchronous copy per contiguous global run, completion counted on an mbarrier -- so the load of tile i + 1 runs under
+// the butterflies of tile i (ntt_pass_bulk_kernel in ntt.cu: persistent CTAs, two tile buffers).  A bulk copy lands
+// bytes exactly as they lie in global memory, so the tile is INTERLEAVED here (element i = chunks 2i, 2i + 1 of 16 B)
+// instead of the two planes of the default kernel:
+//     strided pass: run t = the CW adjacent columns of row t          -> element (t, cw) at  t * CW + cw
+//     last pass   : run cw = the whole contiguous sub-problem of k0 row cw (2^L elements) -> element (t, cw) at
+//                   cw * (2^L + 1) + t   (one element of padding per run: lanes that differ in cw then fall on
+//                   different banks exactly like consecutive elements do)
+// Bank conflicts of the interleaved layout (a quarter-warp reading the low halves of 8 consecutive elements spans
+// 256 B: 2-way) are avoided by letting lanes 4..7 of every quarter-warp touch the HIGH half first (h = (lane >> 2) & 1)
+// and swapping in registers: each 128-bit access of a quarter-warp then covers 8 distinct 16-byte bank groups -- the
+// software form of the 32-byte TMA swizzle.
+// The arithmetic (stages, twiddles, boundary products, digit reversal) is the same as above, element for element.
+// =============================================================================================
+struct NttBulkTile {
+    uint4* sm;
+    uint32_t last, log_len, log_cw;
+    uint32_t h;                    // 0 / 1: which half this lane loads / stores first (any value gives the same result)
+};
+B200_HOSTDEV uint32_t ntt_bulk_tile_elems(uint32_t log_len, uint32_t log_cw, uint32_t last) {
+    return last ? (((1u << log_len) + 1u) << log_cw) : (1u << (log_len + log_cw));
+}
+B200_HD uint32_t bulk_idx(const NttBulkTile& T, uint32_t t, uint32_t cw) {
+    return T.last ? cw * ((1u << T.log_len) + 1u) + t : (t << T.log_cw) + cw;
+}
+B200_HD fr_t bulk_load(const NttBulkTile& T, uint32_t i) {
+    const uint4 a = T.sm[2 * i + T.h], b = T.sm[2 * i + (T.h ^ 1u)];
+    return T.h ? fr_from_u4(b, a) : fr_from_u4(a, b);
+}
+B200_HD void bulk_store(const NttBulkTile& T, uint32_t i, const fr_t& x) {
+    uint4 lo, hi;
+    fr_to_u4(x, lo, hi);
+    T.sm[2 * i + T.h] = T.h ? hi : lo;
+    T.sm[2 * i + (T.h ^ 1u)] = T.h ? lo : hi;
+}
+
+// The contiguous global runs of one tile: run r (r < ntt_bulk_runs) starts at element `src_elem` of the polynomial, is
+// `elems` long and lands at element `dst_elem` of the tile.
+B200_HD uint32_t ntt_bulk_runs(const NttPassParams& p) {
+    const NttGeom g = ntt_geom(p);
+    return g.last ? (1u << g.log_cw) : (1u << g.log_len);
+}
+B200_HD void ntt_bulk_run(const NttPassParams& p, uint32_t tile, uint32_t r, unsigned long long& src_elem,
+                          uint32_t& dst_elem, uint32_t& elems) {
+    const NttGeom g = ntt_geom(p);
+    if (!g.last) {
+        src_elem = ntt_in_index(p, g, tile, r, 0);
+        dst_elem = r << g.log_cw;
+        elems = 1u << g.log_cw;
+    } else {
+        src_elem = ntt_in_index(p, g, tile, 0, r);
+        dst_elem = r * ((1u << g.log_len) + 1u);
+        elems = 1u << g.log_len;
+    }
+}
+
+B200_HD void ntt_bulk_coset_pre(const NttPassParams& p, const NttBulkTile& T, uint32_t tile, uint32_t tid, uint32_t nthreads) {
+    const NttGeom g = ntt_geom(p);
     for (uint32_t e = tid; e < g.tile_elems; e += nthreads) {
-        uint32_t cw = e & ((1u << g.log_cw) - 1), k = e >> g.log_cw;          // k = output index of this pass
-        uint32_t t = bitrev32(k, g.log_len);                                   // where DIF left it
-        fr_t x = tile_load(sm, g.tile_elems, (t << g.log_cw) + cw);
-        unsigned long long out;
-        if (!g.last) {
-            uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
-            unsigned long long sub = tile >> log_tiles_per_sub;
-            unsigned long long m = ((unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw) + cw;
-            out = (sub << g.log_sub) + ((unsigned long long)k << g.log_stride) + m;
-            // twiddle w_{M}^(m*k): one product from the per-pass table when it exists (same offset as the output
-            // inside its sub-problem), else w_N^((m*k mod M) << (log_n - log_sub)) from the two-level tables
-            if (p.boundary_tw) {
-                if (m && k) x = fp_mul(x, fr_load(p.boundary_tw, ((unsigned long long)k << g.log_stride) + m));
-            } else {
-                unsigned long long ex = ((m * k) & ((1ull << g.log_sub) - 1)) << (p.log_n - g.log_sub);
-                if (ex) x = fp_mul(x, pow2level(p.pow_lo, p.pow_hi, ex));
-            }
-        } else if (p.npasses == 1) {
-            out = k;
-        } else {
-            // digit reversal of the row index: row = (k0, k1, .., k_{last-1}) -> k0 + L0*k1 + ...
-            uint32_t log_rows = p.log_n - g.log_len;
-            uint32_t l0 = p.log_len[0];
-            uint32_t log_k0_tiles = l0 - g.log_cw;
-            unsigned long long k0 = ((unsigned long long)(tile & ((1u << log_k0_tiles) - 1)) << g.log_cw) + cw;
-            unsigned long long rest = tile >> log_k0_tiles;            // digits k1 .. k_{last-1}, k1 most significant
-            unsigned long long acc = k0;
-            uint32_t shift = l0;
-            uint32_t rem_bits = log_rows - l0;
-            for (uint32_t i = 1; i + 1 < p.npasses; i++) {
-                rem_bits -= p.log_len[i];
-                unsigned long long digit = (rest >> rem_bits) & ((1ull << p.log_len[i]) - 1);
-                acc += digit << shift;
-                shift += p.log_len[i];
-            }
-            out = acc + ((unsigned long long)k << log_rows);
+        const uint32_t cw = e & ((1u << g.log_cw) - 1), t = e >> g.log_cw;
+        const unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
+        const uint32_t i = bulk_idx(T, t, cw);
+        fr_t x = bulk_load(T, i);
+        x = fp_mul(x, pow2level(p.coset_lo, p.coset_hi, idx));
+        bulk_store(T, i, x);
+    }
+}
+
+B200_HD void ntt_bulk_stage(const NttPassParams& p, const NttBulkTile& T, const NttTwiddles& twd, uint32_t s, uint32_t tid,
+                            uint32_t nthreads) {
+    const NttGeom g = ntt_geom(p);
+    const uint32_t log_d = g.log_len - 1 - s;
+    const uint32_t nbf = g.tile_elems >> 1;
+    const bool j_major = log_d <= 2;
+    const uint32_t log_blocks = g.log_len - 1 - log_d;
+    for (uint32_t u = tid; u < nbf; u += nthreads) {
+        const uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
+        uint32_t j, b;
+        if (j_major) { b = q & ((1u << log_blocks) - 1); j = q >> log_blocks; }
+        else         { j = q & ((1u << log_d) - 1); b = q >> log_d; }
+        const uint32_t t0 = (b << (log_d + 1)) | j;
+        const uint32_t i0 = bulk_idx(T, t0, cw), i1 = bulk_idx(T, t0 + (1u << log_d), cw);
+        const fr_t a = bulk_load(T, i0), bb = bulk_load(T, i1);
+        const fr_t sum = fp_add(a, bb);
+        fr_t dif = fp_sub(a, bb);
+        const uint32_t tw = j << s;
+        if (tw) dif = fp_mul(dif, ntt_twiddle(twd, tw));
+        bulk_store(T, i0, sum);
+        bulk_store(T, i1, dif);
+    }
+}
+
+B200_HD void ntt_bulk_stage2(const NttPassParams& p, const NttBulkTile& T, const NttTwiddles& twd, uint32_t s, uint32_t tid,
+                             uint32_t nthreads) {
+    const NttGeom g = ntt_geom(p);
+    const uint32_t log_d1 = g.log_len - 1 - s, log_d2 = log_d1 - 1;
+    const uint32_t nquads = g.tile_elems >> 2;
+    const bool j_major = log_d2 <= 2;
+    const uint32_t log_blocks = g.log_len - 1 - log_d1;
+    for (uint32_t u = tid; u < nquads; u += nthreads) {
+        const uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
+        uint32_t j, b;
+        if (j_major) { b = q & ((1u << log_blocks) - 1); j = q >> log_blocks; }
+        else         { j = q & ((1u << log_d2) - 1); b = q >> log_d2; }
+        const uint32_t t0 = (b << (log_d1 + 1)) | j;
+        const uint32_t d2 = 1u << log_d2, d1 = d2 << 1;
+        const uint32_t i0 = bulk_idx(T, t0, cw), i1 = bulk_idx(T, t0 + d2, cw), i2 = bulk_idx(T, t0 + d1, cw),
+                       i3 = bulk_idx(T, t0 + d1 + d2, cw);
+        const fr_t x0 = bulk_load(T, i0), x1 = bulk_load(T, i1), x2 = bulk_load(T, i2), x3 = bulk_load(T, i3);
+        fr_t a0 = fp_add(x0, x2), a2 = fp_sub(x0, x2);
+        fr_t a1 = fp_add(x1, x3), a3 = fp_sub(x1, x3);
+        const uint32_t twa = j << s;
+        const uint32_t twb = (j + d2) << s;
+        if (twa) a2 = fp_mul(a2, ntt_twiddle(twd, twa));
+        a3 = fp_mul(a3, ntt_twiddle(twd, twb));
+        const uint32_t tw2 = j << (s + 1);
+        fr_t y0 = fp_add(a0, a1), y1 = fp_sub(a0, a1);
+        fr_t y2 = fp_add(a2, a3), y3 = fp_sub(a2, a3);
+        if (tw2) {
+            const fr_t w2 = ntt_twiddle(twd, tw2);
+            y1 = fp_mul(y1, w2);
+            y3 = fp_mul(y3, w2);
         }
-        if (g.last) {
-            if (p.scale_post) x = fp_mul(x, p.size_inv);
-            if (p.coset_post) x = fp_mul(x, pow2level(p.coset_lo, p.coset_hi, out));
+        bulk_store(T, i0, y0);
+        bulk_store(T, i1, y1);
+        bulk_store(T, i2, y2);
+        bulk_store(T, i3, y3);
+    }
+}
+
+// shared -> global: same addresses, twiddles and scalings as ntt_phase_store
+B200_HD void ntt_bulk_store_out(const NttPassParams& p, const NttBulkTile& T, uint32_t tile, uint32_t batch, uint32_t tid,
+                                uint32_t nthreads) {
+    const NttGeom g = ntt_geom(p);
+    uint4* dst = p.dst + 2ull * batch * p.batch_stride;
+    uint32_t e = tid;
+    if (!g.last && p.boundary_tw) {
+        const uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
+        const unsigned long long m0 = (unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw;
+        for (; e + (NTT_STORE_BATCH - 1) * nthreads < g.tile_elems; e += NTT_STORE_BATCH * nthreads) {
+            fr_t tw[NTT_STORE_BATCH];
+            B200_UNROLL
+            for (int q = 0; q < NTT_STORE_BATCH; q++) {
+                const uint32_t ee = e + q * nthreads;
+                const uint32_t cw = ee & ((1u << g.log_cw) - 1), k = ee >> g.log_cw;
+                tw[q] = fr_load(p.boundary_tw, ((unsigned long long)k << g.log_stride) + m0 + cw);
+            }
+            B200_UNROLL
+            for (int q = 0; q < NTT_STORE_BATCH; q++) {
+                uint32_t t, cw;
+                ntt_store_source(g, e + q * nthreads, t, cw);
+                ntt_store_element(p, g, bulk_load(T, bulk_idx(T, t, cw)), dst, tile, e + q * nthreads, true, tw[q]);
+            }
         }
-        uint4 lo, hi;
-        fr_to_u4(x, lo, hi);
-        dst[2 * out] = lo;                             // (one 256-bit store per element: no measurable difference, L2 merges the halves)
-        dst[2 * out + 1] = hi;
+    }
+    const fr_t none = fp_zero<FrP>();
+    for (; e < g.tile_elems; e += nthreads) {
+        uint32_t t, cw;
+        ntt_store_source(g, e, t, cw);
+        ntt_store_element(p, g, bulk_load(T, bulk_idx(T, t, cw)), dst, tile, e, false, none);
     }
 }

@@ -36,9 +36,19 @@ extern "C" int host_ntt_plan(uint32_t log_n, uint32_t* npasses, uint32_t* log_le
 
 // data: batch polynomials of 2^log_n Montgomery Fr (8 x u32 each), stride in elements.  `nthreads` emulated
 // threads per CTA.  plan_len/plan_cw: explicit plan (npasses entries) or npasses = 0 to use ntt_make_plan.
+// variant 0: the default kernel's phases (planar tile, per-thread loads); 1: the bulk-copy (TMA) variant's phases
+// (interleaved tile filled run by run, as cp.async.bulk does; lanes 4..7 of a quarter-warp touch the high half first).
+extern "C" int host_ntt_variant(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t stride, int direction, int coset,
+                                uint32_t npasses, const uint32_t* plan_len, const uint32_t* plan_cw, uint32_t nthreads,
+                                int use_tables, int variant);
 extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t stride, int direction, int coset,
                         uint32_t npasses, const uint32_t* plan_len, const uint32_t* plan_cw, uint32_t nthreads,
                         int use_tables) {
+    return host_ntt_variant(data, log_n, batch, stride, direction, coset, npasses, plan_len, plan_cw, nthreads, use_tables, 0);
+}
+extern "C" int host_ntt_variant(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t stride, int direction, int coset,
+                                uint32_t npasses, const uint32_t* plan_len, const uint32_t* plan_cw, uint32_t nthreads,
+                                int use_tables, int variant) {
     if (log_n == 0) return 0;
     NttPlan plan;
     if (npasses == 0) {
@@ -108,9 +118,35 @@ extern "C" int host_ntt(uint32_t* data, uint32_t log_n, uint32_t batch, uint64_t
         // a single-pass transform reads and writes the same buffer: like on the GPU, every tile is fully
         // loaded into "shared memory" before it is stored, and tiles of one pass touch disjoint outputs
         // only when src != dst or npasses == 1 (one tile).
-        std::vector<uint4> sm(2 * (size_t)tile_elems);
+        std::vector<uint4> sm(2 * (size_t)ntt_bulk_tile_elems(plan.log_len[i], plan.log_cw[i], last ? 1u : 0u));
         for (uint32_t b = 0; b < batch; b++)
             for (uint32_t tile = 0; tile < ntiles; tile++) {
+                if (variant == 1) {
+                    const uint4* srcp = p.src + 2ull * b * p.batch_stride;
+                    for (uint32_t r = 0; r < ntt_bulk_runs(p); r++) {              // what the bulk copies do
+                        unsigned long long se; uint32_t de, cnt;
+                        ntt_bulk_run(p, tile, r, se, de, cnt);
+                        memcpy(sm.data() + 2 * (size_t)de, srcp + 2 * se, (size_t)cnt * 32);
+                    }
+                    std::vector<uint4> smtw((size_t)1 << plan.log_len[i]);
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage_twiddles(p, smtw.data(), tid, nthreads);
+                    const NttTwiddles twd = ntt_shared_twiddles(smtw.data(), plan.log_len[i]);
+                    auto view = [&](uint32_t tid) {
+                        NttBulkTile T;
+                        T.sm = sm.data(); T.last = last ? 1u : 0u; T.log_len = plan.log_len[i]; T.log_cw = plan.log_cw[i];
+                        T.h = (tid >> 2) & 1u;
+                        return T;
+                    };
+                    if (p.coset_pre)
+                        for (uint32_t tid = 0; tid < nthreads; tid++) ntt_bulk_coset_pre(p, view(tid), tile, tid, nthreads);
+                    uint32_t s = 0;
+                    for (; p.radix4 && s + 1 < plan.log_len[i]; s += 2)
+                        for (uint32_t tid = 0; tid < nthreads; tid++) ntt_bulk_stage2(p, view(tid), twd, s, tid, nthreads);
+                    for (; s < plan.log_len[i]; s++)
+                        for (uint32_t tid = 0; tid < nthreads; tid++) ntt_bulk_stage(p, view(tid), twd, s, tid, nthreads);
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_bulk_store_out(p, view(tid), tile, b, tid, nthreads);
+                    continue;
+                }
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);
                 if (p.coset_pre)
                     for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, nthreads);

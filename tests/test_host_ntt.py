@@ -26,13 +26,13 @@ def hostlib():
     return ctypes.CDLL(so)
 
 
-def run(lib, data, log_n, batch, stride, direction, coset, lens=(), cws=(), nthreads=8, use_tables=1):
+def run(lib, data, log_n, batch, stride, direction, coset, lens=(), cws=(), nthreads=8, use_tables=1, variant=0):
     buf = np.ascontiguousarray(data, dtype=np.uint64).copy()
     L = (ctypes.c_uint32 * 4)(*(list(lens) + [0] * (4 - len(lens))))
     W = (ctypes.c_uint32 * 4)(*(list(cws) + [0] * (4 - len(cws))))
-    rc = lib.host_ntt(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(log_n), ctypes.c_uint32(batch),
-                      ctypes.c_uint64(stride), ctypes.c_int(direction), ctypes.c_int(coset), ctypes.c_uint32(len(lens)),
-                      L, W, ctypes.c_uint32(nthreads), ctypes.c_int(use_tables))
+    rc = lib.host_ntt_variant(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(log_n), ctypes.c_uint32(batch),
+                              ctypes.c_uint64(stride), ctypes.c_int(direction), ctypes.c_int(coset), ctypes.c_uint32(len(lens)),
+                              L, W, ctypes.c_uint32(nthreads), ctypes.c_int(use_tables), ctypes.c_int(variant))
     assert rc == 0
     return buf
 
@@ -60,6 +60,9 @@ def test_pass_decomposition_matches_oracle(hostlib, log_n, lens, cws, direction,
     for b in range(batch):
         want[b * stride:b * stride + n] = C.ntt(data[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
     assert np.array_equal(got, want)          # includes: padding between polynomials untouched
+    # bulk-copy (TMA) variant: interleaved tile filled run by run, padded last-pass layout, half-swapped accesses
+    got3 = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=6, variant=1)
+    assert np.array_equal(got3, want)
 
 
 @pytest.mark.parametrize("log_n", [4, 10, 12, 13, 14])
