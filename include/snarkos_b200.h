@@ -136,6 +136,26 @@ b200_error_t b200_kzg_commit(void* out_jacobian_144B, uint64_t handle, const voi
 b200_error_t b200_kzg_commit_device(void* d_out_jacobian_144B, uint64_t handle, const void* d_coeffs_mont,
                                     size_t ncoeffs, void* stream);
 
+/* k commitments against ONE resident set in one launch set (a Varuna round commits its polynomials together:
+ * SonicKZG10::commit over a slice of labeled polynomials [UPSTREAM algorithms/src/polycommit/sonic_pc/mod.rs]).
+ * Polynomial m = coeffs[offsets[m] .. offsets[m + 1]) (Montgomery Fr, concatenated; offsets[0] = 0, k + 1 entries, a HOST
+ * array in both forms) multiplies powers 0 .. len_m - 1.  out receives k Jacobian points. */
+b200_error_t b200_kzg_commit_batch(void* out_jacobian, uint64_t handle, const void* coeffs_32B_mont,
+                                   const uint64_t* offsets, size_t k);
+b200_error_t b200_kzg_commit_batch_device(void* d_out_jacobian, uint64_t handle, const void* d_coeffs_mont,
+                                          const uint64_t* offsets_host, size_t k, void* stream);
+
+/* KZG10::open [UPSTREAM algorithms/src/polycommit/kzg10/mod.rs: open -> compute_witness_polynomial ->
+ * open_with_witness_polynomial]: out = commitment to the witness polynomial (p(X) - p(z)) / (X - z) against the
+ * resident powers, *out_eval = p(z) (may be NULL).  Montgomery Fr coefficients and point.  The hiding part of
+ * snarkVM's open is the same call on the blinding polynomial against powers_of_beta_times_gamma_g (its evaluation is
+ * random_v), added by the caller.  SonicKZG10::open_combinations first forms ONE polynomial with
+ * b200_fr_linear_combination_device. */
+b200_error_t b200_kzg_open(void* out_jacobian_144B, uint64_t handle, const void* coeffs_32B_mont, size_t ncoeffs,
+                           const void* point_32B_mont, void* out_eval_32B_mont);
+b200_error_t b200_kzg_open_device(void* d_out_jacobian_144B, uint64_t handle, const void* d_coeffs_mont, size_t ncoeffs,
+                                  const void* d_point_mont, void* d_out_eval_mont, void* stream);
+
 /* Window width the library would pick for `npoints` (0 = library default); B200_MSM_C overrides. */
 uint32_t b200_msm_window_bits(size_t npoints);
 /* number of batched-affine pair rounds (snarkVM batched::batch_add counterpart) a call of this size runs before the
@@ -147,6 +167,19 @@ void b200_msm_describe(size_t npoints, uint32_t* out4);
 /* Sum of `count` Jacobian points (144 B each): the multi-GPU partial-sum combine.  Device pointers. */
 b200_error_t b200_g1_sum_jacobian_device(void* d_out_jacobian_144B, const void* d_in, size_t count,
                                          void* stream);
+
+/* ---- output forms of a commitment ----------------------------------------------
+ * Projective::batch_normalization + to_affine [UPSTREAM curves/src/templates/short_weierstrass_jacobian/projective.rs]:
+ * `count` Jacobian images (144 B) -> G1Affine images of `affine_stride` bytes (x, y Montgomery, infinity flag byte at
+ * 96, padding zero), one shared inversion per 16 points. */
+b200_error_t b200_g1_batch_normalize(void* out_affine, const void* in_jacobian, size_t count, size_t affine_stride);
+b200_error_t b200_g1_batch_normalize_device(void* d_out_affine, const void* d_in_jacobian, size_t count,
+                                            size_t affine_stride, void* stream);
+/* Compressed serialisation of the same points, 48 bytes each -- what `ToBytes::write_le` / `serialize_compressed` emit
+ * for a G1Affine inside a Varuna proof [UPSTREAM .../short_weierstrass_jacobian/affine.rs, utilities/src/serialize/
+ * flags.rs]: canonical x little-endian; bit 7 of byte 47 set iff y > -y; bit 6 = infinity (x = 0). */
+b200_error_t b200_g1_compress(void* out_48B, const void* in_jacobian, size_t count);
+b200_error_t b200_g1_compress_device(void* d_out_48B, const void* d_in_jacobian, size_t count, void* stream);
 
 /* ---- EvaluationDomain (i)FFT -------------------------------------------------------------------
  * In-place transform of `batch` polynomials of 2^log_n Montgomery Fr elements, natural order in and
@@ -170,6 +203,16 @@ b200_error_t b200_fr_batch_inverse_device(void* d_inout, size_t n, void* stream)
 /* evals[i] /= v_H(22 * w_K^i) for i < 2^log_k: division by the vanishing polynomial of a size-2^log_h domain on the
  * coset of a size-2^log_k domain [UPSTREAM algorithms/src/fft/domain.rs: divide_by_vanishing_poly_on_coset_in_place]. */
 b200_error_t b200_fr_divide_by_vanishing_on_coset_device(void* d_evals, uint32_t log_k, uint32_t log_h, void* stream);
+
+/* out[i] = sum_m coeffs[m] * p_m[i] for i < out_len, p_m = polys[offsets[m] .. offsets[m + 1]) (zero beyond its length):
+ * the combination by opening challenges that KZG10::open / SonicKZG10::open_combinations form before one witness
+ * division and one MSM.  offsets: HOST array of k + 1 entries; polys, coeffs (k Montgomery Fr), out: device. */
+b200_error_t b200_fr_linear_combination_device(void* d_out, const void* d_polys, const uint64_t* offsets_host, size_t k,
+                                               const void* d_coeffs_mont, size_t out_len, void* stream);
+/* Division of the degree n - 1 polynomial p by (X - z): quotient (n - 1 coefficients, must not alias p) and remainder
+ * p(z) (may be NULL) [UPSTREAM algorithms/src/fft/polynomial/dense.rs: Div by a linear divisor / evaluate]. */
+b200_error_t b200_fr_divide_by_linear_device(void* d_quotient, const void* d_poly, size_t n, const void* d_point_mont,
+                                             void* d_out_remainder, void* stream);
 
 /* Multi-GPU four-step building block: scales a block of a distributed polynomial of total size 2^log_n.
  * kind 0: element (r, c) of the row-major [rows x cols] block times w_N^((row_base + r) * (col_base + c)) -- the

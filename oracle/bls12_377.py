@@ -133,6 +133,70 @@ def jacobian_from_bytes(b: bytes) -> Optional[Tuple[int, int]]:
     return X * zi2 % P_MOD, Y * zi2 * zi % P_MOD
 
 
+def g1_compress(pt: Optional[Tuple[int, int]]) -> bytes:
+    """Compressed G1Affine (48 B), as `CanonicalSerialize::serialize_compressed` / `ToBytes::write_le` emit it inside a
+    Varuna proof [UPSTREAM curves/src/templates/short_weierstrass_jacobian/affine.rs (serialize_with_mode, Compress::Yes),
+    utilities/src/serialize/flags.rs (SWFlags)]: the canonical x coordinate little-endian in ceil((377 + 2) / 8) = 48
+    bytes with the flags OR-ed into the LAST byte -- bit 7 (PositiveY) set iff y > -y as canonical integers, bit 6
+    (Infinity) set for the point at infinity, whose x is serialised as 0.
+    RECALLED from upstream, not read from source (the dependency is not on disk): pinned only once the Rust harness
+    (rust/snarkvm-algorithms-b200/tests/parity.rs::compressed_encoding_matches_to_bytes_le) has run."""
+    if pt is None:
+        out = bytearray(48)
+        out[47] |= 1 << 6
+        return bytes(out)
+    x, y = pt
+    out = bytearray(x.to_bytes(48, "little"))
+    if y > P_MOD - y:
+        out[47] |= 1 << 7
+    return bytes(out)
+
+
+def g1_decompress(b: bytes) -> Optional[Tuple[int, int]]:
+    """inverse of g1_compress (from_x_coordinate + flag); raises on a non-canonical or off-curve encoding"""
+    assert len(b) == 48
+    flags = b[47] & 0xC0
+    x = int.from_bytes(bytes(b[:47]) + bytes([b[47] & 0x3F]), "little")
+    if flags & 0x40:
+        if flags & 0x80 or x != 0:
+            raise ValueError("invalid infinity encoding")
+        return None
+    if x >= P_MOD:
+        raise ValueError("x not reduced")
+    y2 = (x * x * x + G1_B) % P_MOD
+    y = fq_sqrt(y2)
+    if y is None:
+        raise ValueError("x is not on the curve")
+    greater = y > P_MOD - y
+    if bool(flags & 0x80) != greater:
+        y = P_MOD - y
+    return x, y
+
+
+def fq_sqrt(a: int) -> Optional[int]:
+    """square root in Fq by Tonelli-Shanks (p - 1 = 2^46 * t); None for a non-residue"""
+    a %= P_MOD
+    if a == 0:
+        return 0
+    if pow(a, (P_MOD - 1) // 2, P_MOD) != 1:
+        return None
+    s, t = 0, P_MOD - 1
+    while t % 2 == 0:
+        s, t = s + 1, t // 2
+    z = 2
+    while pow(z, (P_MOD - 1) // 2, P_MOD) != P_MOD - 1:
+        z += 1
+    m, c, u, r = s, pow(z, t, P_MOD), pow(a, t, P_MOD), pow(a, (t + 1) // 2, P_MOD)
+    while u != 1:
+        i, v = 0, u
+        while v != 1:
+            v, i = v * v % P_MOD, i + 1
+        b = pow(c, 1 << (m - i - 1), P_MOD)
+        m, c = i, b * b % P_MOD
+        u, r = u * c % P_MOD, r * b % P_MOD
+    return r
+
+
 # --------------------------------------------------------------------------------------
 # G1 arithmetic, affine chord-and-tangent on canonical ints (None = infinity)
 # --------------------------------------------------------------------------------------

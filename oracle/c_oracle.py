@@ -38,6 +38,8 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).restype = None
         L.oracle_g1_to_affine.argtypes = [vp, vp, sz, sz]
         L.oracle_g1_to_affine.restype = None
+        L.oracle_g1_compress.argtypes = [vp, vp, sz]
+        L.oracle_g1_compress.restype = None
         L.oracle_g1_mul_u64.argtypes = [vp, vp, vp, sz, sz]
         L.oracle_g1_mul_u64.restype = None
         L.oracle_g1_is_on_curve.argtypes = [vp]
@@ -142,6 +144,14 @@ def g1_to_affine(jac: np.ndarray, stride: int = 104) -> np.ndarray:
     jac = np.ascontiguousarray(jac, dtype=np.uint8).reshape(-1, 144)
     out = np.zeros((jac.shape[0], stride), dtype=np.uint8)
     lib().oracle_g1_to_affine(_p(out), _p(jac), jac.shape[0], stride)
+    return out
+
+
+def g1_compress(jac: np.ndarray) -> np.ndarray:
+    """Jacobian images [n, 144] -> compressed G1Affine encodings uint8 [n, 48] (Varuna proof wire format of a commitment)"""
+    jac = np.ascontiguousarray(jac, dtype=np.uint8).reshape(-1, 144)
+    out = np.zeros((jac.shape[0], 48), dtype=np.uint8)
+    lib().oracle_g1_compress(_p(out), _p(jac), jac.shape[0])
     return out
 
 

@@ -341,6 +341,29 @@ void oracle_g1_to_affine(uint8_t *out_affine, const uint8_t *in_jac, size_t n, s
     }
 }
 
+/* Jacobian (144 B) -> compressed G1Affine (48 B): canonical x little-endian, flags in the last byte -- bit 7 set iff
+ * y > -y (as canonical integers), bit 6 = infinity (x serialised as 0)
+ * [UPSTREAM curves/src/templates/short_weierstrass_jacobian/affine.rs serialize_with_mode(Compress::Yes);
+ *  utilities/src/serialize/flags.rs SWFlags::u8_bitmask] -- recalled, see oracle/bls12_377.py g1_compress */
+void oracle_g1_compress(uint8_t *out48, const uint8_t *in_jac, size_t n) {
+    static const u64 one_plain[6] = {1, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < n; i++) {
+        jac_t p;
+        memcpy(&p, in_jac + 144 * i, 144);
+        aff_t a;
+        jac_to_affine(&a, &p);
+        uint8_t *o = out48 + 48 * i;
+        memset(o, 0, 48);
+        if (a.inf) { o[47] |= 1u << 6; continue; }
+        u64 x[6], y[6], ny[6];
+        fq_mul(x, a.x, one_plain);                     /* out of Montgomery form */
+        fq_mul(y, a.y, one_plain);
+        fq_sub_nored(ny, FQ_MODULUS, y);                  /* p - y; y != 0 on this curve's prime-order subgroup */
+        memcpy(o, x, 48);
+        if (!fq_is_zero(y) && fq_geq(y, ny) && !fq_eq(y, ny)) o[47] |= 1u << 7;
+    }
+}
+
 /* out[i] = k[i] * base  (64-bit scalars, MSB-first double-and-add), affine out */
 void oracle_g1_mul_u64(uint8_t *out_affine, const uint8_t *base_affine, const u64 *k, size_t n,
                        size_t stride) {

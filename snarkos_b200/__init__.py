@@ -8,6 +8,6 @@ The compute lives in snarkos_b200/libsnarkos_b200.so (CUDA, C ABI in include/sna
 """
 from ._lib import B200Error, counter, init, kernel_launch_count, lib, profile, set_option  # noqa: F401
 from .fft import EvaluationDomain  # noqa: F401
-from .msm import ResidentBases, VariableBase, msm_batch, sum_projective, synthetic_bases  # noqa: F401
+from .msm import ResidentBases, VariableBase, g1_batch_normalize, g1_compress, msm_batch, sum_projective, synthetic_bases  # noqa: F401
 from .kzg10 import KZG10, Powers  # noqa: F401
 from . import dist, poly, varuna  # noqa: F401,E402

@@ -44,6 +44,16 @@ SYMBOLS = {
     "b200_msm_release_bases": (b200_error_t, [_u64]),
     "b200_kzg_commit": (b200_error_t, [_vp, _u64, _vp, _sz]),
     "b200_kzg_commit_device": (b200_error_t, [_vp, _u64, _vp, _sz, _vp]),
+    "b200_kzg_commit_batch": (b200_error_t, [_vp, _u64, _vp, ctypes.POINTER(_u64), _sz]),
+    "b200_kzg_commit_batch_device": (b200_error_t, [_vp, _u64, _vp, ctypes.POINTER(_u64), _sz, _vp]),
+    "b200_kzg_open": (b200_error_t, [_vp, _u64, _vp, _sz, _vp, _vp]),
+    "b200_kzg_open_device": (b200_error_t, [_vp, _u64, _vp, _sz, _vp, _vp, _vp]),
+    "b200_g1_batch_normalize": (b200_error_t, [_vp, _vp, _sz, _sz]),
+    "b200_g1_batch_normalize_device": (b200_error_t, [_vp, _vp, _sz, _sz, _vp]),
+    "b200_g1_compress": (b200_error_t, [_vp, _vp, _sz]),
+    "b200_g1_compress_device": (b200_error_t, [_vp, _vp, _sz, _vp]),
+    "b200_fr_linear_combination_device": (b200_error_t, [_vp, _vp, ctypes.POINTER(_u64), _sz, _vp, _sz, _vp]),
+    "b200_fr_divide_by_linear_device": (b200_error_t, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "b200_msm_window_bits": (_u32, [_sz]),
     "b200_msm_affine_rounds": (_u32, [_sz]),
     "b200_msm_describe": (None, [_sz, ctypes.POINTER(_u32)]),

@@ -17,12 +17,6 @@ std::atomic<uint64_t> g_kernel_launches{0};
 // ---------------------------------------------------------------------------------------------
 // process state
 // ---------------------------------------------------------------------------------------------
-struct RegisteredBases {
-    void* d_packed;      // n packed points; with a window table: nwin * n (window 0 first)
-    size_t n;
-    uint32_t c_tab;      // 0: plain; else the window width of the table 2^(c*w) * P_i
-    bool glv;            // plain sets: stored as 2n records (P_i, phi(P_i)) for the GLV split (msm_glv.cuh)
-};
 struct ApiState {
     std::mutex mu;
     int device = -1;
@@ -555,7 +549,7 @@ extern "C" b200_error_t b200_msm_register_bases_tabulated(const void* points, si
     return b200_msm_register_bases_tabulated_device(d_pts.p, n, stride, window_bits, s, out_handle);
 }
 
-static b200_error_t lookup_bases(uint64_t handle, RegisteredBases* out) {
+b200_error_t b200_lookup_bases(uint64_t handle, RegisteredBases* out) {
     std::lock_guard<std::mutex> lock(g_api.mu);
     auto it = g_api.bases.find(handle);
     if (it == g_api.bases.end()) return b200_err(B200_ERR_BAD_HANDLE, "unknown bases handle");
@@ -567,7 +561,7 @@ extern "C" b200_error_t b200_msm_registered_device(void* d_out, uint64_t handle,
                                                    void* stream) {
     B200_TRY(b200_require_device());
     RegisteredBases rb;
-    B200_TRY(lookup_bases(handle, &rb));
+    B200_TRY(b200_lookup_bases(handle, &rb));
     if (n > rb.n) return b200_err(B200_ERR_INVALID_ARG, "msm_registered: more scalars than registered bases");
     if (rb.c_tab) return msm_run_tabulated_device(d_out, n, d_scalars, rb.d_packed, rb.n, rb.c_tab, (cudaStream_t)stream);
     return msm_run_device(d_out, nullptr, n, d_scalars, 0, rb.d_packed, (cudaStream_t)stream, rb.glv);
@@ -609,7 +603,7 @@ extern "C" b200_error_t b200_kzg_commit_device(void* d_out, uint64_t handle, con
                                                void* stream) {
     B200_TRY(b200_require_device());
     RegisteredBases rb;
-    B200_TRY(lookup_bases(handle, &rb));
+    B200_TRY(b200_lookup_bases(handle, &rb));
     if (n > rb.n) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit: polynomial longer than the registered powers");
     if (!d_out || (n && !d_coeffs_mont)) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -633,6 +627,57 @@ extern "C" b200_error_t b200_kzg_commit(void* out, uint64_t handle, const void* 
     if (n) B200_TRY(b200_h2d(d_c.p, coeffs_mont, n * 32, s));
     B200_TRY(b200_kzg_commit_device(d_out.p, handle, d_c.p, n, s));
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, 144, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return b200_ok();
+}
+
+// k polynomials against ONE resident set in ONE launch set: the commitments of a Varuna round are made together
+// (SonicKZG10::commit over a slice of labeled polynomials [UPSTREAM algorithms/src/polycommit/sonic_pc/mod.rs]), each
+// of them a latency-bound MSM of 2^14 .. 2^17 points.  Polynomial m = coeffs[offsets[m] .. offsets[m + 1]) multiplies
+// bases 0 .. len_m - 1; every MSM gets its own bucket set ("virtual windows"), everything else is one pipeline.
+extern "C" b200_error_t b200_kzg_commit_batch_device(void* d_out, uint64_t handle, const void* d_coeffs_mont,
+                                                     const uint64_t* offsets_host, size_t k, void* stream) {
+    B200_TRY(b200_require_device());
+    RegisteredBases rb;
+    B200_TRY(b200_lookup_bases(handle, &rb));
+    if (k == 0) return b200_ok();
+    if (!d_out || !offsets_host) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: null pointer");
+    if (k > 4096) return b200_err(B200_ERR_TOO_LARGE, "kzg_commit_batch: more than 4096 polynomials per call");
+    if (offsets_host[0] != 0) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: offsets[0] must be 0");
+    for (size_t m = 0; m < k; m++) {
+        if (offsets_host[m + 1] < offsets_host[m]) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: offsets must be non-decreasing");
+        if (offsets_host[m + 1] - offsets_host[m] > rb.n) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: polynomial longer than the registered powers");
+    }
+    const size_t n = (size_t)offsets_host[k];
+    if (n && !d_coeffs_mont) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k == 1) return b200_kzg_commit_device(d_out, handle, d_coeffs_mont, n, stream);
+    DevBuf d_sc, d_off;
+    CUDA_TRY(d_sc.alloc(n * 32, s));
+    CUDA_TRY(d_off.alloc((k + 1) * 8, s));
+    CUDA_TRY(cudaMemcpyAsync(d_off.p, offsets_host, (k + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (n) {
+        fr_from_mont_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_sc.as<uint4>(), reinterpret_cast<const uint4*>(d_coeffs_mont), n);
+        KERNEL_CHECK();
+    }
+    return msm_run_batch_device(d_out, nullptr, n, d_sc.p, 0, rb.d_packed, d_off.as<unsigned long long>(), (uint32_t)k, s,
+                                rb.c_tab ? rb.n : 0, rb.c_tab, rb.glv, true);
+}
+
+extern "C" b200_error_t b200_kzg_commit_batch(void* out, uint64_t handle, const void* coeffs_mont, const uint64_t* offsets,
+                                              size_t k) {
+    B200_TRY(b200_require_device());
+    if (k == 0) return b200_ok();
+    if (!out || !offsets) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: null pointer");
+    const size_t n = (size_t)offsets[k];
+    if (n && !coeffs_mont) return b200_err(B200_ERR_INVALID_ARG, "kzg_commit_batch: null pointer");
+    cudaStream_t s = b200_thread_stream();
+    DevBuf d_c, d_out;
+    CUDA_TRY(d_c.alloc(n * 32, s));
+    CUDA_TRY(d_out.alloc(k * 144, s));
+    if (n) B200_TRY(b200_h2d(d_c.p, coeffs_mont, n * 32, s));
+    B200_TRY(b200_kzg_commit_batch_device(d_out.p, handle, d_c.p, offsets, k, s));
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, k * 144, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return b200_ok();
 }

@@ -113,7 +113,16 @@ b200_error_t msm_run_device(void* d_out, const void* d_points, size_t n, const v
                             bool packed_glv = false /* d_packed holds (P_i, phi(P_i)) pairs: msm_pack_bases_glv_device */);
 b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                                   const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
-                                  cudaStream_t stream, size_t n_reg = 0, uint32_t c_tab = 0, bool packed_glv = false);
+                                  cudaStream_t stream, size_t n_reg = 0, uint32_t c_tab = 0, bool packed_glv = false,
+                                  bool shared_bases = false /* every MSM indexes d_packed from 0: k commits, one SRS */);
+// resident base sets (api.cu)
+struct RegisteredBases {
+    void* d_packed;      // n packed points; with a window table: nwin * n (window 0 first)
+    size_t n;
+    uint32_t c_tab;      // 0: plain; else the window width of the table 2^(c*w) * P_i
+    bool glv;            // plain sets: stored as 2n records (P_i, phi(P_i)) for the GLV split (msm_glv.cuh)
+};
+b200_error_t b200_lookup_bases(uint64_t handle, RegisteredBases* out);
 b200_error_t msm_pack_bases_glv_device(void* d_packed_2n, const void* d_points, size_t n, size_t stride, cudaStream_t stream);
 bool msm_glv_enabled();
 b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scalars, const void* d_table, size_t n_reg,

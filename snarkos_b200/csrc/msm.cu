@@ -140,14 +140,15 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
                                  size_t n_reg, uint32_t glv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
-    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, glv ? i >> 1 : i) * sh.nwin : 0;
+    // bucket set of MSM m: its own nwin windows, or ONE set when the bases are tabulated (all windows share it)
+    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, glv ? i >> 1 : i) * (n_reg ? 1 : sh.nwin) : 0;
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (valid) msm_load_scalar(s, scalars, i, glv);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < sh.nwin; w++) {
         uint32_t neg;
         uint32_t d = msm_signed_digit(s, w, sh.c, carry, neg);
-        warp_aggregated_inc(counts, (n_reg ? 0 : (vbase + w) * sh.nbuckets) + (d ? d - 1 : 0), valid && d != 0);
+        warp_aggregated_inc(counts, (n_reg ? vbase : vbase + w) * sh.nbuckets + (d ? d - 1 : 0), valid && d != 0);
     }
 }
 
@@ -158,18 +159,22 @@ __global__ void msm_count_kernel(uint32_t* __restrict__ counts, const uint4* __r
 __global__ void msm_scatter_kernel(uint32_t* __restrict__ entries, uint32_t* __restrict__ cursor,
                                    const uint4* __restrict__ scalars, size_t n, MsmShape sh,
                                    const unsigned long long* __restrict__ seg_off, uint32_t nmsm, size_t n_reg,
-                                   uint32_t glv) {
+                                   uint32_t glv, uint32_t shared_bases) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     const uint32_t w = blockIdx.y;
-    const size_t vbase = valid ? (size_t)msm_segment_of(seg_off, nmsm, glv ? i >> 1 : i) * sh.nwin : 0;
+    const uint32_t seg = valid ? msm_segment_of(seg_off, nmsm, glv ? i >> 1 : i) : 0;
+    const size_t vbase = (size_t)seg * (n_reg ? 1 : sh.nwin);
+    // shared bases (k polynomials committed against ONE resident set): scalar i of MSM m multiplies base i - seg_off[m]
+    size_t pi = i;
+    if (valid && shared_bases && seg_off) pi = glv ? ((i >> 1) - (size_t)seg_off[seg]) * 2 + (i & 1) : i - (size_t)seg_off[seg];
     uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (valid) msm_load_scalar(s, scalars, i, glv);
     uint32_t carry = 0, neg = 0, d = 0;
     for (uint32_t ww = 0; ww <= w; ww++) d = msm_signed_digit(s, ww, sh.c, carry, neg);
     const bool active = valid && d != 0;
-    uint32_t pos = warp_aggregated_inc(cursor, (n_reg ? 0 : (vbase + w) * sh.nbuckets) + (d ? d - 1 : 0), active);
-    if (active) entries[pos] = (uint32_t)(n_reg ? (size_t)w * n_reg + i : i) | (neg << 31);
+    uint32_t pos = warp_aggregated_inc(cursor, (n_reg ? vbase : vbase + w) * sh.nbuckets + (d ? d - 1 : 0), active);
+    if (active) entries[pos] = (uint32_t)(n_reg ? (size_t)w * n_reg + pi : pi) | (neg << 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -643,6 +648,7 @@ b200_error_t msm_run_tabulated_device(void* d_out, size_t n, const void* d_scala
 // (reduce .. fold); bucket arrays of several ranges computed with the same window width add up bucket by bucket.
 // ---------------------------------------------------------------------------------------------
 struct MsmPlan {
+    bool shared_bases = false;   // batched call whose MSMs all index ONE base set from 0 (k commits against one SRS)
     MsmShape sh;             // per-MSM shape (c, windows, buckets per window)
     MsmShape vsh;            // shape seen after the digit stage: nwin = virtual windows (nmsm * nwin, or 1 when tabulated)
     size_t K;                // total buckets
@@ -683,7 +689,7 @@ static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n
         pl->sh = msm_shape(c_force ? c_force : b200_msm_window_bits(nmsm > 1 ? (n + nmsm - 1) / nmsm : n));
     }
     pl->vsh = pl->sh;
-    pl->vsh.nwin = n_reg ? 1 : pl->sh.nwin * nmsm;           // tabulated: one bucket set, nothing to fold
+    pl->vsh.nwin = n_reg ? nmsm : pl->sh.nwin * nmsm;        // tabulated: one bucket set per MSM, nothing to fold
     pl->K = (size_t)pl->vsh.nwin * pl->sh.nbuckets;
     pl->nmsm = nmsm;
     pl->n_reg = n_reg;
@@ -787,7 +793,8 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     CUDA_TRY(cudaMemcpyAsync(cursor.p, offsets.p, (K + 1) * 4, cudaMemcpyDeviceToDevice, stream));
     STAGE("msm_scatter", stream);
     msm_scatter_kernel<<<dim3(nblk, sh.nwin), 256, 0, stream>>>(entries.as<uint32_t>(), cursor.as<uint32_t>(),
-                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg, glv);
+                                                 reinterpret_cast<const uint4*>(d_scalars), n, sh, d_seg_off, pl.nmsm, pl.n_reg, glv,
+                                                 pl.shared_bases ? 1u : 0u);
     KERNEL_CHECK();
     // ---- batched-affine pair rounds: halve every bucket's list `rounds` times at ~6.3 products per addition ----
     const size_t E = n * sh.nwin;                                   // upper bound on the number of entries
@@ -967,8 +974,10 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
         }
     }
     STAGE("msm_fold", stream);
+    MsmShape fold_sh = pl.sh;
+    if (pl.n_reg) fold_sh.nwin = 1;                          // tabulated: the single bucket set already carries 2^(c*w)
     msm_fold_kernel<<<(pl.nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(),
-                                                            pl.n_reg ? vsh : pl.sh, pl.nmsm);
+                                                            fold_sh, pl.nmsm);
     KERNEL_CHECK();
     STAGE_END(stream);
     return b200_ok();
@@ -978,10 +987,11 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
 // d_out receives nmsm Jacobian points.  d_seg_off == nullptr means a single MSM over everything.
 b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, const void* d_scalars, size_t stride,
                                   const void* d_packed, const unsigned long long* d_seg_off, uint32_t nmsm,
-                                  cudaStream_t stream, size_t n_reg, uint32_t c_tab, bool packed_glv) {
+                                  cudaStream_t stream, size_t n_reg, uint32_t c_tab, bool packed_glv, bool shared_bases) {
     if (!d_out) return b200_err(B200_ERR_INVALID_ARG, "msm: null output pointer");
-    if (n_reg && (nmsm != 1 || !d_packed || c_tab < 2 || n > n_reg))
-        return b200_err(B200_ERR_INVALID_ARG, "msm: tabulated bases need a single MSM over a prefix of the table");
+    if (n_reg && (!d_packed || c_tab < 2 || (nmsm != 1 && !shared_bases) || (nmsm == 1 && n > n_reg)))
+        return b200_err(B200_ERR_INVALID_ARG, "msm: tabulated bases need MSMs over a prefix of the table");
+    if (shared_bases && (!d_packed || !d_seg_off)) return b200_err(B200_ERR_INVALID_ARG, "msm: shared bases need a resident set and offsets");
     if (nmsm == 0) return b200_ok();
     if (n == 0) {
         msm_write_infinity_kernel<<<(nmsm + 63) / 64, 64, 0, stream>>>(reinterpret_cast<uint4*>(d_out), nmsm);
@@ -993,6 +1003,7 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
     if (reinterpret_cast<uintptr_t>(d_scalars) & 15) return b200_err(B200_ERR_INVALID_ARG, "msm: scalars must be 16-byte aligned on the device");
     MsmPlan pl;
     B200_TRY(msm_make_plan(&pl, n, nmsm, n_reg, n_reg ? c_tab : 0, packed_glv || msm_use_glv(d_packed, n_reg)));
+    pl.shared_bases = shared_bases;
     DevBuf buckets;
     CUDA_TRY(buckets.alloc(pl.K * sizeof(g1_xyzz_mem_t), stream));
     B200_TRY(msm_front(pl, buckets.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, d_packed, d_seg_off, stream));

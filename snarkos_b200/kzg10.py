@@ -68,5 +68,62 @@ class KZG10:
         torch.cuda.synchronize()
         return out.cpu().numpy()
 
+    @staticmethod
+    def commit_batch(powers: Powers, polynomials):
+        """k commitments against the same powers in ONE launch set (`SonicKZG10::commit` over the labeled polynomials
+        of a Varuna round [UPSTREAM algorithms/src/polycommit/sonic_pc/mod.rs]): `polynomials` is a list of Montgomery
+        coefficient arrays ([n_m, 4] uint64, or CUDA tensors -- all of one kind).  Returns [k, 144] uint8 (numpy for
+        host inputs, a CUDA tensor for device inputs)."""
+        L = _lib.lib()
+        rb = powers.powers_of_beta_g
+        k = len(polynomials)
+        if k == 0:
+            return np.zeros((0, PROJECTIVE_BYTES), dtype=np.uint8)
+        if _is_cuda_tensor(polynomials[0]):
+            dev = polynomials[0].device
+            flat = [p.contiguous().reshape(-1).view(torch.uint8) if p.numel() else torch.empty(0, dtype=torch.uint8, device=dev)
+                    for p in polynomials]
+            lens = [f.numel() // 32 for f in flat]
+            c = torch.cat(flat) if k > 1 else flat[0]
+            off = (ctypes.c_uint64 * (k + 1))(*np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64).tolist())
+            out = torch.empty((k, PROJECTIVE_BYTES), dtype=torch.uint8, device=c.device)
+            _lib.check(L.b200_kzg_commit_batch_device(ctypes.c_void_p(out.data_ptr()), rb.handle,
+                                                      ctypes.c_void_p(c.data_ptr()), off, k, _stream_ptr()))
+            return out
+        flat = [_host_bytes(p) for p in polynomials]
+        lens = [f.size // 32 for f in flat]
+        c = np.ascontiguousarray(np.concatenate(flat)) if k > 1 else flat[0]
+        off = (ctypes.c_uint64 * (k + 1))(*np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64).tolist())
+        out = np.zeros((k, PROJECTIVE_BYTES), dtype=np.uint8)
+        _lib.check(L.b200_kzg_commit_batch(_np_ptr(out), rb.handle, _np_ptr(c), off, k))
+        return out
+
+    @staticmethod
+    def open(powers: Powers, polynomial_coeffs, point, blinding_coeffs: Optional[object] = None):
+        """`KZG10::open(powers, polynomial, point, rand)`'s arithmetic: the commitment to the witness polynomial
+        (p(X) - p(z)) / (X - z) -- plus, for a hiding commitment, the witness of the blinding polynomial against the
+        gamma powers -- and the evaluations.  Host inputs: Montgomery [n, 4] uint64 coefficients, [4] uint64 point.
+        Returns (w: uint8[144], p(z): uint64[4], random_v: uint64[4] or None)."""
+        L = _lib.lib()
+        z = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
+
+        def one(rb, coeffs):
+            c = _host_bytes(coeffs)
+            out = np.zeros(PROJECTIVE_BYTES, dtype=np.uint8)
+            ev = np.zeros(4, dtype=np.uint64)
+            _lib.check(L.b200_kzg_open(_np_ptr(out), rb.handle, _np_ptr(c), c.size // 32, _np_ptr(z), _np_ptr(ev)))
+            return out, ev
+
+        w, v = one(powers.powers_of_beta_g, polynomial_coeffs)
+        if blinding_coeffs is None:
+            return w, v, None
+        if powers.powers_of_beta_times_gamma_g is None:
+            raise ValueError("hiding opening needs powers_of_beta_times_gamma_g")
+        wr, rv = one(powers.powers_of_beta_times_gamma_g, blinding_coeffs)
+        both = torch.from_numpy(np.stack([w, wr])).cuda()
+        out = sum_projective(both)
+        torch.cuda.synchronize()
+        return out.cpu().numpy(), v, rv
+
     # commit_lagrange is the same sum against the Lagrange-basis powers with evaluations as "coefficients"
     commit_lagrange = commit

@@ -156,3 +156,37 @@ def synthetic_bases(n: int, seed: int = 1234567890, stride: int = AFFINE_STRIDE,
     out = torch.empty(n * stride, dtype=torch.uint8, device=device)
     _lib.check(_lib.lib().b200_g1_synthetic_bases_device(ctypes.c_void_p(out.data_ptr()), n, stride, seed, _stream_ptr()))
     return out
+
+
+def g1_batch_normalize(points, stride: int = AFFINE_STRIDE):
+    """`Projective::batch_normalization` + `to_affine`: k Jacobian images ([k, 144] uint8) -> G1Affine images
+    [k, stride] (x, y Montgomery, infinity flag at byte 96).  numpy in -> numpy out; CUDA tensor in -> CUDA tensor."""
+    L = _lib.lib()
+    if _is_cuda_tensor(points):
+        p = points.contiguous().view(torch.uint8).reshape(-1)
+        k = p.numel() // PROJECTIVE_BYTES
+        out = torch.empty((k, stride), dtype=torch.uint8, device=p.device)
+        _lib.check(L.b200_g1_batch_normalize_device(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(p.data_ptr()), k, stride, _stream_ptr()))
+        return out
+    p = _host_bytes(points)
+    k = p.size // PROJECTIVE_BYTES
+    out = np.zeros((k, stride), dtype=np.uint8)
+    _lib.check(L.b200_g1_batch_normalize(_np_ptr(out), _np_ptr(p), k, stride))
+    return out
+
+
+def g1_compress(points):
+    """Compressed G1Affine encodings [k, 48] of k Jacobian images ([k, 144] uint8): the bytes a commitment has inside a
+    serialised Varuna proof (`ToBytes::write_le` of a G1Affine)."""
+    L = _lib.lib()
+    if _is_cuda_tensor(points):
+        p = points.contiguous().view(torch.uint8).reshape(-1)
+        k = p.numel() // PROJECTIVE_BYTES
+        out = torch.empty((k, 48), dtype=torch.uint8, device=p.device)
+        _lib.check(L.b200_g1_compress_device(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(p.data_ptr()), k, _stream_ptr()))
+        return out
+    p = _host_bytes(points)
+    k = p.size // PROJECTIVE_BYTES
+    out = np.zeros((k, 48), dtype=np.uint8)
+    _lib.check(L.b200_g1_compress(_np_ptr(out), _np_ptr(p), k))
+    return out

@@ -65,3 +65,26 @@ def divide_by_vanishing_poly_on_coset_in_place(evals, log_k: int, log_h: int):
         raise ValueError("evaluation vector must have the size of the coset domain")
     _lib.check(_lib.lib().b200_fr_divide_by_vanishing_on_coset_device(_p(evals), log_k, log_h, _s()))
     return evals
+
+
+def linear_combination(polys, coeffs, out_len: int | None = None):
+    """sum_m coeffs[m] * polys[m] (polynomials of different lengths, zero-extended): the combination by opening
+    challenges in `KZG10::open` / `SonicKZG10::open_combinations`.  polys: list of CUDA [n_m, 4] tensors; coeffs: CUDA
+    [k, 4] Montgomery Fr."""
+    k = len(polys)
+    lens = [_n(p) for p in polys]
+    out_len = max(lens) if out_len is None else out_len
+    flat = torch.cat([p.contiguous().reshape(-1) for p in polys if p.numel()]) if any(lens) else torch.empty(0, dtype=torch.int64, device=coeffs.device)
+    off = (ctypes.c_uint64 * (k + 1))(*([0] + [sum(lens[: i + 1]) for i in range(k)]))
+    out = torch.empty((out_len, 4), dtype=torch.int64, device=coeffs.device)
+    _lib.check(_lib.lib().b200_fr_linear_combination_device(_p(out), _p(flat), off, k, _p(coeffs), out_len, _s()))
+    return out
+
+
+def divide_by_linear(poly, point):
+    """(quotient, remainder) of poly by (X - point); remainder = poly(point).  CUDA [n, 4] and [1, 4] Montgomery Fr."""
+    n = _n(poly)
+    q = torch.empty((max(n - 1, 0), 4), dtype=torch.int64, device=poly.device)
+    rem = torch.empty((1, 4), dtype=torch.int64, device=poly.device)
+    _lib.check(_lib.lib().b200_fr_divide_by_linear_device(_p(q) if n > 1 else None, _p(poly), n, _p(point), _p(rem), _s()))
+    return q, rem

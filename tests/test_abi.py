@@ -62,3 +62,26 @@ def test_options_and_counters_need_no_device():
     assert S.counter("msm_xyzz_fallbacks") >= 0
     with pytest.raises(_lib.B200Error):
         S.counter("no_such_counter")
+
+
+def test_rust_binding_covers_the_header():
+    """rust/snarkvm-algorithms-b200/src/lib.rs cannot be compiled here (no toolchain): at least every function the
+    header declares is bound there with the same number of arguments"""
+    hdr = open(os.path.join(ROOT, "include", "snarkos_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    rs = open(os.path.join(ROOT, "rust", "snarkvm-algorithms-b200", "src", "lib.rs")).read()
+    rs = re.sub(r"//[^\n]*", "", rs)
+
+    def arity(args: str) -> int:
+        args = args.strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    c_decl = {m.group(1): arity(m.group(2)) for m in re.finditer(r"\b(b200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)}
+    rs_decl = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (b200_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
+    assert set(declared_functions()) == set(c_decl)
+    missing = sorted(set(c_decl) - set(rs_decl))
+    assert not missing, f"not bound in the -sys crate: {missing}"
+    extra = sorted(set(rs_decl) - set(c_decl))
+    assert not extra, f"bound in the -sys crate but not declared in the header: {extra}"
+    wrong = {n: (c_decl[n], rs_decl[n]) for n in c_decl if c_decl[n] != rs_decl[n]}
+    assert not wrong, f"argument count differs (header, rust): {wrong}"

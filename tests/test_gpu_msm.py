@@ -172,6 +172,43 @@ def test_kzg_commit_resident_powers():
     powers.release()
 
 
+@pytest.mark.parametrize("n,auto_table", [(1 << 12, 1), (1 << 12, 0), (1 << 9, 1)])
+def test_kzg_commit_batch_shared_powers(n, auto_table):
+    """k polynomials of different lengths against ONE resident set in one launch set == each commit on its own (and the
+    oracle): the tabulated path (auto table at 2^10..2^20), the plain packed path and a set below the table threshold;
+    zero polynomials, empty polynomials, repeated-digit coefficients and a length equal to the whole set included."""
+    import torch
+    import snarkos_b200 as S
+    S.set_option("msm_auto_table", auto_table)
+    try:
+        g_powers = _synthetic(n, 41)
+        powers = S.Powers(g_powers)
+    finally:
+        S.set_option("msm_auto_table", 1)
+    rng = np.random.default_rng(19)
+    lens = [n, 700 if n > 700 else n // 2, 0, 1, 333, n - 1, 64]
+    polys = [H.random_fr_mont_np(rng, (L,)) for L in lens]
+    polys[4][:] = 0                                                   # the zero polynomial
+    polys[1][:50] = 0                                                 # leading zeros
+    one = H.random_fr_mont_np(rng, (1,))
+    polys[6][:] = one                                                 # all coefficients equal: one bucket per window
+    hb = g_powers.cpu().numpy()
+    want = [oracle_msm(hb[:L * 104], C.fr_from_mont(p)) if L else None for L, p in zip(lens, polys)]
+    got = S.KZG10.commit_batch(powers, polys)
+    assert got.shape == (len(lens), 144)
+    for m in range(len(lens)):
+        assert H.jac_bytes_to_affine(got[m]) == want[m], f"polynomial {m} (len {lens[m]})"
+        assert H.jac_bytes_to_affine(S.KZG10.commit(powers, polys[m])) == want[m]
+    dev = S.KZG10.commit_batch(powers, [torch.from_numpy(p.view(np.int64)).cuda() for p in polys])
+    torch.cuda.synchronize()
+    dev = dev.cpu().numpy()
+    for m in range(len(lens)):
+        assert H.jac_bytes_to_affine(dev[m]) == want[m]
+    with pytest.raises(S.B200Error):
+        S.KZG10.commit_batch(powers, [polys[0], H.random_fr_mont_np(rng, (n + 1,))])
+    powers.release()
+
+
 def test_batched_small_msms():
     """config 4 shape: many independent small MSMs (tens of points each) in one call == each one on its own"""
     import snarkos_b200 as S
@@ -452,3 +489,84 @@ def test_single_gpu_2_26_exact_identity():
     torch.cuda.empty_cache()
     k = H.splitmix64_at(seed, np.arange(n))
     assert H.jac_bytes_to_affine(out.cpu().numpy()) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# output forms of a commitment (a8 / f4) and KZG10::open (a9)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_batch_normalize_and_compress():
+    """Projective::batch_normalization / to_affine and the compressed encoding: device == C oracle == Python oracle"""
+    import torch
+    import snarkos_b200 as S
+    n = 100
+    bases = _synthetic(n, 5).cpu().numpy().reshape(n, 104)
+    k = np.arange(3, 3 + n, dtype=np.uint64)
+    # non-trivial Jacobian representatives: k_i * P_i through the device's XYZZ ladder (Z != 1)
+    L = S.lib()
+    jac = np.zeros((n, 144), dtype=np.uint8)
+    from snarkos_b200 import _lib
+    import ctypes
+    _lib.check(L.b200_debug_g1_op(2, jac.ctypes.data_as(ctypes.c_void_p), bases.ctypes.data_as(ctypes.c_void_p),
+                                  k.ctypes.data_as(ctypes.c_void_p), n, 104))
+    jac[17] = 0                                                        # Z = 0: infinity
+    jac[17, 0] = 1
+    jac[40, 96:] = 0                                                   # another infinity, inside a chunk of 16
+    for stride in (104, 112):
+        got = S.g1_batch_normalize(jac, stride=stride)
+        want = C.g1_to_affine(jac, stride)
+        for i in range(n):
+            if want[i, 96]:
+                assert got[i, 96] == 1
+            else:
+                assert bytes(got[i]) == bytes(want[i]), i
+    comp = S.g1_compress(jac)
+    assert np.array_equal(comp, C.g1_compress(jac))
+    for i in (0, 1, 17, 40, 99):
+        assert bytes(comp[i]) == O.g1_compress(H.jac_bytes_to_affine(jac[i]))
+        assert O.g1_decompress(bytes(comp[i])) == H.jac_bytes_to_affine(jac[i])
+    dcomp = S.g1_compress(torch.from_numpy(jac).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dcomp.cpu().numpy(), comp)
+    assert S.g1_compress(np.zeros((0, 144), dtype=np.uint8)).shape == (0, 48)
+
+
+@pytest.mark.parametrize("n", [1, 2, 100, 3000])
+def test_kzg_open_matches_witness_commitment(n):
+    """KZG10::open: w = commit((p - p(z)) / (X - z)), evaluation p(z); with a blinding polynomial the gamma-power part
+    is added.  Also the KZG identity p(beta) - p(z) = w(beta) * (beta - z) in the exponent (powers = beta^i * G)."""
+    import snarkos_b200 as S
+    rng = O.SplitMix64(1000 + n)
+    beta = O.random_fr(rng, 1)[0]
+    npow = max(n, 64)
+    # powers beta^i * G through the oracle (scalar multiples of the generator)
+    pw, acc = [], 1
+    for _ in range(npow):
+        pw.append(acc)
+        acc = acc * beta % O.R_MOD
+    g_pts = [O.g1_mul(O.G1_GEN, e) for e in pw] if npow <= 200 else None     # long sets: synthetic bases + C oracle
+    p = O.random_fr(rng, n)
+    z = O.random_fr(rng, 1)[0]
+    R = O.R_MOD
+    ev = sum(c * pow(z, i, R) for i, c in enumerate(p)) % R
+    q, carry = [0] * max(n - 1, 0), 0
+    for j in range(n - 1, -1, -1):
+        carry = (p[j] + z * carry) % R
+        if j >= 1:
+            q[j - 1] = carry
+    if g_pts is None:
+        bases = _synthetic(npow, 77)
+        hb = bases.cpu().numpy()
+        powers = S.Powers(bases)
+        want = oracle_msm(hb[:(n - 1) * 104], H.scalars_array(q)) if n > 1 else None
+    else:
+        hb = H.bases_array(g_pts)
+        powers = S.Powers(hb)
+        want = O.g1_mul(O.G1_GEN, sum(c * pw[i] for i, c in enumerate(q)) % R) if n > 1 else None
+        # the pairing-free form of the KZG check: (p(beta) - p(z)) * G == (beta - z) * W
+        pb = sum(c * pw[i] for i, c in enumerate(p)) % R
+        assert O.g1_mul(O.G1_GEN, (pb - ev) % R) == O.g1_mul(want, (beta - z) % R)
+    w, v, rv = S.KZG10.open(powers, H.fr_mont_array(p), H.fr_mont_array([z])[0])
+    assert rv is None
+    assert H.fr_from_mont_array(v.reshape(1, 4)) == [ev]
+    assert H.jac_bytes_to_affine(w) == want
+    powers.release()

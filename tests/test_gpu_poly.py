@@ -92,3 +92,39 @@ def test_divide_by_vanishing_and_quotient_pipeline(log_h, log_k):
         assert got[i] == want
     dk.coset_ifft_in_place(ev)
     assert host(ev) == (q + [0] * (nk - len(q)))
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 1000, 4096, 4097, 70000])
+def test_divide_by_linear(n):
+    """quotient and remainder of p by (X - z) == synthetic division with Python big-ints (chunk boundaries at 64 and
+    64^2 = 4096 are the recursion levels of the device algorithm)"""
+    from snarkos_b200 import poly as P
+    rng = O.SplitMix64(n)
+    p = O.random_fr(rng, n)
+    z = O.random_fr(rng, 1)[0]
+    R = O.R_MOD
+    q, carry = [0] * max(n - 1, 0), 0
+    for j in range(n - 1, -1, -1):
+        carry = (p[j] + z * carry) % R
+        if j >= 1:
+            q[j - 1] = carry
+    got_q, got_r = P.divide_by_linear(dev(p), dev([z]))
+    assert host(got_r) == [carry]
+    assert host(got_q) == q if n > 1 else got_q.numel() == 0
+    # degenerate points
+    for zz in (0, 1, R - 1):
+        gq, gr = P.divide_by_linear(dev(p), dev([zz]))
+        assert host(gr) == [sum(c * pow(zz, i, R) for i, c in enumerate(p)) % R]
+
+
+def test_linear_combination():
+    from snarkos_b200 import poly as P
+    rng = O.SplitMix64(5)
+    lens = [100, 1, 0, 257, 64]
+    polys = [O.random_fr(rng, L) for L in lens]
+    cs = O.random_fr(rng, len(lens))
+    import torch
+    dp = [dev(p) if p else torch.empty((0, 4), dtype=torch.int64, device="cuda") for p in polys]
+    got = host(P.linear_combination(dp, dev(cs)))
+    want = [sum(c * p[i] for c, p in zip(cs, polys) if i < len(p)) % O.R_MOD for i in range(max(lens))]
+    assert got == want
