@@ -82,7 +82,7 @@ static void config_from_env(B200Config& c) {
     c.msm_fuse_denoms = getenv("B200_MSM_NO_FUSE_DENOMS") ? 0 : 1;
     c.msm_queue_threshold = env_int("B200_MSM_QUEUE_THRESHOLD", 0);
     if (const char* e = getenv("B200_NTT_PLAN")) { strncpy(c.ntt_plan, e, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
-    c.ntt_tile_log = env_int("B200_NTT_TILE_LOG", 11);
+    c.ntt_tile_log = env_int("B200_NTT_TILE_LOG", 0);
     c.ntt_radix4 = !getenv("B200_NTT_RADIX2");
     c.ntt_boundary_tables = !getenv("B200_NTT_NO_BOUNDARY_TABLES");
     c.ntt_host_pipeline = !getenv("B200_NTT_NO_HOST_PIPELINE");

@@ -52,11 +52,12 @@ struct B200Config {
                                      //                          through the coalescing queue (queue.cu); 0 = off
     int msm_fuse_denoms = 1;         // msm_fuse_denoms          B200_MSM_NO_FUSE_DENOMS (pair round r computes round r+1's denominators)
     char ntt_plan[32] = {0};         // ntt_plan "a,b,c"         B200_NTT_PLAN
-    int ntt_tile_log = 11;           // ntt_tile_log             B200_NTT_TILE_LOG
+    int ntt_tile_log = 0;            // ntt_tile_log             B200_NTT_TILE_LOG
     bool ntt_radix4 = true;          // ntt_radix4               B200_NTT_RADIX2
     bool ntt_boundary_tables = true; // ntt_boundary_tables      B200_NTT_NO_BOUNDARY_TABLES
     bool ntt_host_pipeline = true;   // ntt_host_pipeline        B200_NTT_NO_HOST_PIPELINE
-    int ntt_variant = 0;             // ntt_variant              B200_NTT_VARIANT       0 = default kernel selection
+    int ntt_variant = 0;             // ntt_variant              B200_NTT_VARIANT       0 = default (128-thread CTAs on 1024-element tiles),
+                                     //                          1 = bulk-copy TMA, 3 = 256-thread CTAs only, 4 = warp-column kernel for 2^8 passes
     bool staged_copies = true;       // staged_copies            B200_NO_STAGED_COPIES
     int l2_fetch_granularity = 0;    // (init only)              B200_L2_FETCH_GRANULARITY
     bool graphs = true;              // graphs                   B200_NO_GRAPHS         CUDA-graph replay of small calls

@@ -15,7 +15,12 @@
 #ifndef NTT_MIN_CTAS
 #define NTT_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const NttPassParams p) {
+__device__ __forceinline__ void ntt_pass_body(const NttPassParams& p);
+__global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const NttPassParams p) { ntt_pass_body(p); }
+// the same pass on 128-thread CTAs (option ntt_variant = 2): with 32 KB tiles six CTAs share an SM instead of three, so
+// that more CTAs are in their multiplier-bound stage phases while others load or store
+__global__ void __launch_bounds__(128, 6) ntt_pass_kernel_128(const NttPassParams p) { ntt_pass_body(p); }
+__device__ __forceinline__ void ntt_pass_body(const NttPassParams& p) {
     extern __shared__ uint4 sm[];
     const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     const uint32_t L = p.log_len[p.pass];
@@ -39,6 +44,27 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const NttPa
     }
     ntt_phase_store(p, sm, tile, batch, tid, nt);
 }
+
+// Warp-column pass (ntt_core.cuh): length-2^8 passes over 4 adjacent columns, one warp per column, 8 elements per lane,
+// three in-register rounds with warp-level synchronisation only; two block barriers per tile.
+__global__ void __launch_bounds__(128, 4) ntt_pass_wc_kernel(const NttPassParams p) {
+    extern __shared__ uint4 sm[];
+    const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x;
+    uint4* sm_tw = sm + WC_TILE_U4;
+    ntt_phase_stage_twiddles(p, sm_tw, tid, 128);
+    const NttTwiddles twd = ntt_shared_twiddles(sm_tw, WC_LOG_LEN);
+    wc_phase_load(p, sm, tile, batch, tid, 128);
+    __syncthreads();
+    const uint32_t cw = tid >> 5, lane = tid & 31u;
+    wc_round1(p, sm, twd, tile, cw, lane);
+    __syncwarp();
+    wc_round2(sm, twd, cw, lane);
+    __syncwarp();
+    wc_round3(sm, twd, cw, lane);
+    __syncthreads();
+    wc_phase_store(p, sm, tile, batch, tid, 128);
+}
+#define NTT_WC_SMEM (WC_TILE_U4 * 16 + (1u << WC_LOG_LEN) * 16)
 
 // ---------------------------------------------------------------------------------------------
 // Bulk-copy (TMA) variant: persistent CTAs, two tile buffers, cp.async.bulk (UBLKCP) loads of tile i + 1 completing on
@@ -252,6 +278,11 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         // different L1 / shared splits do not share an SM, which serialises the two streams of the overlapped
         // multi-GPU schedule (measured: NTT 4.01 ms + exchange 0.38 ms = 4.39 ms "concurrently")
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel_128, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (1 << NTT_MAX_TILE_LOG) * 32 + (1 << (NTT_MAX_TILE_LOG - 1)) * 32));
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel_128, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_wc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_WC_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(ntt_pass_wc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         {
@@ -515,6 +546,8 @@ void ntt_release_tables() {
     g_ntt.domains.clear();
 }
 
+static bool ntt_wc_applicable_host(const NttPlan& plan, uint32_t i) { return plan.log_len[i] == WC_LOG_LEN && plan.log_cw[i] == WC_LOG_CW; }
+
 b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction,
                             int coset, cudaStream_t stream) {
     if (log_n > NTT_MAX_LOG_N) return b200_err(B200_ERR_TOO_LARGE, "ntt: log_n > 28 is not supported");
@@ -528,7 +561,11 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
     if (log_n == 0) return b200_ok();
 
     NttPlan plan;
-    if (!ntt_make_plan(log_n, &plan, (uint32_t)b200_config().ntt_tile_log, b200_config().ntt_plan)) return b200_err(B200_ERR_INVALID_ARG, "ntt: no valid pass plan");
+    // tile size: 1024 elements (32 KB, six 128-thread CTAs per SM) unless 2048-element tiles save a whole pass
+    // (2^26: 9 + 9 + 8 in three passes against four with 8-bit passes; measured 16.3 vs 18.5 ms)
+    uint32_t tile_log = (uint32_t)b200_config().ntt_tile_log;
+    if (tile_log == 0) tile_log = (log_n + 8) / 9 < (log_n + 7) / 8 ? 11 : 10;
+    if (!ntt_make_plan(log_n, &plan, tile_log, b200_config().ntt_plan)) return b200_err(B200_ERR_INVALID_ARG, "ntt: no valid pass plan");
     NttDomainTables tabs;
     const uint4* tile_tw = nullptr;
     B200_TRY(get_tables(log_n, direction, stream, &tabs, &tile_tw, &plan));
@@ -559,14 +596,14 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         p.scale_post = (last && direction == 1) ? 1 : 0;
         p.coset_post = (last && coset && direction == 1) ? 1 : 0;
         p.radix4 = b200_config().ntt_radix4 ? 1 : 0;
-        const uint32_t tile_log = plan.log_len[i] + plan.log_cw[i];
-        const uint32_t tile_elems = 1u << tile_log;
+        const uint32_t pass_tile_log = plan.log_len[i] + plan.log_cw[i];
+        const uint32_t tile_elems = 1u << pass_tile_log;
         uint32_t threads = tile_elems / 2;
         if (threads > 256) threads = 256;
         if (threads < 32) threads = 32;
         static const char* const kPassName[NTT_MAX_PASSES] = {"ntt_pass0", "ntt_pass1", "ntt_pass2", "ntt_pass3"};
         STAGE(kPassName[i], stream);
-        const uint32_t tiles_per_poly = 1u << (log_n - tile_log);
+        const uint32_t tiles_per_poly = 1u << (log_n - pass_tile_log);
         const unsigned long long total_tiles = (unsigned long long)tiles_per_poly * batch;
         if (b200_config().ntt_variant == 1 && threads == 256 && total_tiles < (1ull << 31)) {
             // bulk-copy (TMA) variant: persistent CTAs over all tiles of the batch, two tile buffers
@@ -583,8 +620,21 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
             }
         }
         dim3 grid(tiles_per_poly, (unsigned)batch);
+        // Warp-column kernel: built, bit-exact, measured and NOT the default -- 4.12 ms against 3.43 ms at 2^24 (ncu
+        // profiles/r02_ncu_ntt_wc.txt: 30 k instructions of straight-line code per tile, `no_instruction` stalls 2.9 - 3.6
+        // per issue, 16 warps per SM at 128 registers, multiplier pipe 66 - 70 % busy); option ntt_variant = 4 selects it.
+        if (b200_config().ntt_variant == 4 && ntt_wc_applicable_host(plan, i)) {
+            ntt_pass_wc_kernel<<<grid, 128, NTT_WC_SMEM, stream>>>(p);
+            KERNEL_CHECK();
+            continue;
+        }
         const size_t smem = (size_t)tile_elems * 32 + ((size_t)1 << plan.log_len[i]) * 16;   // tile + L/2 twiddles
-        ntt_pass_kernel<<<grid, threads, smem, stream>>>(p);
+        // 1024-element tiles (the default): 128-thread CTAs, six per SM (measured 3.47 vs 3.57 ms at 2^24, 2.98 vs 3.26 ms at
+        // 2^20 x 16 against 256-thread CTAs on 2048-element tiles); ntt_variant = 3 forces the 256-thread CTAs
+        if (tile_elems == 1024 && b200_config().ntt_variant != 3)
+            ntt_pass_kernel_128<<<grid, 128, smem, stream>>>(p);
+        else
+            ntt_pass_kernel<<<grid, threads, smem, stream>>>(p);
         KERNEL_CHECK();
     }
     STAGE_END(stream);

@@ -364,8 +364,15 @@ B200_HD void ntt_store_element(const NttPassParams& p, const NttGeom& g, fr_t x,
     dst[2 * out + 1] = hi;
 }
 
-B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
-                             uint32_t nthreads) {
+// how a tile is laid out in shared memory: planar (default kernel) or warp-column (below)
+struct PlanarTile {
+    const uint4* sm;
+    uint32_t tile_elems, log_cw;
+    B200_HDM fr_t get(uint32_t t, uint32_t cw) const { return tile_load(sm, tile_elems, (t << log_cw) + cw); }
+};
+template <class Tile>
+B200_HD void ntt_phase_store_t(const NttPassParams& p, const Tile& T, uint32_t tile, uint32_t batch, uint32_t tid,
+                               uint32_t nthreads) {
     NttGeom g = ntt_geom(p);
     uint4* dst = p.dst + 2ull * batch * p.batch_stride;
     uint32_t e = tid;
@@ -389,7 +396,7 @@ B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t t
             for (int q = 0; q < NTT_STORE_BATCH; q++) {
                 uint32_t t, cw;
                 ntt_store_source(g, e + q * nthreads, t, cw);
-                ntt_store_element(p, g, tile_load(sm, g.tile_elems, (t << g.log_cw) + cw), dst, tile, e + q * nthreads, true, tw[q]);
+                ntt_store_element(p, g, T.get(t, cw), dst, tile, e + q * nthreads, true, tw[q]);
             }
         }
     }
@@ -397,8 +404,165 @@ B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t t
     for (; e < g.tile_elems; e += nthreads) {
         uint32_t t, cw;
         ntt_store_source(g, e, t, cw);
-        ntt_store_element(p, g, tile_load(sm, g.tile_elems, (t << g.log_cw) + cw), dst, tile, e, false, none);
+        ntt_store_element(p, g, T.get(t, cw), dst, tile, e, false, none);
     }
+}
+B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
+                             uint32_t nthreads) {
+    const NttGeom g = ntt_geom(p);
+    PlanarTile T;
+    T.sm = sm;
+    T.tile_elems = g.tile_elems;
+    T.log_cw = g.log_cw;
+    ntt_phase_store_t(p, T, tile, batch, tid, nthreads);
+}
+
+// =============================================================================================
+// Warp-column variant of a pass of length 2^8 over 4 adjacent columns (ntt_pass_wc_kernel in ntt.cu).
+// The default kernel above runs every stage pair as a block-wide phase over the whole tile: four round trips through
+// shared memory and six block barriers per tile, and all warps of a CTA sit in the same phase at the same time (ncu r02:
+// the multiplier pipe is busy 74 % of the cycles, 1226 instructions per element and pass of which 480 are IMAD.WIDE).
+// Here ONE WARP OWNS ONE COLUMN (256 elements, 8 per lane = 64 registers of data) and runs its 8 DIF stages as three
+// in-register rounds -- radix 8 (distances 128, 64, 32), radix 8 (16, 8, 4), radix 4 (2, 1) -- exchanging through its own
+// slice of the tile with nothing but __syncwarp in between; the CTA (4 warps, one 32 KB tile) meets at two block
+// barriers only (tile loaded / tile transformed), so warps and CTAs drift apart and load, exchange and multiply
+// phases overlap.  Index arithmetic is compile-time; every lane has 4 independent butterflies in flight per stage.
+//
+// Shared layout: two planes of 16-byte halves; column cw of a plane starts at cw * 257 words and element t sits at
+//     wc_idx(t) = t ^ ((t >> 3) & 3) ^ ((((t >> 5) ^ (t >> 7)) & 1) << 2)
+// -- a swizzle of the low three word bits by higher bits of t that makes all access patterns of the kernel hit 8
+// distinct 16-byte bank groups per quarter-warp: round 1 (t = lane + 32 i), round 2 (t = 32 a + 4 k + b, lane = 4 a + b),
+// round 3 (t = 4 (lane + 32 j) + r), the cooperative fill (4 columns x 2 halves of one row; the plane stride
+// 4 * 257 = 4 mod 8 separates the halves, the column stride 257 = 1 mod 8 the columns) and the read-out in
+// bit-reversed row order (rows k, k + 1 come from t, t + 128).
+// =============================================================================================
+#define WC_LOG_LEN 8u
+#define WC_LOG_CW 2u
+#define WC_COL_STRIDE 257u
+#define WC_PLANE_STRIDE (4u * WC_COL_STRIDE)
+#define WC_TILE_U4 (2u * WC_PLANE_STRIDE)              // 16-byte words of one tile (32.9 KB)
+
+B200_HD uint32_t wc_idx(uint32_t t) { return t ^ ((t >> 3) & 3u) ^ ((((t >> 5) ^ (t >> 7)) & 1u) << 2); }
+B200_HD uint32_t wc_word(uint32_t half, uint32_t t, uint32_t cw) { return half * WC_PLANE_STRIDE + cw * WC_COL_STRIDE + wc_idx(t); }
+B200_HD fr_t wc_load(const uint4* sm, uint32_t t, uint32_t cw) { return fr_from_u4(sm[wc_word(0, t, cw)], sm[wc_word(1, t, cw)]); }
+B200_HD void wc_store(uint4* sm, uint32_t t, uint32_t cw, const fr_t& x) { fr_to_u4(x, sm[wc_word(0, t, cw)], sm[wc_word(1, t, cw)]); }
+struct WcTile {
+    const uint4* sm;
+    B200_HDM fr_t get(uint32_t t, uint32_t cw) const { return wc_load(sm, t, cw); }
+};
+B200_HD bool ntt_wc_applicable(const NttPassParams& p) { return p.log_len[p.pass] == WC_LOG_LEN && p.log_cw == WC_LOG_CW; }
+
+// global -> shared, the same coalesced runs as ntt_phase_load (whole CTA)
+B200_HD void wc_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid, uint32_t nthreads) {
+    const NttGeom g = ntt_geom(p);
+    const uint4* src = p.src + 2ull * batch * p.batch_stride;
+    const uint32_t total = 2u * g.tile_elems;
+    uint32_t u = tid;
+    for (; u + (NTT_LOAD_BATCH - 1) * nthreads < total; u += NTT_LOAD_BATCH * nthreads) {
+        uint4 v[NTT_LOAD_BATCH];
+        uint32_t dst[NTT_LOAD_BATCH];
+        B200_UNROLL
+        for (int k = 0; k < NTT_LOAD_BATCH; k++) {
+            const uint32_t uu = u + k * nthreads;
+            const uint32_t half = uu & 1u, e = uu >> 1;
+            uint32_t t, cw;
+            if (!g.last) { cw = e & 3u; t = e >> 2; }
+            else         { t = e & 255u; cw = e >> 8; }
+            v[k] = src[2 * ntt_in_index(p, g, tile, t, cw) + half];
+            dst[k] = wc_word(half, t, cw);
+        }
+        B200_UNROLL
+        for (int k = 0; k < NTT_LOAD_BATCH; k++) sm[dst[k]] = v[k];
+    }
+    for (; u < total; u += nthreads) {
+        const uint32_t half = u & 1u, e = u >> 1;
+        uint32_t t, cw;
+        if (!g.last) { cw = e & 3u; t = e >> 2; }
+        else         { t = e & 255u; cw = e >> 8; }
+        sm[wc_word(half, t, cw)] = src[2 * ntt_in_index(p, g, tile, t, cw) + half];
+    }
+}
+
+// DIF butterfly: (a, b) <- (a + b, (a - b) * w)
+B200_HD void wc_bf(fr_t& a, fr_t& b, const fr_t& w) {
+    const fr_t s = fp_add(a, b);
+    b = fp_mul(fp_sub(a, b), w);
+    a = s;
+}
+B200_HD void wc_bf1(fr_t& a, fr_t& b) {                 // twiddle 1
+    const fr_t s = fp_add(a, b);
+    b = fp_sub(a, b);
+    a = s;
+}
+// three DIF stages on 8 register-resident points x[0..7] at distances 4, 2, 1 (in units of the register index);
+// e0[i] (i < 4), e1[i] (i < 2), e2: exponents of w_256 for the three stages
+B200_HD void wc_radix8(fr_t* x, const NttTwiddles& twd, const uint32_t* e0, const uint32_t* e1, uint32_t e2) {
+    B200_UNROLL
+    for (int i = 0; i < 4; i++) wc_bf(x[i], x[i + 4], ntt_twiddle(twd, e0[i]));
+    B200_UNROLL
+    for (int i = 0; i < 2; i++) {
+        const fr_t w = ntt_twiddle(twd, e1[i]);
+        wc_bf(x[i], x[i + 2], w);
+        wc_bf(x[i + 4], x[i + 6], w);
+    }
+    {
+        const fr_t w = ntt_twiddle(twd, e2);
+        B200_UNROLL
+        for (int i = 0; i < 8; i += 2) wc_bf(x[i], x[i + 1], w);
+    }
+}
+
+// round 1: stages 0..2 (distances 128, 64, 32); lane holds t = lane + 32 i.  Forward coset scaling folded in.
+B200_HD void wc_round1(const NttPassParams& p, uint4* sm, const NttTwiddles& twd, uint32_t tile, uint32_t cw, uint32_t lane) {
+    fr_t x[8];
+    B200_UNROLL
+    for (int i = 0; i < 8; i++) x[i] = wc_load(sm, lane + 32u * i, cw);
+    if (p.coset_pre) {
+        const NttGeom g = ntt_geom(p);
+        B200_UNROLL
+        for (int i = 0; i < 8; i++)
+            x[i] = fp_mul(x[i], pow2level(p.coset_lo, p.coset_hi, ntt_in_index(p, g, tile, lane + 32u * i, cw)));
+    }
+    // stage s pairs t, t + d (d = 128 >> s) with twiddle w^((t mod d) << s)
+    const uint32_t e0[4] = {lane, lane + 32u, lane + 64u, lane + 96u};
+    const uint32_t e1[2] = {lane << 1, (lane + 32u) << 1};
+    wc_radix8(x, twd, e0, e1, lane << 2);
+    B200_UNROLL
+    for (int i = 0; i < 8; i++) wc_store(sm, lane + 32u * i, cw, x[i]);
+}
+// round 2: stages 3..5 (distances 16, 8, 4); lane = 4 a + b holds t = 32 a + 4 k + b
+B200_HD void wc_round2(uint4* sm, const NttTwiddles& twd, uint32_t cw, uint32_t lane) {
+    const uint32_t a = lane >> 2, b = lane & 3u, t0 = 32u * a + b;
+    fr_t x[8];
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) x[k] = wc_load(sm, t0 + 4u * k, cw);
+    const uint32_t e0[4] = {b << 3, (b + 4u) << 3, (b + 8u) << 3, (b + 12u) << 3};      // (t mod 16) << 3
+    const uint32_t e1[2] = {b << 4, (b + 4u) << 4};                                       // (t mod 8) << 4
+    wc_radix8(x, twd, e0, e1, b << 5);                                                    // (t mod 4) << 5
+    B200_UNROLL
+    for (int k = 0; k < 8; k++) wc_store(sm, t0 + 4u * k, cw, x[k]);
+}
+// round 3: stages 6, 7 (distances 2, 1); lane holds the quads t = 4 (lane + 32 j) + r
+B200_HD void wc_round3(uint4* sm, const NttTwiddles& twd, uint32_t cw, uint32_t lane) {
+    const fr_t w64 = ntt_twiddle(twd, 64u);                                               // (t mod 2) << 6 for odd t
+    B200_UNROLL
+    for (int j = 0; j < 2; j++) {
+        const uint32_t t0 = 4u * (lane + 32u * j);
+        fr_t x0 = wc_load(sm, t0, cw), x1 = wc_load(sm, t0 + 1, cw), x2 = wc_load(sm, t0 + 2, cw), x3 = wc_load(sm, t0 + 3, cw);
+        wc_bf1(x0, x2);
+        wc_bf(x1, x3, w64);
+        wc_bf1(x0, x1);
+        wc_bf1(x2, x3);
+        wc_store(sm, t0, cw, x0);
+        wc_store(sm, t0 + 1, cw, x1);
+        wc_store(sm, t0 + 2, cw, x2);
+        wc_store(sm, t0 + 3, cw, x3);
+    }
+}
+B200_HD void wc_phase_store(const NttPassParams& p, const uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid, uint32_t nthreads) {
+    WcTile T;
+    T.sm = sm;
+    ntt_phase_store_t(p, T, tile, batch, tid, nthreads);
 }
 
 // =============================================================================================

@@ -147,6 +147,21 @@ extern "C" int host_ntt_variant(uint32_t* data, uint32_t log_n, uint32_t batch, 
                     for (uint32_t tid = 0; tid < nthreads; tid++) ntt_bulk_store_out(p, view(tid), tile, b, tid, nthreads);
                     continue;
                 }
+                if (variant == 2 && ntt_wc_applicable(p)) {
+                    // what ntt_pass_wc_kernel does: cooperative fill (128 threads), per warp (= column) three rounds
+                    // with all 32 lanes of a round before the next one, cooperative read-out
+                    std::vector<uint4> wsm(WC_TILE_U4), smtw((size_t)1 << WC_LOG_LEN);
+                    for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage_twiddles(p, smtw.data(), tid, 128);
+                    const NttTwiddles twd = ntt_shared_twiddles(smtw.data(), WC_LOG_LEN);
+                    for (uint32_t tid = 0; tid < 128; tid++) wc_phase_load(p, wsm.data(), tile, b, tid, 128);
+                    for (uint32_t cw = 0; cw < 4; cw++) {
+                        for (uint32_t lane = 0; lane < 32; lane++) wc_round1(p, wsm.data(), twd, tile, cw, lane);
+                        for (uint32_t lane = 0; lane < 32; lane++) wc_round2(wsm.data(), twd, cw, lane);
+                        for (uint32_t lane = 0; lane < 32; lane++) wc_round3(wsm.data(), twd, cw, lane);
+                    }
+                    for (uint32_t tid = 0; tid < 128; tid++) wc_phase_store(p, wsm.data(), tile, b, tid, 128);
+                    continue;
+                }
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);
                 if (p.coset_pre)
                     for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, nthreads);

@@ -178,3 +178,33 @@ def test_bulk_copy_tma_variant_matches_oracle(b200_opt, log_n, batch, tile_log):
             want = C.ntt(flat[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
             assert np.array_equal(buf[b * stride:b * stride + n], want), (direction, coset, b)
             assert np.array_equal(buf[b * stride + n:(b + 1) * stride], flat[b * stride + n:(b + 1) * stride])
+
+
+@pytest.mark.parametrize("log_n,plan", [(10, "8,2"), (10, "2,8"), (12, "2,8,2"), (16, "8,8"), (18, "8,8,2"), (24, "8,8,8")])
+def test_warp_column_kernel_matches_generic_and_oracle(b200_opt, log_n, plan):
+    """ntt_pass_wc_kernel (one warp per 2^8 column, in-register radix-8 rounds) in first / middle / last position: same
+    bytes as the default pass kernel for all four transform kinds, and the oracle up to 2^18 (ntt_variant = 4: the
+    kernel is an opt-in variant, measured slower than the default -- see ntt.cu)"""
+    import ctypes
+    import torch
+    from snarkos_b200 import _lib
+    b200_opt("ntt_plan", plan)
+    n = 1 << log_n
+    batch = 2 if log_n <= 18 else 1
+    stride = n + (5 if log_n <= 18 else 0)
+    rng = np.random.default_rng(4000 + log_n)
+    flat = H.random_fr_mont_np(rng, (batch * stride,))
+    L = _lib.lib()
+    for direction, coset in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        outs = []
+        for variant in (4, 0):
+            b200_opt("ntt_variant", variant)
+            buf = flat.copy()
+            _lib.check(L.b200_ntt_fr_bls12_377(buf.ctypes.data_as(ctypes.c_void_p), log_n, batch, stride, direction, coset))
+            outs.append(buf)
+        assert np.array_equal(outs[0], outs[1]), (direction, coset)
+        if log_n <= 18:
+            for b in range(batch):
+                want = C.ntt(flat[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
+                assert np.array_equal(outs[0][b * stride:b * stride + n], want), (direction, coset, b)
+                assert np.array_equal(outs[0][b * stride + n:(b + 1) * stride], flat[b * stride + n:(b + 1) * stride])

@@ -95,3 +95,28 @@ def test_planner_invariants(hostlib):
             else:
                 assert W[i] <= L[0]
             before += L[i]
+
+
+WC_SHAPES = [
+    (10, (8, 2), (2, 2)),              # warp-column strided pass + generic last pass
+    (10, (2, 8), (2, 2)),              # generic strided pass + warp-column LAST pass (digit reversal, t-fastest fill)
+    (16, (8, 8), (2, 2)),              # both passes warp-column (the 2^16 plan)
+    (12, (2, 8, 2), (2, 2, 2)),        # warp-column middle pass
+]
+
+
+@pytest.mark.parametrize("log_n,lens,cws", WC_SHAPES)
+@pytest.mark.parametrize("direction,coset", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_warp_column_passes_match_oracle(hostlib, log_n, lens, cws, direction, coset):
+    """ntt_pass_wc_kernel's phases (one warp per 2^8 column, 8 elements per lane, three in-register rounds, swizzled
+    shared layout) emulated lane by lane: bit-exact against the oracle for all four transform kinds, first / middle /
+    last position of the pass, padded batch stride"""
+    n = 1 << log_n
+    rng = np.random.default_rng(7000 + log_n + 2 * direction + coset)
+    batch, stride = 2, n + 3
+    data = H.random_fr_mont_np(rng, (stride * (batch - 1) + n,))
+    got = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=16, variant=2)
+    want = data.copy()
+    for b in range(batch):
+        want[b * stride:b * stride + n] = C.ntt(data[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
+    assert np.array_equal(got, want)

@@ -9,13 +9,19 @@ import snarkos_b200 as S
 
 S.init(0)
 out = []
-for log_n, batch in ((24, 1), (20, 16), (16, 64), (26, 1)):
+CONFIGS = ((0, 11, ""), (0, 10, ""), (1, 10, ""), (1, 11, ""), (1, 9, ""))
+if os.environ.get("NTT_CONFIGS"):            # "variant:tile_log:plan;..." e.g. "0:11:;2:10:;2:10:8,8,8"
+    CONFIGS = tuple((int(a), int(b), c) for a, b, c in (x.split(":") for x in os.environ["NTT_CONFIGS"].split(";")))
+SIZES = ((24, 1), (20, 16), (16, 64), (26, 1))
+if os.environ.get("NTT_SIZES"):              # "log_n:batch;..."
+    SIZES = tuple((int(a), int(b)) for a, b in (x.split(":") for x in os.environ["NTT_SIZES"].split(";")))
+for log_n, batch in SIZES:
     n = 1 << log_n
     gen = torch.Generator(device="cuda"); gen.manual_seed(log_n)
     src = torch.randint(0, 1 << 59, (batch, n, 4), dtype=torch.int64, device="cuda", generator=gen)
     d = S.EvaluationDomain(n)
     ref = None
-    for variant, tile_log, plan in ((0, 11, ""), (0, 10, ""), (1, 10, ""), (1, 11, ""), (1, 9, "")):
+    for variant, tile_log, plan in CONFIGS:
         S.set_option("ntt_variant", variant); S.set_option("ntt_tile_log", tile_log); S.set_option("ntt_plan", plan)
         try:
             x = src.clone()
@@ -33,7 +39,7 @@ for log_n, batch in ((24, 1), (20, 16), (16, 64), (26, 1)):
             torch.cuda.synchronize()
             with S.profile() as prof:
                 d.fft_in_place(x)
-            rec = {"log_n": log_n, "batch": batch, "variant": variant, "tile_log": tile_log, "ms": e0.elapsed_time(e1) / reps,
+            rec = {"log_n": log_n, "batch": batch, "variant": variant, "tile_log": tile_log, "plan": plan, "ms": e0.elapsed_time(e1) / reps,
                    "gelem_s": n * batch / (e0.elapsed_time(e1) / reps * 1e-3) / 1e9, "same_bytes": same, "stages": prof.totals()}
         except Exception as ex:
             rec = {"log_n": log_n, "batch": batch, "variant": variant, "tile_log": tile_log, "error": repr(ex)}
