@@ -536,38 +536,23 @@ def run_b200(args):
         t_gpu = (time.perf_counter() - t0) / reps
         batch_verify = {"workload": f"{n_tx} independent MSMs x {per} points (KZG10::batch_check linear combinations of a block)",
                         "e2e_ms": t_gpu * 1e3, "msms_per_s": n_tx / t_gpu, "api": "snarkos_b200.msm_batch -> b200_msm_batch_g1_bls12_377 (host buffers)"}
-        # the same 256 MSMs arriving from 64 host threads at once through the coalescing queue (b200_msm_submit / _wait):
-        # what the validator's parallel transaction checks look like at the C ABI
-        import ctypes as ct
-        import threading
-        L = S.lib()
-        outq = np.zeros((n_tx, 144), dtype=np.uint8)
-        n_thr = 64
-
-        def verify_worker(t, barrier_):
-            barrier_.wait()
-            for m in range(t, n_tx, n_thr):
-                tk = ct.c_uint64(0)
-                L.b200_msm_submit(hb[m * per * 104:].ctypes.data_as(ct.c_void_p), per, hs[m * per:].ctypes.data_as(ct.c_void_p), 104, ct.byref(tk))
-                L.b200_msm_wait(tk.value, outq[m].ctypes.data_as(ct.c_void_p))
-
-        best = None
-        b0 = S.counter("queue_batches")
-        for rep in range(4):
-            bar = threading.Barrier(n_thr + 1)
-            ths = [threading.Thread(target=verify_worker, args=(t, bar)) for t in range(n_thr)]
-            for th in ths:
-                th.start()
-            bar.wait()
-            t0 = time.perf_counter()
-            for th in ths:
-                th.join()
-            dt = time.perf_counter() - t0
-            if rep and (best is None or dt < best):
-                best = dt
-        batch_verify["queued_64_threads_ms"] = best * 1e3
-        batch_verify["queued_batches_per_block"] = (S.counter("queue_batches") - b0) / 4
-        batch_verify["queued_api"] = "b200_msm_submit + b200_msm_wait from 64 threads, 4 MSMs each (python threads: includes GIL hand-offs)"
+        # the same kind of load arriving from NATIVE host threads at once (tools/queue_bench.cpp: 256 threads x 1 MSM and
+        # 64 threads x 4 MSMs of 40 points, its own synthetic points): every thread calling b200_msm_g1_bls12_377 itself,
+        # versus the coalescing queue (b200_msm_submit / b200_msm_wait), versus one batch call.  Python threads cannot
+        # show this (the GIL serialises the submits), so the C ABI is driven by a small C++ program here.
+        import subprocess
+        qb = os.path.join(os.path.dirname(os.path.abspath(__file__)), "snarkos_b200", "csrc", "build", "queue_bench")
+        if os.path.exists(qb):
+            native = []
+            for thr, per_thr in ((256, 1), (64, 4)):
+                try:
+                    r = subprocess.run([qb, str(thr), str(per_thr), str(per), "5"], capture_output=True, text=True, timeout=300)
+                    native.append(json.loads(r.stdout.strip().splitlines()[-1]))
+                except Exception as ex:      # noqa: BLE001
+                    native.append({"threads": thr, "error": repr(ex)})
+            batch_verify["native_threads"] = native
+            batch_verify["native_threads_api"] = ("direct_ms: every thread calls b200_msm_g1_bls12_377; queued_ms: b200_msm_submit + "
+                                                  "b200_msm_wait (coalescing dispatcher); one_batch_call_ms: b200_msm_batch_g1_bls12_377")
         if not args.no_cpu_baseline:
             from oracle import c_oracle as C
             C.msm_many(hb, hs, off, nthreads=host_threads())
@@ -577,6 +562,51 @@ def run_b200(args):
             batch_verify["cpu_port_ms"] = t_cpu * 1e3
             batch_verify["cpu_port_note"] = (f"the same 256 MSMs through the batched::msm port, one task per MSM on {host_threads()} threads "
                                              f"(the reference verifies a block's transactions rayon-parallel)")
+
+    # ---- BASELINE configs[2] shape: an end-to-end prover with Varuna's round structure at Varuna's domain sizes ---------
+    # (stand-in protocol, see snarkos_b200/varuna.py: the real AHP lives in snarkVM sources that are not on disk)
+    prover = None
+    if world == 1:
+        prover = {"workload": "stand-in row-check prover with Varuna's shape: batched iFFT + 3 commits, coset-FFT quotient + commit, "
+                              "4 evaluations + combined KZG opening; proof = 5 compressed G1 + 4 Fr (368 B); witness uploaded from "
+                              "pinned host memory, challenges hashed on the host between rounds", "sizes": {}}
+        from oracle import rowcheck_prover as RP
+        for lg in (14, 16, 17):
+            nn = 1 << lg
+            pw = S.Powers(bases[: nn * 104])
+            wit = torch.from_numpy(RP.random_witness(np.random.default_rng(lg), lg).view(np.int64)).pin_memory()
+            pr = S.varuna.RowCheckProver(pw, lg)
+            proof = pr.prove(wit.cuda())
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                proof = pr.prove(wit.cuda(non_blocking=True))
+            t_gpu = (time.perf_counter() - t0) / reps
+            rec = {"prove_ms": t_gpu * 1e3, "h2d_bytes": 3 * nn * 32, "proof_bytes": len(proof)}
+            # commitments of one round in one launch set vs one call each; one opening
+            cs = [torch.from_numpy(RP.random_witness(np.random.default_rng(lg + k), lg)[k % 2].view(np.int64)).cuda() for k in range(8)]
+            S.KZG10.commit_batch(pw, cs); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                S.KZG10.commit_batch(pw, cs)
+            torch.cuda.synchronize()
+            rec["commit_batch_x8_ms"] = (time.perf_counter() - t0) / reps * 1e3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for c_ in cs:
+                    S.KZG10.commit(pw, c_)
+            torch.cuda.synchronize()
+            rec["commit_x8_one_by_one_ms"] = (time.perf_counter() - t0) / reps * 1e3
+            if not args.no_cpu_baseline and lg <= 16:
+                hbp = bases[: nn * 104].cpu().numpy()
+                t0 = time.perf_counter()
+                want = RP.prove(hbp, lg, wit.numpy().view(np.uint64))
+                rec["cpu_twin_prove_ms"] = (time.perf_counter() - t0) * 1e3
+                rec["proof_bytes_identical"] = bool(want == proof)
+            prover["sizes"][f"2^{lg}"] = rec
+            pw.release()
+        prover["cpu_twin_note"] = (f"oracle/rowcheck_prover.py: the same protocol on the C oracle (NTT, batched::msm port, {host_threads()} threads) "
+                                   "with Python big-int glue (Horner evaluations, combination, witness division: single-threaded)")
 
     # ---- BASELINE configs[0]: 2^16 random bases / scalars through VariableBase::msm (rank 0, N = 1) ----------------------
     config0 = None
@@ -629,6 +659,8 @@ def run_b200(args):
     }
     if batch_verify is not None:
         line["batch_verify_msm"] = batch_verify
+    if prover is not None:
+        line["config2_prover_shape"] = prover
     if config0 is not None:
         line["config0_msm_2^16"] = config0
     if strong is not None:

@@ -70,7 +70,8 @@ uint32_t b200_abi_version(void);
  * staged_copies, graphs.  Unknown key -> B200_ERR_INVALID_ARG. */
 b200_error_t b200_set_option(const char* key, const char* value);
 /* Observable fallbacks / activity: kernel_launches, msm_xyzz_fallbacks (calls whose pair-round lists did not fit in HBM
- * and ran the XYZZ-only accumulation), queue_submits, queue_batches, graph_captures, graph_replays. */
+ * and ran the XYZZ-only accumulation), queue_submits, queue_batches, graph_captures, graph_replays, streams_created (per-thread
+ * CUDA streams alive: bounded by the number of threads calling at the same time, exited threads hand theirs back). */
 b200_error_t b200_get_counter(const char* name, uint64_t* out);
 
 /* ---- VariableBase::msm ------------------------------------------------------------------------

@@ -24,18 +24,59 @@ struct ApiState {
     std::unordered_map<uint64_t, RegisteredBases> bases;
     uint64_t next_handle = 1;
     std::vector<cudaStream_t> streams;       // every per-thread stream ever created (for shutdown)
+    std::vector<cudaStream_t> free_streams[2];   // streams handed back by threads that exited ([1]: high priority)
+    std::vector<cudaStream_t> kind_streams[2];   // all streams of a kind, for sharing once the cap is reached
+    size_t shared_rr[2] = {0, 0};
     uint64_t generation = 0;                 // bumped by every successful b200_init: stale per-thread streams are dropped
     bool generator_uploaded = false;         // c_gen_x / c_gen_y live in the bound device's constant memory
 };
-static ApiState g_api;
+// never destroyed: thread_local destructors of late-exiting threads still hand their streams back to it
+static ApiState& g_api = *new ApiState();
 
+// Callers are rayon workers and tokio blocking threads (up to 512, created and RETIRED by the runtime --
+// /root/reference/cli/src/commands/start.rs:623-640): a stream per thread that is never given back piles up thousands
+// of streams, and every stream-ordered allocation and synchronisation slows down with them (measured with
+// tools/queue_bench.cpp: a 256-MSM batch call went from 3 ms to 66 ms after 256 short-lived threads per repetition).
+// A thread hands its streams back when it exits; a new thread takes them over.
+#define B200_MAX_STREAMS_PER_KIND 96u         /* main + two copy streams per caller: 32 callers with streams of their own */
 struct ThreadStream {
     cudaStream_t s = nullptr;
     uint64_t generation = 0;
+    int kind = 0;
+    bool shared = false;                     // taken round-robin from the capped pool: not this thread's to hand back
+    ~ThreadStream() {
+        if (!s || shared) return;
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        if (generation == g_api.generation && g_api.initialized) g_api.free_streams[kind].push_back(s);
+    }
 };
 // the calling thread's stream of this kind, (re)created when the library was shut down and bound again
 static cudaStream_t thread_stream_get(ThreadStream& t, bool high_priority) {
     if (t.s && t.generation == g_api.generation) return t.s;
+    const int kind = high_priority ? 1 : 0;
+    {
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        if (!g_api.free_streams[kind].empty()) {
+            t.s = g_api.free_streams[kind].back();
+            g_api.free_streams[kind].pop_back();
+            t.generation = g_api.generation;
+            t.kind = kind;
+            t.shared = false;
+            return t.s;
+        }
+        // Cap: beyond B200_MAX_STREAMS_PER_KIND live streams further threads SHARE one round-robin.  The GPU does not run
+        // more grids than that side by side anyway, while the stream-ordered allocator gets slower with every stream that
+        // holds freed blocks (a 256-MSM batch call: 3.8 ms with 16 caller threads alive, 16 ms with 256, 30 ms with 512).
+        // Work of two threads on one stream is simply ordered; each caller still waits for its own results only after
+        // its own enqueue.
+        if (g_api.kind_streams[kind].size() >= B200_MAX_STREAMS_PER_KIND) {
+            t.s = g_api.kind_streams[kind][g_api.shared_rr[kind]++ % g_api.kind_streams[kind].size()];
+            t.generation = g_api.generation;
+            t.kind = kind;
+            t.shared = true;
+            return t.s;
+        }
+    }
     cudaStream_t s = nullptr;
     cudaError_t e;
     if (high_priority) {
@@ -49,7 +90,10 @@ static cudaStream_t thread_stream_get(ThreadStream& t, bool high_priority) {
     std::lock_guard<std::mutex> lock(g_api.mu);
     t.s = s;
     t.generation = g_api.generation;
+    t.kind = kind;
+    t.shared = false;
     g_api.streams.push_back(s);
+    g_api.kind_streams[kind].push_back(s);
     return s;
 }
 static thread_local ThreadStream t_stream;
@@ -62,6 +106,100 @@ static thread_local ThreadStream t_aux_stream;
 cudaStream_t b200_thread_aux_stream() { return thread_stream_get(t_aux_stream, true); }
 
 B200Counters g_counters;
+
+// ---------------------------------------------------------------------------------------------
+// scratch cache (see common.cuh)
+// ---------------------------------------------------------------------------------------------
+#define SCRATCH_MAX_CACHED_BLOCK ((size_t)64 << 20)
+#define SCRATCH_MAX_CACHED_TOTAL ((size_t)1 << 30)        /* per thread */
+struct ScratchCache {
+    std::mutex mu;                                          // uncontended: the owner thread, and b200_shutdown
+    struct Key { cudaStream_t s; uint32_t cls; bool operator<(const Key& o) const { return s != o.s ? s < o.s : cls < o.cls; } };
+    std::map<Key, std::vector<void*>> free_blocks;
+    size_t cached_bytes = 0;
+    uint64_t generation = 0;
+    ScratchCache();
+    ~ScratchCache();
+};
+struct ScratchRegistry {
+    std::mutex mu;
+    std::vector<ScratchCache*> caches;
+};
+static ScratchRegistry& g_scratch = *new ScratchRegistry();
+ScratchCache::ScratchCache() {
+    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    g_scratch.caches.push_back(this);
+}
+static void scratch_drop_locked(ScratchCache& c, bool free_blocks) {
+    if (free_blocks)
+        for (auto& kv : c.free_blocks)
+            for (void* p : kv.second) cudaFreeAsync(p, kv.first.s);
+    c.free_blocks.clear();
+    c.cached_bytes = 0;
+}
+ScratchCache::~ScratchCache() {
+    {
+        std::lock_guard<std::mutex> lock(g_scratch.mu);
+        for (size_t i = 0; i < g_scratch.caches.size(); i++)
+            if (g_scratch.caches[i] == this) { g_scratch.caches.erase(g_scratch.caches.begin() + i); break; }
+    }
+    // a retiring thread gives its blocks back to the driver pool (its stream goes to the next thread); at process exit
+    // the library may already be shut down, then the blocks went with it.  (g_api.mu is never taken under a cache
+    // mutex: b200_shutdown holds it while it walks the registry.)
+    bool live;
+    {
+        std::lock_guard<std::mutex> l2(g_api.mu);
+        live = g_api.initialized && generation == g_api.generation;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    scratch_drop_locked(*this, live);
+}
+static thread_local ScratchCache t_scratch;
+
+static uint32_t scratch_class(size_t bytes) {
+    uint32_t c = 8;                                         // 256 B minimum
+    while (((size_t)1 << c) < bytes) c++;
+    return c;
+}
+cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
+    if (bytes > SCRATCH_MAX_CACHED_BLOCK) return cudaMallocAsync(p, bytes, stream);
+    const uint32_t cls = scratch_class(bytes);
+    ScratchCache& c = t_scratch;
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (c.generation != g_api.generation) {             // the library was shut down and bound again: old blocks are gone
+            scratch_drop_locked(c, false);
+            c.generation = g_api.generation;
+        }
+        auto it = c.free_blocks.find(ScratchCache::Key{stream, cls});
+        if (it != c.free_blocks.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            c.cached_bytes -= (size_t)1 << cls;
+            return cudaSuccess;
+        }
+    }
+    return cudaMallocAsync(p, (size_t)1 << cls, stream);
+}
+void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream) {
+    if (bytes > SCRATCH_MAX_CACHED_BLOCK) { cudaFreeAsync(p, stream); return; }
+    const uint32_t cls = scratch_class(bytes);
+    ScratchCache& c = t_scratch;
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.generation != g_api.generation || c.cached_bytes + ((size_t)1 << cls) > SCRATCH_MAX_CACHED_TOTAL) {
+        if (c.generation == g_api.generation) cudaFreeAsync(p, stream);
+        return;
+    }
+    c.free_blocks[ScratchCache::Key{stream, cls}].push_back(p);
+    c.cached_bytes += (size_t)1 << cls;
+}
+void b200_scratch_release_all() {
+    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    for (ScratchCache* c : g_scratch.caches) {
+        std::lock_guard<std::mutex> l2(c->mu);
+        scratch_drop_locked(*c, true);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // tuning knobs: environment read once, b200_set_option afterwards
@@ -135,6 +273,10 @@ extern "C" b200_error_t b200_get_counter(const char* name, uint64_t* out) {
     else if (k == "queue_batches") *out = g_counters.queue_batches.load();
     else if (k == "graph_replays") *out = g_counters.graph_replays.load();
     else if (k == "graph_captures") *out = g_counters.graph_captures.load();
+    else if (k == "streams_created") {
+        std::lock_guard<std::mutex> lock(g_api.mu);
+        *out = g_api.streams.size();
+    }
     else return b200_err(B200_ERR_INVALID_ARG, "get_counter: unknown counter");
     return b200_ok();
 }
@@ -203,12 +345,14 @@ extern "C" void b200_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto& kv : g_api.bases) cudaFree(kv.second.d_packed);
     g_api.bases.clear();
+    b200_scratch_release_all();
     ntt_release_tables();
     msm_release_graphs();
     hostcopy_release();
     // per-thread streams: the owning threads notice the new generation and create fresh ones on their next call
     for (cudaStream_t s : g_api.streams) cudaStreamDestroy(s);
     g_api.streams.clear();
+    for (int k = 0; k < 2; k++) { g_api.free_streams[k].clear(); g_api.kind_streams[k].clear(); g_api.shared_rr[k] = 0; }
     g_api.generator_uploaded = false;
     g_api.initialized = false;
     g_api.device = -1;

@@ -72,18 +72,30 @@ struct B200Counters {
 };
 extern B200Counters g_counters;
 
+// Stream-ordered scratch (api.cu): blocks up to 64 MiB are recycled through a per-thread, per-stream cache in power-of-two
+// size classes, so a call in steady state makes no allocator call at all; larger blocks go to cudaMallocAsync /
+// cudaFreeAsync directly.  Reuse on the SAME stream needs no synchronisation, and -- unlike the driver's pool -- a block
+// freed by one caller thread is never handed to another stream: with hundreds of caller threads the driver pool's
+// cross-stream reuse put milliseconds of waits into every small call (tools/queue_bench.cpp: a 256-MSM batch call took
+// 3.4 ms after 16 caller threads had run and 12.8 ms after 256; stage events showed the time inside the allocations).
+cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream);
+void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream);
+void b200_scratch_release_all();     // b200_shutdown
+
 // stream-ordered scratch buffer (freed on the same stream when it goes out of scope)
 struct DevBuf {
     void* p = nullptr;
     cudaStream_t s = nullptr;
+    size_t bytes = 0;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+    cudaError_t alloc(size_t nbytes, cudaStream_t stream) {
         s = stream;
-        return cudaMallocAsync(&p, bytes ? bytes : 16, stream);
+        bytes = nbytes ? nbytes : 16;
+        return b200_scratch_alloc(&p, bytes, stream);
     }
-    void release() { if (p) cudaFreeAsync(p, s); p = nullptr; }
+    void release() { if (p) b200_scratch_free(p, bytes, s); p = nullptr; }
     ~DevBuf() { release(); }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };

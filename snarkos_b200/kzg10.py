@@ -105,6 +105,17 @@ class KZG10:
         gamma powers -- and the evaluations.  Host inputs: Montgomery [n, 4] uint64 coefficients, [4] uint64 point.
         Returns (w: uint8[144], p(z): uint64[4], random_v: uint64[4] or None)."""
         L = _lib.lib()
+        if _is_cuda_tensor(polynomial_coeffs):
+            # device-resident form: coefficients and point are CUDA tensors; returns (w [144] uint8, p(z) [1, 4] int64) on
+            # the device, nothing synchronises (the hiding part is a second call by the caller)
+            c = polynomial_coeffs.contiguous()
+            n = c.numel() * c.element_size() // 32
+            out = _dev_out(c.device)
+            ev = torch.empty((1, 4), dtype=torch.int64, device=c.device)
+            _lib.check(L.b200_kzg_open_device(ctypes.c_void_p(out.data_ptr()), powers.powers_of_beta_g.handle,
+                                              ctypes.c_void_p(c.data_ptr()), n, ctypes.c_void_p(point.data_ptr()),
+                                              ctypes.c_void_p(ev.data_ptr()), _stream_ptr()))
+            return out, ev, None
         z = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
 
         def one(rb, coeffs):

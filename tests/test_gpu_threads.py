@@ -43,3 +43,38 @@ def test_concurrent_callers():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_short_lived_threads_do_not_pile_up_streams():
+    """tokio's blocking pool creates and retires threads: a thread hands its CUDA streams back when it exits and the next
+    thread takes them over, so the number of streams follows the number of CONCURRENT callers, not of threads ever seen
+    (thousands of streams slow every stream-ordered allocation: tools/queue_bench.cpp, 3 ms -> 66 ms per batch call)"""
+    import torch
+    import snarkos_b200 as S
+    n = 64
+    bases = S.synthetic_bases(n, seed=3)
+    torch.cuda.synchronize()
+    hb = bases.cpu().numpy()
+    sc = H.random_scalars_np(np.random.default_rng(1), n)
+    want = H.jac_bytes_to_affine(C.msm(hb, sc))
+    errors = []
+
+    def work():
+        try:
+            assert H.jac_bytes_to_affine(S.VariableBase.msm(hb, sc)) == want
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    def round_of(k):
+        ts = [threading.Thread(target=work) for _ in range(k)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    round_of(8)
+    before = S.counter("streams_created")
+    for _ in range(10):
+        round_of(8)
+    assert not errors, errors
+    assert S.counter("streams_created") <= before + 8, (before, S.counter("streams_created"))
