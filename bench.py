@@ -373,6 +373,8 @@ def run_b200(args):
     if not args.no_strong:
         L26 = args.strong_log_n
         per = (1 << L26) // world
+        S.release_scratch()                                         # the 2^24 steps' cached temporaries: this call has another shape
+        torch.cuda.empty_cache()
         Ks = min(K, 3)
         b26 = S.synthetic_bases(per, seed=26000 + rank)            # rank r holds points [r * per, (r + 1) * per)
         s26 = rand_limbs(per)

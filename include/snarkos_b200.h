@@ -61,6 +61,10 @@ enum { B200_NTT_FORWARD = 0, B200_NTT_INVERSE = 1 };
  * tables.  Idempotent.  b200_shutdown releases every cached table and registered base set. */
 b200_error_t b200_init(int device);
 void b200_shutdown(void);
+/* Hands every cached scratch block (per-thread, per-stream caches of the calls' temporaries, up to 40 GiB in total) back
+ * to the driver's pool and trims that pool: for a long-running node between proving bursts, or before another library
+ * needs the memory.  Never required for correctness: an allocation that fails does the same before it retries. */
+b200_error_t b200_release_scratch(void);
 /* ABI version of this header (for the -sys crate's build-time check). */
 uint32_t b200_abi_version(void);
 /* Tuning knobs.  The B200_* environment variables are read once, on first use; this call changes a knob afterwards

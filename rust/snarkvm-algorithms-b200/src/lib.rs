@@ -25,6 +25,7 @@ pub mod sys {
         pub fn b200_init(device: c_int) -> b200_error_t;
         pub fn b200_shutdown();
         pub fn b200_abi_version() -> u32;
+        pub fn b200_release_scratch() -> b200_error_t;
         pub fn b200_set_option(key: *const c_char, value: *const c_char) -> b200_error_t;
         pub fn b200_get_counter(name: *const c_char, out: *mut u64) -> b200_error_t;
         // VariableBase::msm

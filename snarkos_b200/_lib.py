@@ -27,6 +27,7 @@ SYMBOLS = {
     "b200_init": (b200_error_t, [_i]),
     "b200_shutdown": (None, []),
     "b200_abi_version": (_u32, []),
+    "b200_release_scratch": (b200_error_t, []),
     "b200_set_option": (b200_error_t, [ctypes.c_char_p, ctypes.c_char_p]),
     "b200_get_counter": (b200_error_t, [ctypes.c_char_p, ctypes.POINTER(_u64)]),
     "b200_msm_submit": (b200_error_t, [_vp, _sz, _vp, _sz, ctypes.POINTER(_u64)]),
@@ -140,6 +141,11 @@ def counter(name: str) -> int:
     v = _u64(0)
     check(lib().b200_get_counter(name.encode(), ctypes.byref(v)))
     return int(v.value)
+
+
+def release_scratch() -> None:
+    """b200_release_scratch: hand all cached scratch memory back to the driver (and trim its pool)"""
+    check(lib().b200_release_scratch())
 
 
 def kernel_launch_count() -> int:

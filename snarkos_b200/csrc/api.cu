@@ -110,13 +110,17 @@ B200Counters g_counters;
 // ---------------------------------------------------------------------------------------------
 // scratch cache (see common.cuh)
 // ---------------------------------------------------------------------------------------------
-#define SCRATCH_MAX_CACHED_BLOCK ((size_t)64 << 20)
-#define SCRATCH_MAX_CACHED_TOTAL ((size_t)1 << 30)        /* per thread */
+// size classes: powers of two up to 64 MiB, eighths of an octave above (<= 12.5 % over-allocation on the GB-sized lists
+// of a large MSM); one budget for everything the caches of all threads hold
+#define SCRATCH_POW2_LIMIT ((size_t)64 << 20)
+#define SCRATCH_GLOBAL_BUDGET ((size_t)40 << 30)
+static std::atomic<size_t> g_scratch_cached{0};
 struct ScratchCache {
-    std::mutex mu;                                          // uncontended: the owner thread, and b200_shutdown
-    struct Key { cudaStream_t s; uint32_t cls; bool operator<(const Key& o) const { return s != o.s ? s < o.s : cls < o.cls; } };
-    std::map<Key, std::vector<void*>> free_blocks;
-    size_t cached_bytes = 0;
+    std::mutex mu;                                          // uncontended: the owner thread, and b200_shutdown / out-of-memory
+    struct Key { cudaStream_t s; size_t bytes; bool operator<(const Key& o) const { return s != o.s ? s < o.s : bytes < o.bytes; } };
+    struct Block { void* p; uint64_t tick; };
+    std::map<Key, std::vector<Block>> free_blocks;
+    uint64_t tick = 0;                                      // last-use order, for eviction
     uint64_t generation = 0;
     ScratchCache();
     ~ScratchCache();
@@ -131,11 +135,12 @@ ScratchCache::ScratchCache() {
     g_scratch.caches.push_back(this);
 }
 static void scratch_drop_locked(ScratchCache& c, bool free_blocks) {
-    if (free_blocks)
-        for (auto& kv : c.free_blocks)
-            for (void* p : kv.second) cudaFreeAsync(p, kv.first.s);
+    for (auto& kv : c.free_blocks) {
+        if (free_blocks)
+            for (auto& b : kv.second) cudaFreeAsync(b.p, kv.first.s);
+        g_scratch_cached.fetch_sub(kv.first.bytes * kv.second.size());
+    }
     c.free_blocks.clear();
-    c.cached_bytes = 0;
 }
 ScratchCache::~ScratchCache() {
     {
@@ -156,14 +161,19 @@ ScratchCache::~ScratchCache() {
 }
 static thread_local ScratchCache t_scratch;
 
-static uint32_t scratch_class(size_t bytes) {
-    uint32_t c = 8;                                         // 256 B minimum
-    while (((size_t)1 << c) < bytes) c++;
-    return c;
+static size_t scratch_round(size_t bytes) {
+    if (bytes <= SCRATCH_POW2_LIMIT) {
+        size_t c = 256;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+    size_t top = SCRATCH_POW2_LIMIT;
+    while ((top << 1) <= bytes) top <<= 1;                  // largest power of two <= bytes
+    const size_t step = top >> 3;
+    return (bytes + step - 1) / step * step;
 }
 cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
-    if (bytes > SCRATCH_MAX_CACHED_BLOCK) return cudaMallocAsync(p, bytes, stream);
-    const uint32_t cls = scratch_class(bytes);
+    const size_t rounded = scratch_round(bytes);
     ScratchCache& c = t_scratch;
     {
         std::lock_guard<std::mutex> lock(c.mu);
@@ -171,27 +181,47 @@ cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
             scratch_drop_locked(c, false);
             c.generation = g_api.generation;
         }
-        auto it = c.free_blocks.find(ScratchCache::Key{stream, cls});
+        auto it = c.free_blocks.find(ScratchCache::Key{stream, rounded});
         if (it != c.free_blocks.end() && !it->second.empty()) {
-            *p = it->second.back();
+            *p = it->second.back().p;
             it->second.pop_back();
-            c.cached_bytes -= (size_t)1 << cls;
+            g_scratch_cached.fetch_sub(rounded);
             return cudaSuccess;
         }
     }
-    return cudaMallocAsync(p, (size_t)1 << cls, stream);
+    cudaError_t e = cudaMallocAsync(p, rounded, stream);
+    if (e == cudaErrorMemoryAllocation) {                   // give everything cached back to the driver and try once more
+        (void)cudaGetLastError();
+        b200_scratch_release_all();
+        e = cudaMallocAsync(p, rounded, stream);
+    }
+    return e;
 }
 void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream) {
-    if (bytes > SCRATCH_MAX_CACHED_BLOCK) { cudaFreeAsync(p, stream); return; }
-    const uint32_t cls = scratch_class(bytes);
+    const size_t rounded = scratch_round(bytes);
     ScratchCache& c = t_scratch;
     std::lock_guard<std::mutex> lock(c.mu);
-    if (c.generation != g_api.generation || c.cached_bytes + ((size_t)1 << cls) > SCRATCH_MAX_CACHED_TOTAL) {
-        if (c.generation == g_api.generation) cudaFreeAsync(p, stream);
+    if (c.generation != g_api.generation) return;           // belongs to a library instance that was shut down
+    if (rounded > SCRATCH_GLOBAL_BUDGET / 2) {              // a block of this size would evict everything else
+        cudaFreeAsync(p, stream);
         return;
     }
-    c.free_blocks[ScratchCache::Key{stream, cls}].push_back(p);
-    c.cached_bytes += (size_t)1 << cls;
+    c.free_blocks[ScratchCache::Key{stream, rounded}].push_back(ScratchCache::Block{p, ++c.tick});
+    g_scratch_cached.fetch_add(rounded);
+    // over budget: this thread's least recently used blocks go back to the driver (a call of another shape, or on
+    // another stream, left them behind)
+    while (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET) {
+        std::map<ScratchCache::Key, std::vector<ScratchCache::Block>>::iterator oldest = c.free_blocks.end();
+        size_t oldest_i = 0;
+        for (auto it = c.free_blocks.begin(); it != c.free_blocks.end(); ++it)
+            for (size_t i = 0; i < it->second.size(); i++)
+                if (oldest == c.free_blocks.end() || it->second[i].tick < oldest->second[oldest_i].tick) { oldest = it; oldest_i = i; }
+        if (oldest == c.free_blocks.end()) break;           // the rest belongs to other threads
+        cudaFreeAsync(oldest->second[oldest_i].p, oldest->first.s);
+        g_scratch_cached.fetch_sub(oldest->first.bytes);
+        oldest->second.erase(oldest->second.begin() + oldest_i);
+        if (oldest->second.empty()) c.free_blocks.erase(oldest);
+    }
 }
 void b200_scratch_release_all() {
     std::lock_guard<std::mutex> lock(g_scratch.mu);
@@ -292,6 +322,16 @@ b200_error_t b200_require_device() {
     return b200_init(-1);
 }
 
+extern "C" b200_error_t b200_release_scratch(void) {
+    B200_TRY(b200_require_device());
+    b200_scratch_release_all();
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return b200_ok();
+}
 extern "C" uint32_t b200_abi_version(void) { return 2; }
 extern "C" uint64_t b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
 

@@ -72,12 +72,14 @@ struct B200Counters {
 };
 extern B200Counters g_counters;
 
-// Stream-ordered scratch (api.cu): blocks up to 64 MiB are recycled through a per-thread, per-stream cache in power-of-two
-// size classes, so a call in steady state makes no allocator call at all; larger blocks go to cudaMallocAsync /
-// cudaFreeAsync directly.  Reuse on the SAME stream needs no synchronisation, and -- unlike the driver's pool -- a block
-// freed by one caller thread is never handed to another stream: with hundreds of caller threads the driver pool's
-// cross-stream reuse put milliseconds of waits into every small call (tools/queue_bench.cpp: a 256-MSM batch call took
-// 3.4 ms after 16 caller threads had run and 12.8 ms after 256; stage events showed the time inside the allocations).
+// Stream-ordered scratch (api.cu): blocks are recycled through a per-thread, per-stream cache -- size classes are powers
+// of two up to 64 MiB and eighths of an octave above, one 40 GiB budget for all caches together, everything handed back
+// to the driver when an allocation fails -- so a call in steady state makes no allocator call at all.  Reuse on the
+// SAME stream needs no synchronisation, and -- unlike the driver's pool -- a block freed by one caller thread is never
+// handed to another stream: with hundreds of caller threads the driver pool's cross-stream reuse put milliseconds of
+// waits into every small call (tools/queue_bench.cpp: a 256-MSM batch call took 3.4 ms after 16 caller threads had run
+// and 12.8 ms after 256; stage events showed the time inside the allocations), and even the GB-sized lists of a 2^24
+// MSM cost ~2 ms of stream time per call to obtain from it.
 cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream);
 void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream);
 void b200_scratch_release_all();     // b200_shutdown

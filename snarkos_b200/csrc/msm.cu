@@ -17,6 +17,7 @@
 #include "msm_core.cuh"
 #include "msm_affine.cuh"
 #include "msm_glv.cuh"
+#include "ec_coop.cuh"
 
 #define MSM_ACC_THREADS 128
 #define MSM_RED_THREADS 64
@@ -457,6 +458,41 @@ __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_segments_kernel(g1
     g1_xyzz_store(segs + t, r);
 }
 
+// The same segment sums with a quad of lanes per segment (ec_coop.cuh), for calls with so few segments that the
+// kernel is one dependent chain per thread on a mostly idle chip (a 2^16-point commit: 4096 segments, 16 additions and a
+// ~24-step double-and-add each: 0.69 ms with one lane per segment).
+__global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_segments_quad_kernel(g1_xyzz_mem_t* __restrict__ segs,
+                                                                                  const g1_xyzz_mem_t* __restrict__ buckets,
+                                                                                  MsmShape sh, uint32_t seg_len,
+                                                                                  uint32_t segs_per_win) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (t >= segs_per_win * sh.nwin) return;
+    const Quad Q = quad_here();
+    const uint32_t w = t / segs_per_win, s = t % segs_per_win;
+    const uint32_t s0 = s * seg_len;
+    const uint32_t len = sh.nbuckets - s0 < seg_len ? sh.nbuckets - s0 : seg_len;
+    const g1_xyzz_mem_t* b = buckets + (size_t)w * sh.nbuckets + s0;
+    g1_xyzz_t running = g1_xyzz_infinity(), acc = g1_xyzz_infinity();
+    for (uint32_t i = len; i-- > 0;) {
+        const g1_xyzz_t v = g1_xyzz_load(b + i);
+        g1_add_quad(Q, running, v);
+        g1_add_quad(Q, acc, running);
+    }
+    if (s0) {                                                  // + s0 * running, left-to-right double-and-add
+        g1_xyzz_t m = g1_xyzz_infinity();
+        bool started = false;
+        for (int i = 31 - __clz(s0); i >= 0; i--) {
+            if (started) g1_dbl_quad(Q, m);
+            if ((s0 >> i) & 1u) {
+                if (started) g1_add_quad(Q, m, running);
+                else { m = running; started = true; }
+            }
+        }
+        g1_add_quad(Q, acc, m);
+    }
+    if (Q.q == 0) g1_xyzz_store(segs + t, acc);
+}
+
 // Sum of the segment results of every window, in up to two levels: blockIdx.x = window, blockIdx.y = slice of that
 // window's `count` inputs (each block adds its slice: strided per-thread sums, then a shared-memory tree) and writes
 // out[window * gridDim.y + blockIdx.y].  The launcher runs it once with many slices per window and once more over the
@@ -496,12 +532,22 @@ __device__ __forceinline__ void store_jacobian(uint4* out, const g1_xyzz_t& p) {
     fq_to_u4x3(Z, out + 6);
 }
 
+// Horner over the windows, high window first: total = sum_w 2^(c*w) * W_w.  One dependent chain per MSM, so it is run
+// by a QUAD of lanes per MSM (ec_coop.cuh: the independent products of every doubling / addition on different lanes):
+// 3 product latencies per doubling instead of 9, 4 per addition instead of 14.
 __global__ void __launch_bounds__(32) msm_fold_kernel(uint4* __restrict__ out_jac, const g1_xyzz_mem_t* __restrict__ wsum,
                                                       MsmShape sh, uint32_t nmsm) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nmsm) return;
-    g1_xyzz_t total = msm_fold_windows(wsum + (size_t)m * sh.nwin, sh.nwin, sh.c);
-    store_jacobian(out_jac + 9 * (size_t)m, total);
+    const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (m >= nmsm) return;                                    // whole quads leave together
+    const Quad Q = quad_here();
+    const g1_xyzz_mem_t* w = wsum + (size_t)m * sh.nwin;
+    g1_xyzz_t total = g1_xyzz_infinity();
+    for (uint32_t i = sh.nwin; i-- > 0;) {
+        for (uint32_t k = 0; k < sh.c; k++) g1_dbl_quad(Q, total);
+        const g1_xyzz_t s = g1_xyzz_load(w + i);
+        g1_add_quad(Q, total, s);
+    }
+    if (Q.q == 0) store_jacobian(out_jac + 9 * (size_t)m, total);
 }
 
 __global__ void msm_write_infinity_kernel(uint4* out_jac, uint32_t count) {
@@ -950,8 +996,12 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
     CUDA_TRY(wsum.alloc((size_t)vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
     STAGE("msm_reduce_segments", stream);
     const uint32_t nseg_threads = pl.segs_per_win * vsh.nwin;
-    msm_reduce_segments_kernel<<<(nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
-        segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
+    if (nseg_threads <= 8192)          // latency-bound: four lanes per segment
+        msm_reduce_segments_quad_kernel<<<(4 * nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
+            segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
+    else
+        msm_reduce_segments_kernel<<<(nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
+            segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
     KERNEL_CHECK();
     STAGE("msm_window_sum", stream);
     {
@@ -976,8 +1026,8 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
     STAGE("msm_fold", stream);
     MsmShape fold_sh = pl.sh;
     if (pl.n_reg) fold_sh.nwin = 1;                          // tabulated: the single bucket set already carries 2^(c*w)
-    msm_fold_kernel<<<(pl.nmsm + 31) / 32, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(),
-                                                            fold_sh, pl.nmsm);
+    msm_fold_kernel<<<(pl.nmsm + 7) / 8, 32, 0, stream>>>(reinterpret_cast<uint4*>(d_out), wsum.as<g1_xyzz_mem_t>(),
+                                                          fold_sh, pl.nmsm);
     KERNEL_CHECK();
     STAGE_END(stream);
     return b200_ok();
