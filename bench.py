@@ -315,6 +315,8 @@ def run_b200(args):
             barrier()
             t7 = time.perf_counter()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rbt.msm(scalars)                                 # warm-up on THIS stream (scratch is cached per stream)
+            torch.cuda.synchronize()
             ev0.record()
             for _ in range(Ke):
                 rbt.msm(scalars)
