@@ -20,6 +20,53 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const NttPa
 // the same pass on 128-thread CTAs (option ntt_variant = 2): with 32 KB tiles six CTAs share an SM instead of three, so
 // that more CTAs are in their multiplier-bound stage phases while others load or store
 __global__ void __launch_bounds__(128, 6) ntt_pass_kernel_128(const NttPassParams p) { ntt_pass_body(p); }
+// Shape-specialised pass (ntt_core.cuh NttShape): 2^L x 2^CW = 1024-element tiles on 128 threads with every tile shift
+// and mask known at compile time, ONE code instance of the stage-pair body for all stage pairs (rolled loop: unrolling it
+// per stage pair makes the kernel slower -- 3.78 against 3.25 ms at 2^24 -- the hot loop no longer fits the
+// instruction cache), and a store phase that contains only what this pass needs (STORE 1: strided pass with its
+// boundary table; 2: last pass of a plain forward transform; 0: everything, chosen at run time).
+template <int L, int CW, int STORE>
+__global__ void __launch_bounds__(128, 6) ntt_pass_shaped_kernel(const NttPassParams p) {
+    typedef NttShape<L, CW, 128, 1, STORE> SH;
+    static_assert(L + CW == 10, "1024-element tiles");
+    extern __shared__ uint4 sm[];
+    const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x;
+    uint4* sm_tw = sm + 2 * 1024;
+    ntt_phase_stage_twiddles<SH>(p, sm_tw, tid, 128);
+    const NttTwiddles twd = ntt_shared_twiddles(sm_tw, L);
+    ntt_phase_load<SH>(p, sm, tile, batch, tid, 128);
+    __syncthreads();
+    if (STORE == 0 && p.coset_pre) {                          // the launcher sends forward coset passes to STORE 0
+        ntt_phase_coset_pre(p, sm, tile, tid, 128);
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int s = 0; s + 1 < L; s += 2) {
+        ntt_phase_stage2<SH>(p, sm, twd, s, tid, 128);
+        __syncthreads();
+    }
+    if (L & 1) {
+        ntt_phase_stage<SH>(p, sm, twd, L - 1, tid, 128);
+        __syncthreads();
+    }
+    ntt_phase_store<SH>(p, sm, tile, batch, tid, 128);
+}
+template <int L, int CW, int STORE> static cudaError_t ntt_shaped_attr() {
+    cudaError_t e = cudaFuncSetAttribute(ntt_pass_shaped_kernel<L, CW, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 + (1 << L) * 16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_shaped_kernel<L, CW, STORE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return e;
+}
+template <int L, int CW> static cudaError_t ntt_shaped_attrs() {
+    cudaError_t e = ntt_shaped_attr<L, CW, 0>();
+    if (e == cudaSuccess) e = ntt_shaped_attr<L, CW, 1>();
+    if (e == cudaSuccess) e = ntt_shaped_attr<L, CW, 2>();
+    return e;
+}
+template <int L, int CW> static void ntt_launch_shaped(int store, dim3 grid, size_t smem, cudaStream_t stream, const NttPassParams& p) {
+    if (store == 1) ntt_pass_shaped_kernel<L, CW, 1><<<grid, 128, smem, stream>>>(p);
+    else if (store == 2) ntt_pass_shaped_kernel<L, CW, 2><<<grid, 128, smem, stream>>>(p);
+    else ntt_pass_shaped_kernel<L, CW, 0><<<grid, 128, smem, stream>>>(p);
+}
 __device__ __forceinline__ void ntt_pass_body(const NttPassParams& p) {
     extern __shared__ uint4 sm[];
     const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
@@ -281,6 +328,9 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel_128, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (1 << NTT_MAX_TILE_LOG) * 32 + (1 << (NTT_MAX_TILE_LOG - 1)) * 32));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_kernel_128, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY((ntt_shaped_attrs<8, 2>()));
+        CUDA_TRY((ntt_shaped_attrs<7, 3>()));
+        CUDA_TRY((ntt_shaped_attrs<6, 4>()));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_wc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_WC_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_wc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -631,7 +681,16 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         const size_t smem = (size_t)tile_elems * 32 + ((size_t)1 << plan.log_len[i]) * 16;   // tile + L/2 twiddles
         // 1024-element tiles (the default): 128-thread CTAs, six per SM (measured 3.47 vs 3.57 ms at 2^24, 2.98 vs 3.26 ms at
         // 2^20 x 16 against 256-thread CTAs on 2048-element tiles); ntt_variant = 3 forces the 256-thread CTAs
-        if (tile_elems == 1024 && b200_config().ntt_variant != 3)
+        // shape-specialised kernels for the 1024-element tiles of the default plans (ntt_variant 2 / 3: generic kernels)
+        const bool shaped = b200_config().ntt_variant == 0 && b200_config().ntt_radix4;
+        const int store = (p.coset_pre || p.scale_post || p.coset_post) ? 0 : last ? (plan.npasses > 1 ? 2 : 0) : (p.boundary_tw ? 1 : 0);
+        if (shaped && plan.log_len[i] == 8 && plan.log_cw[i] == 2)
+            ntt_launch_shaped<8, 2>(store, grid, smem, stream, p);
+        else if (shaped && plan.log_len[i] == 7 && plan.log_cw[i] == 3)
+            ntt_launch_shaped<7, 3>(store, grid, smem, stream, p);
+        else if (shaped && plan.log_len[i] == 6 && plan.log_cw[i] == 4)
+            ntt_launch_shaped<6, 4>(store, grid, smem, stream, p);
+        else if (tile_elems == 1024 && b200_config().ntt_variant != 3)
             ntt_pass_kernel_128<<<grid, 128, smem, stream>>>(p);
         else
             ntt_pass_kernel<<<grid, threads, smem, stream>>>(p);

@@ -25,6 +25,11 @@
 #include "field.cuh"
 
 #define NTT_MAX_PASSES 4
+#if defined(__CUDACC__)
+#define B200_UNROLL_SHAPED _Pragma("unroll (SH::unroll)")
+#else
+#define B200_UNROLL_SHAPED
+#endif
 #define NTT_TILE_TW_LOG 12          // tile twiddle table: w_{2^12}^e, e < 2^11
 #define NTT_POW_LO_LOG 13           // two-level power tables: x^e = LO[e & 8191] * HI[e >> 13]
 
@@ -97,10 +102,23 @@ struct NttGeom {
     uint32_t tile_elems;                             // L * CW
     uint32_t log_tiles;                              // tiles per polynomial = N / (L * CW)
 };
-B200_HD NttGeom ntt_geom(const NttPassParams& p) {
+// Compile-time shape of a pass (length, tile width, threads per CTA): with it the stage loops have constant trip
+// counts and every shift / mask of the tile arithmetic folds into the instruction -- the specialised kernels of
+// ntt.cu; NttDyn (all -1) is the generic run-time form, also what the host shim exercises by default.
+// STORE: what the store phase of the pass has to do -- 0: anything (run-time flags); 1: strided pass with its boundary
+// twiddle table (exactly one product per element); 2: last pass of a plain forward transform (no product at all).
+// The generic store inlines six product sites per element (table / two-level twiddle, n^-1, coset powers) five times:
+// 60 % of the kernel's code for paths a forward transform never takes.
+template <int L, int CW, int NT, int UNR = 2, int STORE = 0> struct NttShape {
+    static constexpr int log_len = L, log_cw = CW, nthreads = NT, unroll = UNR, store = STORE;
+};
+typedef NttShape<-1, -1, -1, 1, 0> NttDyn;
+template <class SH> B200_HD uint32_t ntt_nthreads(uint32_t nthreads) { return SH::nthreads > 0 ? (uint32_t)SH::nthreads : nthreads; }
+
+template <class SH> B200_HD NttGeom ntt_geom_t(const NttPassParams& p) {
     NttGeom g;
-    g.log_len = p.log_len[p.pass];
-    g.log_cw = p.log_cw;
+    g.log_len = SH::log_len >= 0 ? (uint32_t)SH::log_len : p.log_len[p.pass];
+    g.log_cw = SH::log_cw >= 0 ? (uint32_t)SH::log_cw : p.log_cw;
     uint32_t before = 0;
     for (uint32_t i = 0; i < p.pass; i++) before += p.log_len[i];
     g.log_sub = p.log_n - before;
@@ -110,6 +128,7 @@ B200_HD NttGeom ntt_geom(const NttPassParams& p) {
     g.log_tiles = p.log_n - g.log_len - g.log_cw;
     return g;
 }
+B200_HD NttGeom ntt_geom(const NttPassParams& p) { return ntt_geom_t<NttDyn>(p); }
 
 // Global element index (within the polynomial) of tile element (t, cw) on the INPUT side.
 //   strided pass: tile -> (sub-problem p, column base m0): idx = p*M + t*S + m0 + cw
@@ -135,9 +154,11 @@ B200_HD unsigned long long ntt_in_index(const NttPassParams& p, const NttGeom& g
 // ---------------------------------------------------------------------------------------------
 // phase 1: global -> shared (coalesced), optional coset pre-scaling
 // ---------------------------------------------------------------------------------------------
+template <class SH = NttDyn>
 B200_HD void ntt_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
-                            uint32_t nthreads) {
-    NttGeom g = ntt_geom(p);
+                            uint32_t nthreads_rt) {
+    const NttGeom g = ntt_geom_t<SH>(p);
+    const uint32_t nthreads = ntt_nthreads<SH>(nthreads_rt);
     const uint4* src = p.src + 2ull * batch * p.batch_stride;
     uint32_t total = 2u * g.tile_elems;                 // 16-byte words
     // Batches of NTT_LOAD_BATCH independent global loads before their shared-memory stores: the trip count is a run-time
@@ -212,8 +233,10 @@ B200_HD NttTwiddles ntt_global_twiddles(const NttPassParams& p, uint32_t log_len
     return t;
 }
 // phase 0 (device): copy the L/2 twiddles of this pass into shared memory, planar
-B200_HD void ntt_phase_stage_twiddles(const NttPassParams& p, uint4* sm_tw, uint32_t tid, uint32_t nthreads) {
-    const uint32_t log_len = p.log_len[p.pass];
+template <class SH = NttDyn>
+B200_HD void ntt_phase_stage_twiddles(const NttPassParams& p, uint4* sm_tw, uint32_t tid, uint32_t nthreads_rt) {
+    const uint32_t nthreads = ntt_nthreads<SH>(nthreads_rt);
+    const uint32_t log_len = SH::log_len >= 0 ? (uint32_t)SH::log_len : p.log_len[p.pass];
     const uint32_t half = log_len ? (1u << (log_len - 1)) : 0;
     const uint32_t shift = NTT_TILE_TW_LOG - log_len;
     for (uint32_t u = tid; u < 2 * half; u += nthreads) {
@@ -230,9 +253,11 @@ B200_HD NttTwiddles ntt_shared_twiddles(const uint4* sm_tw, uint32_t log_len) {
     return t;
 }
 
+template <class SH = NttDyn>
 B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, const NttTwiddles& twd, uint32_t s, uint32_t tid,
-                             uint32_t nthreads) {
-    NttGeom g = ntt_geom(p);
+                             uint32_t nthreads_rt) {
+    const NttGeom g = ntt_geom_t<SH>(p);
+    const uint32_t nthreads = ntt_nthreads<SH>(nthreads_rt);
     uint32_t log_d = g.log_len - 1 - s;
     uint32_t nbf = g.tile_elems >> 1;                   // butterflies in the tile
     // Butterfly (block b, offset j) pairs t0 = b*2d + j with t0 + d and uses twiddle w_L^(j << s); j == 0 needs no
@@ -241,6 +266,7 @@ B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, const NttTwiddle
     // skip the multiplication (1/d of the butterflies of a stage; d = 1: all of them).
     const bool j_major = log_d <= 2;
     const uint32_t log_blocks = g.log_len - 1 - log_d;  // blocks of 2d points
+    B200_UNROLL_SHAPED
     for (uint32_t u = tid; u < nbf; u += nthreads) {
         uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
         uint32_t j, b;
@@ -266,13 +292,16 @@ B200_HD void ntt_phase_stage(const NttPassParams& p, uint4* sm, const NttTwiddle
 //   stage s + 1: (x0', x1') and (x2', x3'), both twiddle w_L^(j << (s + 1))
 // For the short-distance quads (d2 <= 4) lanes are ordered j-major so that the j == 0 quads, whose two twiddles are 1,
 // fill whole warps and really skip their products.
+template <class SH = NttDyn>
 B200_HD void ntt_phase_stage2(const NttPassParams& p, uint4* sm, const NttTwiddles& twd, uint32_t s, uint32_t tid,
-                              uint32_t nthreads) {
-    NttGeom g = ntt_geom(p);
+                              uint32_t nthreads_rt) {
+    const NttGeom g = ntt_geom_t<SH>(p);
+    const uint32_t nthreads = ntt_nthreads<SH>(nthreads_rt);
     const uint32_t log_d1 = g.log_len - 1 - s, log_d2 = log_d1 - 1;
     const uint32_t nquads = g.tile_elems >> 2;
     const bool j_major = log_d2 <= 2;
     const uint32_t log_blocks = g.log_len - 1 - log_d1;      // blocks of 2 * d1 points
+    B200_UNROLL_SHAPED
     for (uint32_t u = tid; u < nquads; u += nthreads) {
         const uint32_t cw = u & ((1u << g.log_cw) - 1), q = u >> g.log_cw;
         uint32_t j, b;
@@ -317,11 +346,18 @@ B200_HD void ntt_store_source(const NttGeom& g, uint32_t e, uint32_t& t, uint32_
     cw = e & ((1u << g.log_cw) - 1);
     t = bitrev32(e >> g.log_cw, g.log_len);
 }
+template <int STORE = 0>
 B200_HD void ntt_store_element(const NttPassParams& p, const NttGeom& g, fr_t x, uint4* dst, uint32_t tile, uint32_t e,
                                bool have_tw, const fr_t& tw) {
     uint32_t cw = e & ((1u << g.log_cw) - 1), k = e >> g.log_cw;          // k = output index of this pass
     unsigned long long out;
-    if (!g.last) {
+    if (STORE == 1) {                                                     // strided pass, twiddle already fetched
+        uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
+        unsigned long long sub = tile >> log_tiles_per_sub;
+        unsigned long long m = ((unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw) + cw;
+        out = (sub << g.log_sub) + ((unsigned long long)k << g.log_stride) + m;
+        if (m && k) x = fp_mul(x, tw);
+    } else if (STORE != 2 && !g.last) {
         uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
         unsigned long long sub = tile >> log_tiles_per_sub;
         unsigned long long m = ((unsigned long long)(tile & ((1u << log_tiles_per_sub) - 1)) << g.log_cw) + cw;
@@ -354,7 +390,7 @@ B200_HD void ntt_store_element(const NttPassParams& p, const NttGeom& g, fr_t x,
         }
         out = acc + ((unsigned long long)k << log_rows);
     }
-    if (g.last) {
+    if (STORE == 0 && g.last) {
         if (p.scale_post) x = fp_mul(x, p.size_inv);
         if (p.coset_post) x = fp_mul(x, pow2level(p.coset_lo, p.coset_hi, out));
     }
@@ -370,13 +406,24 @@ struct PlanarTile {
     uint32_t tile_elems, log_cw;
     B200_HDM fr_t get(uint32_t t, uint32_t cw) const { return tile_load(sm, tile_elems, (t << log_cw) + cw); }
 };
-template <class Tile>
+template <class Tile, class SH = NttDyn>
 B200_HD void ntt_phase_store_t(const NttPassParams& p, const Tile& T, uint32_t tile, uint32_t batch, uint32_t tid,
-                               uint32_t nthreads) {
-    NttGeom g = ntt_geom(p);
+                               uint32_t nthreads_rt) {
+    const NttGeom g = ntt_geom_t<SH>(p);
+    const uint32_t nthreads = ntt_nthreads<SH>(nthreads_rt);
     uint4* dst = p.dst + 2ull * batch * p.batch_stride;
     uint32_t e = tid;
-    if (!g.last && p.boundary_tw) {
+    if (SH::store == 2) {                                     // last pass, nothing to multiply: digit-reversed store only
+        const fr_t none2 = fp_zero<FrP>();
+        B200_UNROLL_SHAPED
+        for (; e < g.tile_elems; e += nthreads) {
+            uint32_t t, cw;
+            ntt_store_source(g, e, t, cw);
+            ntt_store_element<2>(p, g, T.get(t, cw), dst, tile, e, false, none2);
+        }
+        return;
+    }
+    if (SH::store == 1 || (!g.last && p.boundary_tw)) {
         // the boundary twiddles of NTT_STORE_BATCH elements are fetched together, ahead of the products that use them
         // (ncu r02: the first IMAD behind the one-at-a-time twiddle load carried 7 % of all stall samples)
 #ifndef NTT_STORE_BATCH
@@ -396,10 +443,11 @@ B200_HD void ntt_phase_store_t(const NttPassParams& p, const Tile& T, uint32_t t
             for (int q = 0; q < NTT_STORE_BATCH; q++) {
                 uint32_t t, cw;
                 ntt_store_source(g, e + q * nthreads, t, cw);
-                ntt_store_element(p, g, T.get(t, cw), dst, tile, e + q * nthreads, true, tw[q]);
+                ntt_store_element<SH::store>(p, g, T.get(t, cw), dst, tile, e + q * nthreads, true, tw[q]);
             }
         }
     }
+    if (SH::store == 1) return;                               // compile-time shape: the batches cover the tile exactly
     const fr_t none = fp_zero<FrP>();
     for (; e < g.tile_elems; e += nthreads) {
         uint32_t t, cw;
@@ -407,14 +455,15 @@ B200_HD void ntt_phase_store_t(const NttPassParams& p, const Tile& T, uint32_t t
         ntt_store_element(p, g, T.get(t, cw), dst, tile, e, false, none);
     }
 }
+template <class SH = NttDyn>
 B200_HD void ntt_phase_store(const NttPassParams& p, const uint4* sm, uint32_t tile, uint32_t batch, uint32_t tid,
                              uint32_t nthreads) {
-    const NttGeom g = ntt_geom(p);
+    const NttGeom g = ntt_geom_t<SH>(p);
     PlanarTile T;
     T.sm = sm;
     T.tile_elems = g.tile_elems;
     T.log_cw = g.log_cw;
-    ntt_phase_store_t(p, T, tile, batch, tid, nthreads);
+    ntt_phase_store_t<PlanarTile, SH>(p, T, tile, batch, tid, nthreads);
 }
 
 // =============================================================================================

@@ -61,7 +61,7 @@ static bool ntt_make_plan(uint32_t log_n, NttPlan* plan, uint32_t tile_log = 11,
     for (uint32_t i = 0; i < plan->npasses; i++) {
         uint32_t l = plan->log_len[i];
         uint32_t room = (l >= tile_log) ? 0 : tile_log - l;
-        if (room > 3) room = 3;                        // 8 columns = 256 B runs are plenty
+        if (room > 4) room = 4;                        // up to 16 columns (512 B runs): a 2^6 pass fills a 1024-element tile
         uint32_t avail;
         if (plan->npasses == 1) avail = 0;
         else if (i + 1 < plan->npasses) avail = log_n - before - l;     // log2(columns) = log_stride

@@ -4,6 +4,7 @@
 // oracle without a GPU.  Not part of the shipped library; not a CPU fallback.
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../snarkos_b200/csrc/ntt_core.cuh"
@@ -160,6 +161,38 @@ extern "C" int host_ntt_variant(uint32_t* data, uint32_t log_n, uint32_t batch, 
                         for (uint32_t lane = 0; lane < 32; lane++) wc_round3(wsm.data(), twd, cw, lane);
                     }
                     for (uint32_t tid = 0; tid < 128; tid++) wc_phase_store(p, wsm.data(), tile, b, tid, 128);
+                    continue;
+                }
+                const bool s82 = plan.log_len[i] == 8 && plan.log_cw[i] == 2, s73 = plan.log_len[i] == 7 && plan.log_cw[i] == 3,
+                           s64 = plan.log_len[i] == 6 && plan.log_cw[i] == 4;
+                if (variant == 3 && p.radix4 && (s82 || s73 || s64)) {
+                    // what ntt_pass_shaped_kernel<L, CW, STORE> does (compile-time shape, 128 threads, the launcher's choice
+                    // of the store mode)
+                    const int store = (p.coset_pre || p.scale_post || p.coset_post) ? 0 : last ? (plan.npasses > 1 ? 2 : 0) : (p.boundary_tw ? 1 : 0);
+                    std::vector<uint4> smtw((size_t)1 << plan.log_len[i]);
+                    auto run_shaped = [&](auto shape) {
+                        typedef decltype(shape) SH;
+                        for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage_twiddles<SH>(p, smtw.data(), tid, 0);
+                        const NttTwiddles twd = ntt_shared_twiddles(smtw.data(), plan.log_len[i]);
+                        for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_load<SH>(p, sm.data(), tile, b, tid, 0);
+                        if (SH::store == 0 && p.coset_pre)
+                            for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, 128);
+                        uint32_t s = 0;
+                        for (; s + 1 < plan.log_len[i]; s += 2)
+                            for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage2<SH>(p, sm.data(), twd, s, tid, 0);
+                        for (; s < plan.log_len[i]; s++)
+                            for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage<SH>(p, sm.data(), twd, s, tid, 0);
+                        for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_store<SH>(p, sm.data(), tile, b, tid, 0);
+                    };
+                    auto by_store = [&](auto l, auto c) {
+                        constexpr int LL = decltype(l)::value, CC = decltype(c)::value;
+                        if (store == 1) run_shaped(NttShape<LL, CC, 128, 1, 1>());
+                        else if (store == 2) run_shaped(NttShape<LL, CC, 128, 1, 2>());
+                        else run_shaped(NttShape<LL, CC, 128, 1, 0>());
+                    };
+                    if (s82) by_store(std::integral_constant<int, 8>(), std::integral_constant<int, 2>());
+                    else if (s73) by_store(std::integral_constant<int, 7>(), std::integral_constant<int, 3>());
+                    else by_store(std::integral_constant<int, 6>(), std::integral_constant<int, 4>());
                     continue;
                 }
                 for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);

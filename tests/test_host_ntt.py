@@ -116,7 +116,23 @@ def test_warp_column_passes_match_oracle(hostlib, log_n, lens, cws, direction, c
     batch, stride = 2, n + 3
     data = H.random_fr_mont_np(rng, (stride * (batch - 1) + n,))
     got = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=16, variant=2)
+    got_shaped = run(hostlib, data, log_n, batch, stride, direction, coset, lens, cws, nthreads=16, variant=3)
     want = data.copy()
     for b in range(batch):
         want[b * stride:b * stride + n] = C.ntt(data[b * stride:b * stride + n], log_n, direction=direction, coset=coset)
     assert np.array_equal(got, want)
+    assert np.array_equal(got_shaped, want)      # ntt_pass_shaped_kernel<8, 2>'s phases (compile-time shape)
+
+
+@pytest.mark.parametrize("log_n,lens,cws", [(10, (7, 3), (3, 3)), (10, (3, 7), (3, 3)), (14, (7, 7), (3, 3)), (13, (3, 7, 3), (3, 3, 3)),
+                                            (12, (6, 6), (4, 4)), (13, (7, 6), (3, 4)), (10, (4, 6), (4, 4))])
+@pytest.mark.parametrize("direction,coset", [(0, 0), (1, 1), (0, 1), (1, 0)])
+def test_shape_specialised_7_3_and_6_4_match_oracle(hostlib, log_n, lens, cws, direction, coset):
+    """ntt_pass_shaped_kernel<7, 3> (odd length: three stage pairs and one single stage) and <6, 4> (16-column tiles)
+    emulated thread by thread, with the launcher's choice of the store mode (forward plain: modes 1 / 2; coset and
+    inverse: mode 0)"""
+    n = 1 << log_n
+    rng = np.random.default_rng(8000 + log_n + 2 * direction + coset)
+    data = H.random_fr_mont_np(rng, (n,))
+    got = run(hostlib, data, log_n, 1, n, direction, coset, lens, cws, nthreads=16, variant=3)
+    assert np.array_equal(got, C.ntt(data, log_n, direction=direction, coset=coset))
