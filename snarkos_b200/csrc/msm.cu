@@ -399,7 +399,10 @@ __global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_denoms_kernel(PairR
     if (t < t1) pair_denoms_thread(rd, t, pre, partial);
 }
 
-__global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_add_kernel(PairRound rd, const uint4* __restrict__ pre,
+#ifndef MSM_PAIR_ADD_MIN_BLOCKS
+#define MSM_PAIR_ADD_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(MSM_PAIR_THREADS, MSM_PAIR_ADD_MIN_BLOCKS) msm_pair_add_kernel(PairRound rd, const uint4* __restrict__ pre,
                                                                        const uint4* __restrict__ partial_inv,
                                                                        uint4* __restrict__ out_x, uint4* __restrict__ out_y,
                                                                        uint32_t t0, uint32_t t1) {
@@ -445,6 +448,9 @@ static b200_error_t fq_batch_inverse_nonzero(uint4* d_data, size_t n, cudaStream
 // bucket reduction
 // ---------------------------------------------------------------------------------------------
 // (An out-of-line g1_add here -- 168 registers instead of 255 -- was measured slower: 14.0 vs 11.5 ms at 2^24, c = 20.)
+// (A compact form -- the exceptional doubling out of line, all additions of the running-sum loop through one call site
+// picked with selects -- was also built: 27 k instead of 43 k instructions, but still 255 registers and a 408-byte
+// stack frame for the call; not pursued.)
 __global__ void __launch_bounds__(MSM_RED_THREADS) msm_reduce_segments_kernel(g1_xyzz_mem_t* __restrict__ segs,
                                                                              const g1_xyzz_mem_t* __restrict__ buckets,
                                                                              MsmShape sh, uint32_t seg_len,
