@@ -399,6 +399,10 @@ __global__ void __launch_bounds__(MSM_PAIR_THREADS) msm_pair_denoms_kernel(PairR
     if (t < t1) pair_denoms_thread(rd, t, pre, partial);
 }
 
+// Four 128-thread blocks per SM at 128 registers (16 warps).  Measured alternatives: 5 blocks (96 registers, 124 bytes
+// of spills, 20 warps) is SLOWER -- 23.56 / 21.83 ms against 22.75 / 21.00 ms for round 0 / rounds 1..4 at 2^24; 3 blocks
+// change nothing (the kernel wants 132 registers).  The 19 % it is short of the multiplier peak are fixed-latency waits
+// of the IMAD.WIDE carry chains with four warps per scheduler (ncu: `wait` 3.9, `long_scoreboard` 1.6 - 2.8).
 #ifndef MSM_PAIR_ADD_MIN_BLOCKS
 #define MSM_PAIR_ADD_MIN_BLOCKS 4
 #endif
