@@ -25,34 +25,37 @@ __global__ void __launch_bounds__(128, 6) ntt_pass_kernel_128(const NttPassParam
 // per stage pair makes the kernel slower -- 3.78 against 3.25 ms at 2^24 -- the hot loop no longer fits the
 // instruction cache), and a store phase that contains only what this pass needs (STORE 1: strided pass with its
 // boundary table; 2: last pass of a plain forward transform; 0: everything, chosen at run time).
+// 1024-element tiles run on 128 threads (six CTAs per SM), 2048-element tiles -- the plans that save a pass with 9-bit
+// passes: 2^17, 2^18, 2^25 .. 2^27 -- on 256 threads (three per SM): eight elements per thread either way.
 template <int L, int CW, int STORE>
-__global__ void __launch_bounds__(128, 6) ntt_pass_shaped_kernel(const NttPassParams p) {
-    typedef NttShape<L, CW, 128, 1, STORE> SH;
-    static_assert(L + CW == 10, "1024-element tiles");
+__global__ void __launch_bounds__((1 << (L + CW)) / 8, (L + CW == 10 ? 6 : 3)) ntt_pass_shaped_kernel(const NttPassParams p) {
+    constexpr int NT = (1 << (L + CW)) / 8;
+    typedef NttShape<L, CW, NT, 1, STORE> SH;
+    static_assert(L + CW == 10 || L + CW == 11, "1024- or 2048-element tiles");
     extern __shared__ uint4 sm[];
     const uint32_t tile = blockIdx.x, batch = blockIdx.y, tid = threadIdx.x;
-    uint4* sm_tw = sm + 2 * 1024;
-    ntt_phase_stage_twiddles<SH>(p, sm_tw, tid, 128);
+    uint4* sm_tw = sm + 2 * (1 << (L + CW));
+    ntt_phase_stage_twiddles<SH>(p, sm_tw, tid, NT);
     const NttTwiddles twd = ntt_shared_twiddles(sm_tw, L);
-    ntt_phase_load<SH>(p, sm, tile, batch, tid, 128);
+    ntt_phase_load<SH>(p, sm, tile, batch, tid, NT);
     __syncthreads();
     if (STORE == 0 && p.coset_pre) {                          // the launcher sends forward coset passes to STORE 0
-        ntt_phase_coset_pre(p, sm, tile, tid, 128);
+        ntt_phase_coset_pre(p, sm, tile, tid, NT);
         __syncthreads();
     }
 #pragma unroll 1
     for (int s = 0; s + 1 < L; s += 2) {
-        ntt_phase_stage2<SH>(p, sm, twd, s, tid, 128);
+        ntt_phase_stage2<SH>(p, sm, twd, s, tid, NT);
         __syncthreads();
     }
     if (L & 1) {
-        ntt_phase_stage<SH>(p, sm, twd, L - 1, tid, 128);
+        ntt_phase_stage<SH>(p, sm, twd, L - 1, tid, NT);
         __syncthreads();
     }
-    ntt_phase_store<SH>(p, sm, tile, batch, tid, 128);
+    ntt_phase_store<SH>(p, sm, tile, batch, tid, NT);
 }
 template <int L, int CW, int STORE> static cudaError_t ntt_shaped_attr() {
-    cudaError_t e = cudaFuncSetAttribute(ntt_pass_shaped_kernel<L, CW, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 32 + (1 << L) * 16);
+    cudaError_t e = cudaFuncSetAttribute(ntt_pass_shaped_kernel<L, CW, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << (L + CW)) * 32 + (1 << L) * 16);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_shaped_kernel<L, CW, STORE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return e;
 }
@@ -63,9 +66,10 @@ template <int L, int CW> static cudaError_t ntt_shaped_attrs() {
     return e;
 }
 template <int L, int CW> static void ntt_launch_shaped(int store, dim3 grid, size_t smem, cudaStream_t stream, const NttPassParams& p) {
-    if (store == 1) ntt_pass_shaped_kernel<L, CW, 1><<<grid, 128, smem, stream>>>(p);
-    else if (store == 2) ntt_pass_shaped_kernel<L, CW, 2><<<grid, 128, smem, stream>>>(p);
-    else ntt_pass_shaped_kernel<L, CW, 0><<<grid, 128, smem, stream>>>(p);
+    constexpr int NT = (1 << (L + CW)) / 8;
+    if (store == 1) ntt_pass_shaped_kernel<L, CW, 1><<<grid, NT, smem, stream>>>(p);
+    else if (store == 2) ntt_pass_shaped_kernel<L, CW, 2><<<grid, NT, smem, stream>>>(p);
+    else ntt_pass_shaped_kernel<L, CW, 0><<<grid, NT, smem, stream>>>(p);
 }
 __device__ __forceinline__ void ntt_pass_body(const NttPassParams& p) {
     extern __shared__ uint4 sm[];
@@ -277,7 +281,7 @@ __global__ void ntt_size_inv_kernel(fr_t* out, uint32_t log_n) {
 // ---------------------------------------------------------------------------------------------
 // cached per-(log_n, direction) tables
 // ---------------------------------------------------------------------------------------------
-#define NTT_BOUNDARY_TABLE_MAX_LOG 25          // up to 2^25 entries = 1 GiB per pass boundary; larger -> two-level powers
+#define NTT_BOUNDARY_TABLE_MAX_LOG 27          // up to 2^27 entries = 4 GiB per pass boundary (180 GB of HBM); larger -> two-level powers
 struct NttDomainTables {
     // per-pass inter-pass twiddle tables, valid for the plan recorded next to them
     uint4* boundary[NTT_MAX_PASSES] = {nullptr, nullptr, nullptr, nullptr};
@@ -331,6 +335,8 @@ static b200_error_t get_tables(uint32_t log_n, int direction, cudaStream_t strea
         CUDA_TRY((ntt_shaped_attrs<8, 2>()));
         CUDA_TRY((ntt_shaped_attrs<7, 3>()));
         CUDA_TRY((ntt_shaped_attrs<6, 4>()));
+        CUDA_TRY((ntt_shaped_attrs<9, 2>()));
+        CUDA_TRY((ntt_shaped_attrs<8, 3>()));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_wc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_WC_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_wc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaFuncSetAttribute(ntt_pass_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -690,6 +696,10 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
             ntt_launch_shaped<7, 3>(store, grid, smem, stream, p);
         else if (shaped && plan.log_len[i] == 6 && plan.log_cw[i] == 4)
             ntt_launch_shaped<6, 4>(store, grid, smem, stream, p);
+        else if (shaped && plan.log_len[i] == 9 && plan.log_cw[i] == 2)
+            ntt_launch_shaped<9, 2>(store, grid, smem, stream, p);
+        else if (shaped && plan.log_len[i] == 8 && plan.log_cw[i] == 3)
+            ntt_launch_shaped<8, 3>(store, grid, smem, stream, p);
         else if (tile_elems == 1024 && b200_config().ntt_variant != 3)
             ntt_pass_kernel_128<<<grid, 128, smem, stream>>>(p);
         else

@@ -164,34 +164,38 @@ extern "C" int host_ntt_variant(uint32_t* data, uint32_t log_n, uint32_t batch, 
                     continue;
                 }
                 const bool s82 = plan.log_len[i] == 8 && plan.log_cw[i] == 2, s73 = plan.log_len[i] == 7 && plan.log_cw[i] == 3,
-                           s64 = plan.log_len[i] == 6 && plan.log_cw[i] == 4;
-                if (variant == 3 && p.radix4 && (s82 || s73 || s64)) {
+                           s64 = plan.log_len[i] == 6 && plan.log_cw[i] == 4, s92 = plan.log_len[i] == 9 && plan.log_cw[i] == 2,
+                           s83 = plan.log_len[i] == 8 && plan.log_cw[i] == 3;
+                if (variant == 3 && p.radix4 && (s82 || s73 || s64 || s92 || s83)) {
                     // what ntt_pass_shaped_kernel<L, CW, STORE> does (compile-time shape, 128 threads, the launcher's choice
                     // of the store mode)
                     const int store = (p.coset_pre || p.scale_post || p.coset_post) ? 0 : last ? (plan.npasses > 1 ? 2 : 0) : (p.boundary_tw ? 1 : 0);
                     std::vector<uint4> smtw((size_t)1 << plan.log_len[i]);
                     auto run_shaped = [&](auto shape) {
                         typedef decltype(shape) SH;
-                        for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage_twiddles<SH>(p, smtw.data(), tid, 0);
+                        const uint32_t NT = SH::nthreads;
+                        for (uint32_t tid = 0; tid < NT; tid++) ntt_phase_stage_twiddles<SH>(p, smtw.data(), tid, 0);
                         const NttTwiddles twd = ntt_shared_twiddles(smtw.data(), plan.log_len[i]);
-                        for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_load<SH>(p, sm.data(), tile, b, tid, 0);
+                        for (uint32_t tid = 0; tid < NT; tid++) ntt_phase_load<SH>(p, sm.data(), tile, b, tid, 0);
                         if (SH::store == 0 && p.coset_pre)
-                            for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, 128);
+                            for (uint32_t tid = 0; tid < NT; tid++) ntt_phase_coset_pre(p, sm.data(), tile, tid, NT);
                         uint32_t s = 0;
                         for (; s + 1 < plan.log_len[i]; s += 2)
-                            for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage2<SH>(p, sm.data(), twd, s, tid, 0);
+                            for (uint32_t tid = 0; tid < NT; tid++) ntt_phase_stage2<SH>(p, sm.data(), twd, s, tid, 0);
                         for (; s < plan.log_len[i]; s++)
-                            for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_stage<SH>(p, sm.data(), twd, s, tid, 0);
-                        for (uint32_t tid = 0; tid < 128; tid++) ntt_phase_store<SH>(p, sm.data(), tile, b, tid, 0);
+                            for (uint32_t tid = 0; tid < NT; tid++) ntt_phase_stage<SH>(p, sm.data(), twd, s, tid, 0);
+                        for (uint32_t tid = 0; tid < NT; tid++) ntt_phase_store<SH>(p, sm.data(), tile, b, tid, 0);
                     };
                     auto by_store = [&](auto l, auto c) {
-                        constexpr int LL = decltype(l)::value, CC = decltype(c)::value;
-                        if (store == 1) run_shaped(NttShape<LL, CC, 128, 1, 1>());
-                        else if (store == 2) run_shaped(NttShape<LL, CC, 128, 1, 2>());
-                        else run_shaped(NttShape<LL, CC, 128, 1, 0>());
+                        constexpr int LL = decltype(l)::value, CC = decltype(c)::value, NT = (1 << (LL + CC)) / 8;
+                        if (store == 1) run_shaped(NttShape<LL, CC, NT, 1, 1>());
+                        else if (store == 2) run_shaped(NttShape<LL, CC, NT, 1, 2>());
+                        else run_shaped(NttShape<LL, CC, NT, 1, 0>());
                     };
                     if (s82) by_store(std::integral_constant<int, 8>(), std::integral_constant<int, 2>());
                     else if (s73) by_store(std::integral_constant<int, 7>(), std::integral_constant<int, 3>());
+                    else if (s92) by_store(std::integral_constant<int, 9>(), std::integral_constant<int, 2>());
+                    else if (s83) by_store(std::integral_constant<int, 8>(), std::integral_constant<int, 3>());
                     else by_store(std::integral_constant<int, 6>(), std::integral_constant<int, 4>());
                     continue;
                 }

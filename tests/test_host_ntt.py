@@ -125,7 +125,9 @@ def test_warp_column_passes_match_oracle(hostlib, log_n, lens, cws, direction, c
 
 
 @pytest.mark.parametrize("log_n,lens,cws", [(10, (7, 3), (3, 3)), (10, (3, 7), (3, 3)), (14, (7, 7), (3, 3)), (13, (3, 7, 3), (3, 3, 3)),
-                                            (12, (6, 6), (4, 4)), (13, (7, 6), (3, 4)), (10, (4, 6), (4, 4))])
+                                            (12, (6, 6), (4, 4)), (13, (7, 6), (3, 4)), (10, (4, 6), (4, 4)),
+                                            (11, (9, 2), (2, 2)), (11, (2, 9), (2, 2)), (11, (8, 3), (3, 3)), (11, (3, 8), (3, 3)),
+                                            (17, (9, 8), (2, 3))])
 @pytest.mark.parametrize("direction,coset", [(0, 0), (1, 1), (0, 1), (1, 0)])
 def test_shape_specialised_7_3_and_6_4_match_oracle(hostlib, log_n, lens, cws, direction, coset):
     """ntt_pass_shaped_kernel<7, 3> (odd length: three stage pairs and one single stage) and <6, 4> (16-column tiles)
