@@ -47,10 +47,10 @@ def parse_args():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r01_ncu_full_selected_metrics.txt, r01_ncu_msm_affine_full.txt), valid for the default workload only (2^24)
-NCU_TRAFFIC_BYTES = {"msm_accumulate_kernel@2^24": 42.036437e9 + 1.545928e9, "ntt_pass_kernel@2^24": (1.071753 + 0.504116 + 0.539175 + 0.480226 + 0.536956 + 0.487881) * 1e9,   # profiles/r01_ncu_ntt_full.txt
-                     # five launches (pair rounds 0..4) of one 2^24 MSM, GLV split, c = 19: profiles/r01_ncu_msm_affine_full.txt
-                     "msm_pair_add_kernel@2^24": (40.571 + 13.103 + 16.321 + 6.539 + 8.275 + 3.298 + 4.233 + 1.676 + 2.220 + 0.865) * 1e9}
+# (profiles/r02_ncu_msm_pairs_full.txt, r02_ncu_ntt_shaped.txt; r01 for the XYZZ-only kernel), valid for the default workload only (2^24)
+NCU_TRAFFIC_BYTES = {"msm_accumulate_kernel@2^24": 42.036437e9 + 1.545928e9, "ntt_pass_kernel@2^24": (1.071711 + 0.502226 + 0.539092 + 0.477465 + 0.537232 + 0.486516) * 1e9,   # profiles/r02_ncu_ntt_shaped.txt
+                     # five launches (pair rounds 0..4) of one 2^24 MSM, GLV split, c = 19: profiles/r02_ncu_msm_pairs_full.txt
+                     "msm_pair_add_kernel@2^24": (40.564 + 13.101 + 16.315 + 6.539 + 8.274 + 3.298 + 4.238 + 1.678 + 2.226 + 0.867) * 1e9}
 
 
 def measured_peaks():
@@ -497,11 +497,26 @@ def run_b200(args):
                         "Fq Montgomery product rate of this GPU (276 IMAD.WIDE each, 96 % of the 31.5 IMAD.WIDE/clk/SM pipe); "
                         "roofline_hbm keeps the HBM view the base contract asks for")
     ntt_pass_ms = sum(v for k_, v in stage.items() if k_.startswith("ntt_pass")) / K
-    ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,
+    ntt_roof = {"bound": "hbm", "kernel": "ntt_pass_shaped_kernel (all passes of one transform)", "achieved": 64.0 * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
                 "traffic": NCU_TRAFFIC_BYTES["ntt_pass_kernel@2^24"] if args.log_n == 24 else None,
                 "algorithmic_bytes_per_transform": 64 * n, "passes": len([k_ for k_ in stage if k_.startswith("ntt_pass")])}
     ntt_roof["frac"] = ntt_roof["achieved"] / hbm_peak if ntt_roof["achieved"] else None
+    # the binding resource of the transform is the multiplier too: Fr products per element against
+    # the Fr modmul rate of a pure fp_mul<Fr> loop measured in the same run
+    best_fr = 0.0
+    for _ in range(3):
+        S._lib.check(S.lib().b200_debug_microbench(3, 512, ctypes.byref(ms_), ctypes.byref(ops_)))
+        best_fr = max(best_fr, ops_.value / (ms_.value * 1e-3))
+    npass = ntt_roof["passes"] or 3
+    fr_per_elem = 3.05 * npass + (npass - 1) if args.log_n == 24 else 0.5 * args.log_n + (npass - 1)
+    ntt_roof_int = {"bound": "int_mul_pipe", "kernel": "ntt_pass_shaped_kernel (all passes of one transform)", "unit": "G Fr-modmul/s",
+                    "achieved": fr_per_elem * n / (ntt_pass_ms * 1e-3) / 1e9 if ntt_pass_ms else None, "peak": best_fr / 1e9,
+                    "peak_source": "fp_mul<Fr> dependent-chain microbenchmark, same run, full occupancy",
+                    "modmul_per_element": fr_per_elem,
+                    "note": "butterfly products after the trivial-twiddle skips (3.05 per element and 8-bit pass) + one inter-pass "
+                            "twiddle per element and pass boundary; ncu (profiles/r02_ncu_ntt_shaped.txt): multiplier pipe 81 % busy"}
+    ntt_roof_int["frac"] = ntt_roof_int["achieved"] / ntt_roof_int["peak"] if ntt_roof_int["achieved"] else None
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------------------
     cpu = None
@@ -658,7 +673,7 @@ def run_b200(args):
         "msm_ms": msm_ms / K, "clocks": clocks, "gpu_launches": int(launches),
         "stage_ms_per_step": {k_: v / K for k_, v in stage.items()},
         "roofline": roofline, "roofline_hbm": roofline_hbm,
-        "ntt": {"value": world * n * K / (ntt_ms * 1e-3) / 1e9, "unit": "Gelem/s", "ms": ntt_ms / K, "roofline": ntt_roof,
+        "ntt": {"value": world * n * K / (ntt_ms * 1e-3) / 1e9, "unit": "Gelem/s", "ms": ntt_ms / K, "roofline": ntt_roof, "roofline_int": ntt_roof_int,
                 "e2e": ntt_e2e, "cpu_baseline": ntt_cpu},
     }
     if batch_verify is not None:
