@@ -115,51 +115,50 @@ B200Counters g_counters;
 #define SCRATCH_POW2_LIMIT ((size_t)64 << 20)
 #define SCRATCH_GLOBAL_BUDGET ((size_t)40 << 30)
 static std::atomic<size_t> g_scratch_cached{0};
+// One cache per STREAM (not per thread): a caller thread that exits hands its stream to the next thread, and the
+// scratch cached on that stream goes with it -- a new thread's first call finds the blocks of the same shape already
+// there (per-thread caches made every short-lived thread pay the driver allocations again: two 2^20 MSMs from two fresh
+// threads took 25 ms each instead of 7 ms).
 struct ScratchCache {
-    std::mutex mu;                                          // uncontended: the owner thread, and b200_shutdown / out-of-memory
-    struct Key { cudaStream_t s; size_t bytes; bool operator<(const Key& o) const { return s != o.s ? s < o.s : bytes < o.bytes; } };
+    std::mutex mu;                                          // the stream's current user; shutdown / eviction use try_lock or wait
+    cudaStream_t stream = nullptr;
     struct Block { void* p; uint64_t tick; };
-    std::map<Key, std::vector<Block>> free_blocks;
+    std::map<size_t, std::vector<Block>> free_blocks;       // rounded size -> blocks
     uint64_t tick = 0;                                      // last-use order, for eviction
-    uint64_t generation = 0;
-    ScratchCache();
-    ~ScratchCache();
 };
 struct ScratchRegistry {
-    std::mutex mu;
-    std::vector<ScratchCache*> caches;
+    std::mutex mu;                                          // the map itself; never held together with a cache mutex except by try_lock
+    std::map<cudaStream_t, ScratchCache*> caches;
+    uint64_t generation = 0;
 };
 static ScratchRegistry& g_scratch = *new ScratchRegistry();
-ScratchCache::ScratchCache() {
+
+static ScratchCache* scratch_cache_of(cudaStream_t stream) {
+    static thread_local cudaStream_t t_last_stream = nullptr;
+    static thread_local ScratchCache* t_last_cache = nullptr;
+    static thread_local uint64_t t_last_generation = 0;
+    const uint64_t gen = g_api.generation;                  // changes only in b200_init / b200_shutdown
+    if (t_last_cache && t_last_stream == stream && t_last_generation == gen) return t_last_cache;     // no lock on the usual path
     std::lock_guard<std::mutex> lock(g_scratch.mu);
-    g_scratch.caches.push_back(this);
-}
-static void scratch_drop_locked(ScratchCache& c, bool free_blocks) {
-    for (auto& kv : c.free_blocks) {
-        if (free_blocks)
-            for (auto& b : kv.second) cudaFreeAsync(b.p, kv.first.s);
-        g_scratch_cached.fetch_sub(kv.first.bytes * kv.second.size());
+    if (g_scratch.generation != gen) {         // the library was shut down and bound again: old blocks are gone
+        for (auto& kv : g_scratch.caches) {
+            std::lock_guard<std::mutex> l2(kv.second->mu);
+            for (auto& fb : kv.second->free_blocks) g_scratch_cached.fetch_sub(fb.first * fb.second.size());
+            kv.second->free_blocks.clear();
+        }
+        g_scratch.generation = gen;
     }
-    c.free_blocks.clear();
-}
-ScratchCache::~ScratchCache() {
-    {
-        std::lock_guard<std::mutex> lock(g_scratch.mu);
-        for (size_t i = 0; i < g_scratch.caches.size(); i++)
-            if (g_scratch.caches[i] == this) { g_scratch.caches.erase(g_scratch.caches.begin() + i); break; }
+    auto it = g_scratch.caches.find(stream);
+    if (it == g_scratch.caches.end()) {
+        ScratchCache* c = new ScratchCache();
+        c->stream = stream;
+        it = g_scratch.caches.emplace(stream, c).first;
     }
-    // a retiring thread gives its blocks back to the driver pool (its stream goes to the next thread); at process exit
-    // the library may already be shut down, then the blocks went with it.  (g_api.mu is never taken under a cache
-    // mutex: b200_shutdown holds it while it walks the registry.)
-    bool live;
-    {
-        std::lock_guard<std::mutex> l2(g_api.mu);
-        live = g_api.initialized && generation == g_api.generation;
-    }
-    std::lock_guard<std::mutex> lock(mu);
-    scratch_drop_locked(*this, live);
+    t_last_stream = stream;
+    t_last_cache = it->second;
+    t_last_generation = g_scratch.generation;
+    return it->second;
 }
-static thread_local ScratchCache t_scratch;
 
 static size_t scratch_round(size_t bytes) {
     if (bytes <= SCRATCH_POW2_LIMIT) {
@@ -172,17 +171,27 @@ static size_t scratch_round(size_t bytes) {
     const size_t step = top >> 3;
     return (bytes + step - 1) / step * step;
 }
+// least recently used block of one cache back to the driver; false when the cache is empty (cache mutex held)
+static bool scratch_evict_one_locked(ScratchCache& c) {
+    std::map<size_t, std::vector<ScratchCache::Block>>::iterator oldest = c.free_blocks.end();
+    size_t oldest_i = 0;
+    for (auto it = c.free_blocks.begin(); it != c.free_blocks.end(); ++it)
+        for (size_t i = 0; i < it->second.size(); i++)
+            if (oldest == c.free_blocks.end() || it->second[i].tick < oldest->second[oldest_i].tick) { oldest = it; oldest_i = i; }
+    if (oldest == c.free_blocks.end()) return false;
+    cudaFreeAsync(oldest->second[oldest_i].p, c.stream);
+    g_scratch_cached.fetch_sub(oldest->first);
+    oldest->second.erase(oldest->second.begin() + oldest_i);
+    if (oldest->second.empty()) c.free_blocks.erase(oldest);
+    return true;
+}
 cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
     const size_t rounded = scratch_round(bytes);
-    ScratchCache& c = t_scratch;
+    ScratchCache* c = scratch_cache_of(stream);
     {
-        std::lock_guard<std::mutex> lock(c.mu);
-        if (c.generation != g_api.generation) {             // the library was shut down and bound again: old blocks are gone
-            scratch_drop_locked(c, false);
-            c.generation = g_api.generation;
-        }
-        auto it = c.free_blocks.find(ScratchCache::Key{stream, rounded});
-        if (it != c.free_blocks.end() && !it->second.empty()) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        auto it = c->free_blocks.find(rounded);
+        if (it != c->free_blocks.end() && !it->second.empty()) {
             *p = it->second.back().p;
             it->second.pop_back();
             g_scratch_cached.fetch_sub(rounded);
@@ -199,35 +208,37 @@ cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
 }
 void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream) {
     const size_t rounded = scratch_round(bytes);
-    ScratchCache& c = t_scratch;
-    std::lock_guard<std::mutex> lock(c.mu);
-    if (c.generation != g_api.generation) return;           // belongs to a library instance that was shut down
     if (rounded > SCRATCH_GLOBAL_BUDGET / 2) {              // a block of this size would evict everything else
         cudaFreeAsync(p, stream);
         return;
     }
-    c.free_blocks[ScratchCache::Key{stream, rounded}].push_back(ScratchCache::Block{p, ++c.tick});
-    g_scratch_cached.fetch_add(rounded);
-    // over budget: this thread's least recently used blocks go back to the driver (a call of another shape, or on
-    // another stream, left them behind)
-    while (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET) {
-        std::map<ScratchCache::Key, std::vector<ScratchCache::Block>>::iterator oldest = c.free_blocks.end();
-        size_t oldest_i = 0;
-        for (auto it = c.free_blocks.begin(); it != c.free_blocks.end(); ++it)
-            for (size_t i = 0; i < it->second.size(); i++)
-                if (oldest == c.free_blocks.end() || it->second[i].tick < oldest->second[oldest_i].tick) { oldest = it; oldest_i = i; }
-        if (oldest == c.free_blocks.end()) break;           // the rest belongs to other threads
-        cudaFreeAsync(oldest->second[oldest_i].p, oldest->first.s);
-        g_scratch_cached.fetch_sub(oldest->first.bytes);
-        oldest->second.erase(oldest->second.begin() + oldest_i);
-        if (oldest->second.empty()) c.free_blocks.erase(oldest);
+    ScratchCache* c = scratch_cache_of(stream);
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        c->free_blocks[rounded].push_back(ScratchCache::Block{p, ++c->tick});
+        g_scratch_cached.fetch_add(rounded);
+        // over budget: this stream's least recently used blocks go first (a call of another shape left them behind)
+        while (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET && c->free_blocks.size() > 1)
+            if (!scratch_evict_one_locked(*c)) break;
+        // still over budget (other streams' caches hold the rest): this block is not cached either.  Other streams are
+        // never touched from here -- their owners may have destroyed them, and a stream-ordered free on a destroyed
+        // stream crashes inside the driver; b200_release_scratch / an allocation failure empty every cache safely.
+        if (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET) scratch_evict_one_locked(*c);
     }
 }
+// Every cached block back to the driver.  No stream is used: a cache may outlive its stream (the queue's dispatcher
+// stream, a caller's own stream), and cudaFreeAsync on a destroyed stream crashes inside the driver -- so the device is
+// synchronised (all work that touched the blocks is complete) and the blocks are freed with cudaFree.
 void b200_scratch_release_all() {
+    cudaDeviceSynchronize();
     std::lock_guard<std::mutex> lock(g_scratch.mu);
-    for (ScratchCache* c : g_scratch.caches) {
-        std::lock_guard<std::mutex> l2(c->mu);
-        scratch_drop_locked(*c, true);
+    for (auto& kv : g_scratch.caches) {
+        std::lock_guard<std::mutex> l2(kv.second->mu);
+        for (auto& fb : kv.second->free_blocks) {
+            for (auto& b : fb.second) cudaFree(b.p);
+            g_scratch_cached.fetch_sub(fb.first * fb.second.size());
+        }
+        kv.second->free_blocks.clear();
     }
 }
 

@@ -42,3 +42,41 @@ def test_reinit_and_shutdown_cycle():
         rb = S.ResidentBases(hb)
         assert C.g1_to_affine(rb.msm(sc)).tobytes() == want_msm
     rb.release()
+
+
+def test_shutdown_after_queue_and_foreign_streams():
+    """Scratch is cached per stream and a cache can outlive its stream: the queue's dispatcher stream is destroyed by
+    b200_shutdown before the caches are emptied, and a caller may destroy a stream of its own.  Neither may be touched
+    when the cached blocks are handed back (a stream-ordered free on a destroyed stream crashed inside the driver:
+    tools/queue_bench.cpp, round 2); b200_release_scratch does the same outside a shutdown."""
+    import ctypes
+    import torch
+    import snarkos_b200 as S
+    from snarkos_b200 import _lib
+    L = _lib.lib()
+    S.init(0)
+    n = 64
+    hb = S.synthetic_bases(n, seed=9).cpu().numpy()
+    sc = H.random_scalars_np(np.random.default_rng(3), n)
+    want = C.g1_to_affine(C.msm(hb, sc)).tobytes()
+    for cycle in range(2):
+        # through the coalescing queue: scratch cached on the dispatcher's stream
+        tk = ctypes.c_uint64(0)
+        out = np.zeros(144, dtype=np.uint8)
+        _lib.check(L.b200_msm_submit(hb.ctypes.data_as(ctypes.c_void_p), n, sc.ctypes.data_as(ctypes.c_void_p), 104, ctypes.byref(tk)))
+        _lib.check(L.b200_msm_wait(tk.value, out.ctypes.data_as(ctypes.c_void_p)))
+        assert C.g1_to_affine(out).tobytes() == want
+        # on a caller's stream that is destroyed right afterwards: its cache stays behind
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            dev = S.VariableBase.msm(torch.from_numpy(hb).cuda(), torch.from_numpy(sc.view(np.int64)).cuda())
+        st.synchronize()
+        assert C.g1_to_affine(dev.cpu().numpy()).tobytes() == want
+        del st
+        if cycle == 0:
+            S.release_scratch()
+            assert C.g1_to_affine(S.VariableBase.msm(hb, sc)).tobytes() == want
+        torch.cuda.synchronize()
+        L.b200_shutdown()
+        S.init(0)
+        assert C.g1_to_affine(S.VariableBase.msm(hb, sc)).tobytes() == want

@@ -7,6 +7,9 @@
 // Results of the three are compared through b200_g1_compress.  Prints one JSON line.  Python threads cannot show this
 // (the GIL serialises the submits): bench.py runs this binary for its batch_verify_msm entry.
 #include <cuda_runtime.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -27,7 +30,18 @@ static uint64_t splitmix(uint64_t& s) {
 }
 #define CHECK(e) do { b200_error_t _r = (e); if (_r.code != 0) { fprintf(stderr, "error %d: %s (%s)\n", _r.code, _r.msg, #e); exit(1); } } while (0)
 
+static void on_segv(int sig) {                      // a crash must say where: frames resolve with addr2line against the .so
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "queue_bench: fatal signal, backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char** argv) {
+    signal(SIGSEGV, on_segv);
+    signal(SIGABRT, on_segv);
     const int T = argc > 1 ? atoi(argv[1]) : 64, M = argc > 2 ? atoi(argv[2]) : 4, P = argc > 3 ? atoi(argv[3]) : 40;
     const int reps = argc > 4 ? atoi(argv[4]) : 7;
     const size_t nmsm = (size_t)T * M, npts = nmsm * P;
