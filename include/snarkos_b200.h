@@ -61,7 +61,7 @@ enum { B200_NTT_FORWARD = 0, B200_NTT_INVERSE = 1 };
  * tables.  Idempotent.  b200_shutdown releases every cached table and registered base set. */
 b200_error_t b200_init(int device);
 void b200_shutdown(void);
-/* Hands every cached scratch block (per-thread, per-stream caches of the calls' temporaries, up to 40 GiB in total) back
+/* Hands every cached scratch block (per-stream caches of the calls' temporaries, up to 40 GiB in total) back
  * to the driver's pool and trims that pool: for a long-running node between proving bursts, or before another library
  * needs the memory.  Never required for correctness: an allocation that fails does the same before it retries. */
 b200_error_t b200_release_scratch(void);
@@ -69,12 +69,12 @@ b200_error_t b200_release_scratch(void);
 uint32_t b200_abi_version(void);
 /* Tuning knobs.  The B200_* environment variables are read once, on first use; this call changes a knob afterwards
  * (sweep tools, tests, the -sys crate's init).  Keys: msm_window_bits, msm_glv, msm_affine_rounds, msm_slices,
- * msm_chunk, msm_host_pipeline, msm_host_first_log, msm_auto_table, msm_list_budget_bytes, msm_fuse_denoms,
+ * msm_chunk, msm_host_pipeline, msm_host_first_log, msm_auto_table, msm_list_budget_bytes,
  * msm_queue_threshold, ntt_plan ("a,b,c"), ntt_tile_log, ntt_radix4, ntt_boundary_tables, ntt_host_pipeline, ntt_variant,
- * staged_copies, graphs.  Unknown key -> B200_ERR_INVALID_ARG. */
+ * staged_copies.  Unknown key -> B200_ERR_INVALID_ARG. */
 b200_error_t b200_set_option(const char* key, const char* value);
 /* Observable fallbacks / activity: kernel_launches, msm_xyzz_fallbacks (calls whose pair-round lists did not fit in HBM
- * and ran the XYZZ-only accumulation), queue_submits, queue_batches, graph_captures, graph_replays, streams_created (per-thread
+ * and ran the XYZZ-only accumulation), queue_submits, queue_batches, streams_created (per-thread
  * CUDA streams alive: bounded by the number of threads calling at the same time, exited threads hand theirs back). */
 b200_error_t b200_get_counter(const char* name, uint64_t* out);
 

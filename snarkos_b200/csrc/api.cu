@@ -258,7 +258,6 @@ static void config_from_env(B200Config& c) {
     c.msm_host_pipeline = !getenv("B200_MSM_NO_HOST_PIPELINE");
     c.msm_host_first_log = env_int("B200_MSM_HOST_FIRST_LOG", 20);
     c.msm_auto_table = !getenv("B200_MSM_NO_AUTO_TABLE");
-    c.msm_fuse_denoms = getenv("B200_MSM_NO_FUSE_DENOMS") ? 0 : 1;
     c.msm_queue_threshold = env_int("B200_MSM_QUEUE_THRESHOLD", 0);
     if (const char* e = getenv("B200_NTT_PLAN")) { strncpy(c.ntt_plan, e, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
     c.ntt_tile_log = env_int("B200_NTT_TILE_LOG", 0);
@@ -268,7 +267,6 @@ static void config_from_env(B200Config& c) {
     c.ntt_variant = env_int("B200_NTT_VARIANT", 0);
     c.staged_copies = !getenv("B200_NO_STAGED_COPIES");
     c.l2_fetch_granularity = env_int("B200_L2_FETCH_GRANULARITY", 0);
-    c.graphs = !getenv("B200_NO_GRAPHS");
 }
 B200Config& b200_config() {
     static B200Config cfg;
@@ -291,7 +289,6 @@ extern "C" b200_error_t b200_set_option(const char* key, const char* value) {
     else if (k == "msm_host_first_log") c.msm_host_first_log = v;
     else if (k == "msm_auto_table") c.msm_auto_table = v != 0;
     else if (k == "msm_list_budget_bytes") c.msm_list_budget = strtoull(value, nullptr, 0);
-    else if (k == "msm_fuse_denoms") c.msm_fuse_denoms = v;
     else if (k == "msm_queue_threshold") c.msm_queue_threshold = v;
     else if (k == "ntt_plan") { strncpy(c.ntt_plan, value, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
     else if (k == "ntt_tile_log") c.ntt_tile_log = v;
@@ -300,7 +297,6 @@ extern "C" b200_error_t b200_set_option(const char* key, const char* value) {
     else if (k == "ntt_host_pipeline") c.ntt_host_pipeline = v != 0;
     else if (k == "ntt_variant") c.ntt_variant = v;
     else if (k == "staged_copies") c.staged_copies = v != 0;
-    else if (k == "graphs") c.graphs = v != 0;
     else return b200_err(B200_ERR_INVALID_ARG, "set_option: unknown key");
     return b200_ok();
 }
@@ -312,8 +308,6 @@ extern "C" b200_error_t b200_get_counter(const char* name, uint64_t* out) {
     else if (k == "msm_xyzz_fallbacks") *out = g_counters.msm_xyzz_fallbacks.load();
     else if (k == "queue_submits") *out = g_counters.queue_submits.load();
     else if (k == "queue_batches") *out = g_counters.queue_batches.load();
-    else if (k == "graph_replays") *out = g_counters.graph_replays.load();
-    else if (k == "graph_captures") *out = g_counters.graph_captures.load();
     else if (k == "streams_created") {
         std::lock_guard<std::mutex> lock(g_api.mu);
         *out = g_api.streams.size();
@@ -398,7 +392,6 @@ extern "C" void b200_shutdown(void) {
     g_api.bases.clear();
     b200_scratch_release_all();
     ntt_release_tables();
-    msm_release_graphs();
     hostcopy_release();
     // per-thread streams: the owning threads notice the new generation and create fresh ones on their next call
     for (cudaStream_t s : g_api.streams) cudaStreamDestroy(s);

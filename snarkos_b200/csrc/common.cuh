@@ -50,7 +50,6 @@ struct B200Config {
                                      //                          runs the XYZZ-only path, exactly as on an allocation failure
     int msm_queue_threshold = 0;     // msm_queue_threshold      B200_MSM_QUEUE_THRESHOLD  host MSMs of <= this many points go
                                      //                          through the coalescing queue (queue.cu); 0 = off
-    int msm_fuse_denoms = 1;         // msm_fuse_denoms          B200_MSM_NO_FUSE_DENOMS (pair round r computes round r+1's denominators)
     char ntt_plan[32] = {0};         // ntt_plan "a,b,c"         B200_NTT_PLAN
     int ntt_tile_log = 0;            // ntt_tile_log             B200_NTT_TILE_LOG
     bool ntt_radix4 = true;          // ntt_radix4               B200_NTT_RADIX2
@@ -60,7 +59,6 @@ struct B200Config {
                                      //                          1 = bulk-copy TMA, 3 = 256-thread CTAs only, 4 = warp-column kernel for 2^8 passes
     bool staged_copies = true;       // staged_copies            B200_NO_STAGED_COPIES
     int l2_fetch_granularity = 0;    // (init only)              B200_L2_FETCH_GRANULARITY
-    bool graphs = true;              // graphs                   B200_NO_GRAPHS         CUDA-graph replay of small calls
 };
 B200Config& b200_config();           // loaded from the environment on first use
 
@@ -68,7 +66,6 @@ B200Config& b200_config();           // loaded from the environment on first use
 struct B200Counters {
     std::atomic<uint64_t> msm_xyzz_fallbacks{0};     // pair rounds skipped: lists did not fit (allocation failure / budget)
     std::atomic<uint64_t> queue_submits{0}, queue_batches{0};
-    std::atomic<uint64_t> graph_replays{0}, graph_captures{0};
 };
 extern B200Counters g_counters;
 
@@ -154,7 +151,6 @@ b200_error_t msm_pack_bases_device(void* d_packed, const void* d_points, size_t 
 b200_error_t b200_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream);
 b200_error_t b200_d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream);
 void ntt_release_tables();
-void msm_release_graphs();           // cached CUDA graphs of small MSMs (msm.cu)
 void hostcopy_release();             // pinned staging slots (hostcopy.cu)
 void b200_queue_shutdown();          // submit / wait dispatcher (queue.cu)
 cudaStream_t b200_thread_copy_stream();

@@ -1127,7 +1127,6 @@ b200_error_t msm_stream_finish(void* session, void* d_out, cudaStream_t stream) 
     return r;
 }
 
-void msm_release_graphs() {}
 
 void msm_stream_abort(void* session) { delete reinterpret_cast<MsmStream*>(session); }
 
