@@ -408,6 +408,8 @@ def run_b200(args):
             fabric = D.PeerExchange(per)
             variants = {"fused_natural": lambda: D.ntt_distributed_fused(blk, L26, fabric, natural_out=True),
                         "fused_slab": lambda: D.ntt_distributed_fused(blk, L26, fabric, natural_out=False),
+                        "fused_separate_kernels_natural": lambda: D.ntt_distributed_fused(blk, L26, fabric, natural_out=True, fuse_transforms=False),
+                        "fused_separate_kernels_slab": lambda: D.ntt_distributed_fused(blk, L26, fabric, natural_out=False, fuse_transforms=False),
                         "nccl_natural": lambda: D.ntt_distributed(blk, L26, natural_out=True),
                         "nccl_slab": lambda: D.ntt_distributed(blk, L26, natural_out=False)}
             for name, fn in variants.items():

@@ -246,6 +246,15 @@ b200_error_t b200_fr_exchange_transpose_part_device(const void* d_src_slab, void
                                                     unsigned long long col_lo, unsigned long long col_cnt, uint32_t log_n,
                                                     int direction, int twiddle, unsigned long long row_base,
                                                     uint32_t cta_limit, void* stream);
+/* The local transform and the exchange in ONE launch set: `rows` rows of 2^log_len elements at d_rows (row-major, left
+ * unchanged) are transformed (direction as in b200_ntt_fr_bls12_377; the inverse scales by 2^-log_len) and the LAST pass
+ * of the transform stores every output (row, col) -- times w_N^((row_base + row) * col), N = 2^log_n_total, when
+ * `twiddle` -- straight to its place in the transposed slab of the rank that owns column col, exactly where
+ * b200_fr_exchange_transpose_device would put it: no local slab is written and read again between the butterflies and
+ * the peer stores.  Tiles of that pass hold up to 16 adjacent rows, so every column leaves as one run of up to 512 B. */
+b200_error_t b200_ntt_rows_exchange_device(const void* d_rows, void* const* dst_ptrs, uint32_t world, uint32_t rank,
+                                           unsigned long long rows, uint32_t log_len, uint32_t log_n_total, int direction,
+                                           int twiddle, unsigned long long row_base, void* stream);
 /* Exchange buffers: cudaMalloc memory with its 64-byte CUDA IPC handle (sent to the other ranks by the caller), the
  * mapping of a peer's buffer into this process, and their release. */
 b200_error_t b200_peer_buffer_alloc(size_t bytes, void** d_ptr, void* handle64);

@@ -71,6 +71,7 @@ pub mod sys {
         pub fn b200_fr_mul_powers_device(d_data: *mut c_void, log_n: u32, direction: c_int, kind: c_int, rows: u64, cols: u64, row_base: u64, col_base: u64, stream: *mut c_void) -> b200_error_t;
         pub fn b200_fr_exchange_transpose_device(d_src: *const c_void, dst_ptrs: *const *mut c_void, world: u32, rank: u32, r_local: u64, c: u64, log_n: u32, direction: c_int, twiddle: c_int, row_base: u64, stream: *mut c_void) -> b200_error_t;
         pub fn b200_fr_exchange_transpose_part_device(d_src_slab: *const c_void, dst_ptrs: *const *mut c_void, world: u32, rank: u32, r_local: u64, row_off: u64, r_count: u64, c: u64, col_lo: u64, col_cnt: u64, log_n: u32, direction: c_int, twiddle: c_int, row_base: u64, cta_limit: u32, stream: *mut c_void) -> b200_error_t;
+        pub fn b200_ntt_rows_exchange_device(d_rows: *const c_void, dst_ptrs: *const *mut c_void, world: u32, rank: u32, rows: u64, log_len: u32, log_n_total: u32, direction: c_int, twiddle: c_int, row_base: u64, stream: *mut c_void) -> b200_error_t;
         pub fn b200_peer_buffer_alloc(bytes: usize, d_ptr: *mut *mut c_void, handle64: *mut c_void) -> b200_error_t;
         pub fn b200_peer_buffer_open(handle64: *const c_void, d_ptr: *mut *mut c_void) -> b200_error_t;
         pub fn b200_peer_buffer_close(d_ptr: *mut c_void) -> b200_error_t;

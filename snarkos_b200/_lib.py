@@ -67,6 +67,7 @@ SYMBOLS = {
     "b200_fr_mul_powers_device": (b200_error_t, [_vp, _u32, _i, _i, _u64, _u64, _u64, _u64, _vp]),
     "b200_fr_exchange_transpose_device": (b200_error_t, [_vp, ctypes.POINTER(_vp), _u32, _u32, _u64, _u64, _u32, _i, _i, _u64, _vp]),
     "b200_fr_exchange_transpose_part_device": (b200_error_t, [_vp, ctypes.POINTER(_vp), _u32, _u32, _u64, _u64, _u64, _u64, _u64, _u64, _u32, _i, _i, _u64, _u32, _vp]),
+    "b200_ntt_rows_exchange_device": (b200_error_t, [_vp, ctypes.POINTER(_vp), _u32, _u32, _u64, _u32, _u32, _i, _i, _u64, _vp]),
     "b200_peer_buffer_alloc": (b200_error_t, [_sz, ctypes.POINTER(_vp), _vp]),
     "b200_peer_buffer_open": (b200_error_t, [_vp, ctypes.POINTER(_vp)]),
     "b200_peer_buffer_close": (b200_error_t, [_vp]),

@@ -437,7 +437,6 @@ extern "C" b200_error_t b200_fr_mul_powers_device(void* d_data, uint32_t log_n, 
 // that column -- peer memory over NVLink when that rank is another GPU (dst[d] = that rank's buffer, opened through
 // CUDA IPC).  Replaces: local re-tiling pass, NCCL all-to-all, second re-tiling pass and the separate twiddle pass.
 // ---------------------------------------------------------------------------------------------
-#define NTT_XCHG_MAX_WORLD 16
 #define NTT_XCHG_TILE 32
 struct NttExchangeParams {
     const uint4* src;               // first row of the part of the slab this launch handles
@@ -604,8 +603,21 @@ void ntt_release_tables() {
 
 static bool ntt_wc_applicable_host(const NttPlan& plan, uint32_t i) { return plan.log_len[i] == WC_LOG_LEN && plan.log_cw[i] == WC_LOG_CW; }
 
+// fused exchange of the LAST pass (multi-GPU four-step transform): see NttPassParams::xchg in ntt_core.cuh
+struct NttXchg {
+    void* const* dst_ptrs;          // host array of `world` device pointers
+    uint32_t world, rank, log_n_total;
+    int twiddle;
+    unsigned long long row_base;
+};
+static b200_error_t ntt_run_device_x(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction, int coset,
+                                     cudaStream_t stream, const NttXchg* xc);
 b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction,
                             int coset, cudaStream_t stream) {
+    return ntt_run_device_x(d_inout, log_n, batch, batch_stride, direction, coset, stream, nullptr);
+}
+static b200_error_t ntt_run_device_x(void* d_inout, uint32_t log_n, size_t batch, size_t batch_stride, int direction, int coset,
+                                     cudaStream_t stream, const NttXchg* xc) {
     if (log_n > NTT_MAX_LOG_N) return b200_err(B200_ERR_TOO_LARGE, "ntt: log_n > 28 is not supported");
     if (direction != 0 && direction != 1) return b200_err(B200_ERR_INVALID_ARG, "ntt: direction must be 0 or 1");
     if (batch == 0) return b200_ok();
@@ -625,6 +637,19 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
     NttDomainTables tabs;
     const uint4* tile_tw = nullptr;
     B200_TRY(get_tables(log_n, direction, stream, &tabs, &tile_tw, &plan));
+    NttDomainTables xtabs;
+    if (xc) {
+        // last pass in "adjacent rows" tiles: 2^cw rows of one sub-problem each (1024-element tiles, at most 16 rows)
+        const uint32_t ll = plan.log_len[plan.npasses - 1];
+        uint32_t cw = ll >= 10 ? 0 : 10 - ll;
+        if (cw > 4) cw = 4;
+        while (cw && (batch & ((1u << cw) - 1))) cw--;
+        plan.log_cw[plan.npasses - 1] = cw;
+        if (xc->twiddle) {
+            const uint4* unused = nullptr;
+            B200_TRY(get_tables(xc->log_n_total, direction, stream, &xtabs, &unused));
+        }
+    }
 
     DevBuf scratch;
     if (plan.npasses > 1) CUDA_TRY(scratch.alloc(((batch - 1) * batch_stride + n) * 32, stream));
@@ -652,6 +677,19 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         p.scale_post = (last && direction == 1) ? 1 : 0;
         p.coset_post = (last && coset && direction == 1) ? 1 : 0;
         p.radix4 = b200_config().ntt_radix4 ? 1 : 0;
+        const bool xpass = xc && last;
+        if (xpass) {
+            p.xchg = 1;
+            p.x_world = xc->world;
+            p.x_rank = xc->rank;
+            p.x_twiddle = xc->twiddle ? 1 : 0;
+            p.x_log_n = xc->log_n_total;
+            p.x_r_total = batch;
+            p.x_row_base = xc->row_base;
+            p.x_pow_lo = xtabs.pow_lo;
+            p.x_pow_hi = xtabs.pow_hi;
+            for (uint32_t d = 0; d < xc->world; d++) p.x_dst[d] = reinterpret_cast<uint4*>(xc->dst_ptrs[d]);
+        }
         const uint32_t pass_tile_log = plan.log_len[i] + plan.log_cw[i];
         const uint32_t tile_elems = 1u << pass_tile_log;
         uint32_t threads = tile_elems / 2;
@@ -661,7 +699,7 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
         STAGE(kPassName[i], stream);
         const uint32_t tiles_per_poly = 1u << (log_n - pass_tile_log);
         const unsigned long long total_tiles = (unsigned long long)tiles_per_poly * batch;
-        if (b200_config().ntt_variant == 1 && threads == 256 && total_tiles < (1ull << 31)) {
+        if (b200_config().ntt_variant == 1 && threads == 256 && total_tiles < (1ull << 31) && !xpass) {
             // bulk-copy (TMA) variant: persistent CTAs over all tiles of the batch, two tile buffers
             const uint32_t buf_elems = ntt_bulk_tile_elems(plan.log_len[i], plan.log_cw[i], last ? 1u : 0u);
             const size_t smem = NTT_BULK_HEADER_U4 * 16 + ((size_t)1 << plan.log_len[i]) * 16 + 2 * (size_t)buf_elems * 32;
@@ -676,6 +714,15 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
             }
         }
         dim3 grid(tiles_per_poly, (unsigned)batch);
+        if (xpass) {
+            // one tile = one sub-problem of 2^cw adjacent rows; generic kernels (run-time flags), 8 elements per thread
+            grid = dim3(1u << (log_n - plan.log_len[i]), (unsigned)(batch >> plan.log_cw[i]));
+            const size_t xsmem = (size_t)tile_elems * 32 + ((size_t)1 << plan.log_len[i]) * 16;
+            if (tile_elems == 1024) ntt_pass_kernel_128<<<grid, 128, xsmem, stream>>>(p);
+            else ntt_pass_kernel<<<grid, threads, xsmem, stream>>>(p);
+            KERNEL_CHECK();
+            continue;
+        }
         // Warp-column kernel: built, bit-exact, measured and NOT the default -- 4.12 ms against 3.43 ms at 2^24 (ncu
         // profiles/r02_ncu_ntt_wc.txt: 30 k instructions of straight-line code per tile, `no_instruction` stalls 2.9 - 3.6
         // per issue, 16 warps per SM at 128 registers, multiplier pipe 66 - 70 % busy); option ntt_variant = 4 selects it.
@@ -709,3 +756,28 @@ b200_error_t ntt_run_device(void* d_inout, uint32_t log_n, size_t batch, size_t 
     STAGE_END(stream);
     return b200_ok();
 }
+
+// Batch of row transforms whose last pass IS the exchange (see NttPassParams::xchg): `rows` rows of 2^log_len elements at
+// d_rows (row-major, not modified) are transformed and every output (row, col) is stored -- times w_N^((row_base + row) * col)
+// when `twiddle` -- at its place in the transposed slab of the rank that owns column col.
+extern "C" b200_error_t b200_ntt_rows_exchange_device(const void* d_rows, void* const* dst_ptrs, uint32_t world, uint32_t rank,
+                                                      unsigned long long rows, uint32_t log_len, uint32_t log_n_total,
+                                                      int direction, int twiddle, unsigned long long row_base, void* stream) {
+    B200_TRY(b200_require_device());
+    if (world == 0 || world > NTT_XCHG_MAX_WORLD || rank >= world || log_n_total > NTT_MAX_LOG_N || log_len == 0 || log_len > log_n_total)
+        return b200_err(B200_ERR_INVALID_ARG, "ntt_rows_exchange: bad argument");
+    if (rows == 0) return b200_ok();
+    if (!d_rows || !dst_ptrs) return b200_err(B200_ERR_INVALID_ARG, "ntt_rows_exchange: null pointer");
+    if (((1ull << log_len) % world) != 0) return b200_err(B200_ERR_INVALID_ARG, "ntt_rows_exchange: row length must divide by the world size");
+    for (uint32_t d = 0; d < world; d++)
+        if (!dst_ptrs[d]) return b200_err(B200_ERR_INVALID_ARG, "ntt_rows_exchange: null destination");
+    NttXchg xc;
+    xc.dst_ptrs = dst_ptrs;
+    xc.world = world;
+    xc.rank = rank;
+    xc.log_n_total = log_n_total;
+    xc.twiddle = twiddle;
+    xc.row_base = row_base;
+    return ntt_run_device_x(const_cast<void*>(d_rows), log_len, (size_t)rows, (size_t)1 << log_len, direction, 0, (cudaStream_t)stream, &xc);
+}
+

@@ -52,7 +52,18 @@ struct NttPassParams {
     uint32_t scale_post;            // multiply output by n^-1     (inverse, last pass)
     uint32_t coset_post;            // multiply output j by g^-j   (inverse coset, last pass)
     uint32_t radix4;                // 1: process stage pairs on register quads (default), 0: radix-2 stages only
+    // Fused exchange of the multi-GPU four-step transform (xchg != 0, LAST pass of a batch of row transforms only): the
+    // pass stores its outputs straight into the slabs of the ranks that own them -- transposed, optionally times the
+    // twiddle between the two transform axes -- instead of writing the local slab for a separate exchange kernel.  The
+    // tile then holds ONE sub-problem of 2^log_cw ADJACENT ROWS (polynomials), so that for every output column the rows
+    // of the tile form one contiguous run of 2^log_cw * 32 B in the destination slab.
+    uint32_t xchg, x_world, x_rank, x_twiddle, x_log_n;     // x_log_n: log2 of the distributed transform (twiddle domain)
+    unsigned long long x_r_total, x_row_base;               // rows per rank, global index of this rank's row 0
+    const uint4* x_pow_lo;          // w_N^e for the distributed size N = 2^x_log_n (two-level tables)
+    const uint4* x_pow_hi;
+    uint4* x_dst[16];               // destination slab of every rank (peer memory for the others)
 };
+#define NTT_XCHG_MAX_WORLD 16
 
 // ---------------------------------------------------------------------------------------------
 // element access helpers (global / shared element = two uint4 halves)
@@ -151,6 +162,14 @@ B200_HD unsigned long long ntt_in_index(const NttPassParams& p, const NttGeom& g
     return (row << g.log_len) + t;
 }
 
+// Fused-exchange last pass: element offset (from p.src, in elements) of tile element (t, cw): row (batch << log_cw) + cw of
+// the batch, sub-problem `tile` of that row (its 2^log_len contiguous elements).
+B200_HD unsigned long long ntt_xchg_in_offset(const NttPassParams& p, const NttGeom& g, uint32_t tile, uint32_t batch, uint32_t t,
+                                              uint32_t cw) {
+    const unsigned long long row = ((unsigned long long)batch << g.log_cw) + cw;
+    return row * p.batch_stride + ((unsigned long long)tile << g.log_len) + t;
+}
+
 // ---------------------------------------------------------------------------------------------
 // phase 1: global -> shared (coalesced), optional coset pre-scaling
 // ---------------------------------------------------------------------------------------------
@@ -159,7 +178,7 @@ B200_HD void ntt_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, ui
                             uint32_t nthreads_rt) {
     const NttGeom g = ntt_geom_t<SH>(p);
     const uint32_t nthreads = ntt_nthreads<SH>(nthreads_rt);
-    const uint4* src = p.src + 2ull * batch * p.batch_stride;
+    const uint4* src = (g.last && p.xchg) ? p.src : p.src + 2ull * batch * p.batch_stride;       // xchg: the offset carries the row
     uint32_t total = 2u * g.tile_elems;                 // 16-byte words
     // Batches of NTT_LOAD_BATCH independent global loads before their shared-memory stores: the trip count is a run-time
     // value, so the compiler keeps ONE load in flight per thread otherwise and the phase pays the global latency once per
@@ -178,7 +197,7 @@ B200_HD void ntt_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, ui
             uint32_t t, cw;
             if (!g.last) { cw = e & ((1u << g.log_cw) - 1); t = e >> g.log_cw; }      // cw fastest in memory
             else         { t = e & ((1u << g.log_len) - 1); cw = e >> g.log_len; }    // t fastest in memory
-            unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
+            unsigned long long idx = (g.last && p.xchg) ? ntt_xchg_in_offset(p, g, tile, batch, t, cw) : ntt_in_index(p, g, tile, t, cw);
             v[k] = src[2 * idx + half];
             dst[k] = half * g.tile_elems + ((t << g.log_cw) + cw);
         }
@@ -190,7 +209,7 @@ B200_HD void ntt_phase_load(const NttPassParams& p, uint4* sm, uint32_t tile, ui
         uint32_t t, cw;
         if (!g.last) { cw = e & ((1u << g.log_cw) - 1); t = e >> g.log_cw; }
         else         { t = e & ((1u << g.log_len) - 1); cw = e >> g.log_len; }
-        unsigned long long idx = ntt_in_index(p, g, tile, t, cw);
+        unsigned long long idx = (g.last && p.xchg) ? ntt_xchg_in_offset(p, g, tile, batch, t, cw) : ntt_in_index(p, g, tile, t, cw);
         sm[half * g.tile_elems + ((t << g.log_cw) + cw)] = src[2 * idx + half];
     }
 }
@@ -348,9 +367,43 @@ B200_HD void ntt_store_source(const NttGeom& g, uint32_t e, uint32_t& t, uint32_
 }
 template <int STORE = 0>
 B200_HD void ntt_store_element(const NttPassParams& p, const NttGeom& g, fr_t x, uint4* dst, uint32_t tile, uint32_t e,
-                               bool have_tw, const fr_t& tw) {
+                               bool have_tw, const fr_t& tw, uint32_t batch = 0) {
     uint32_t cw = e & ((1u << g.log_cw) - 1), k = e >> g.log_cw;          // k = output index of this pass
     unsigned long long out;
+    if (STORE == 0 && g.last && p.xchg) {
+        // column of this output inside its row: digit reversal of the sub-problem index `tile` = (k0, k1, ..) and k
+        const uint32_t log_rows = p.log_n - g.log_len;
+        unsigned long long col;
+        if (p.npasses == 1) {
+            col = k;
+        } else {
+            const uint32_t l0 = p.log_len[0];
+            unsigned long long acc = (unsigned long long)tile >> (log_rows - l0);      // k0
+            const unsigned long long rest = tile & ((1ull << (log_rows - l0)) - 1);
+            uint32_t shift = l0, rem_bits = log_rows - l0;
+            for (uint32_t i = 1; i + 1 < p.npasses; i++) {
+                rem_bits -= p.log_len[i];
+                acc += ((rest >> rem_bits) & ((1ull << p.log_len[i]) - 1)) << shift;
+                shift += p.log_len[i];
+            }
+            col = acc + ((unsigned long long)k << log_rows);
+        }
+        const unsigned long long row = ((unsigned long long)batch << g.log_cw) + cw;     // local row of the slab
+        if (p.scale_post) x = fp_mul(x, p.size_inv);
+        if (p.x_twiddle) {
+            const unsigned long long ex = ((p.x_row_base + row) * col) & ((1ull << p.x_log_n) - 1);
+            if (ex) x = fp_mul(x, pow2level(p.x_pow_lo, p.x_pow_hi, ex));
+        }
+        // destination: the rank that owns column `col` of the [r_total * world x 2^log_n] matrix, transposed slab
+        const unsigned long long c_local = (1ull << p.log_n) / p.x_world;
+        const unsigned long long d = col / c_local, cl = col - d * c_local;
+        uint4* o = p.x_dst[d] + 2 * (cl * (p.x_r_total * p.x_world) + (unsigned long long)p.x_rank * p.x_r_total + row);
+        uint4 lo, hi;
+        fr_to_u4(x, lo, hi);
+        o[0] = lo;
+        o[1] = hi;
+        return;
+    }
     if (STORE == 1) {                                                     // strided pass, twiddle already fetched
         uint32_t log_tiles_per_sub = g.log_stride - g.log_cw;
         unsigned long long sub = tile >> log_tiles_per_sub;
@@ -443,7 +496,7 @@ B200_HD void ntt_phase_store_t(const NttPassParams& p, const Tile& T, uint32_t t
             for (int q = 0; q < NTT_STORE_BATCH; q++) {
                 uint32_t t, cw;
                 ntt_store_source(g, e + q * nthreads, t, cw);
-                ntt_store_element<SH::store>(p, g, T.get(t, cw), dst, tile, e + q * nthreads, true, tw[q]);
+                ntt_store_element<SH::store>(p, g, T.get(t, cw), dst, tile, e + q * nthreads, true, tw[q], batch);
             }
         }
     }
@@ -452,7 +505,7 @@ B200_HD void ntt_phase_store_t(const NttPassParams& p, const Tile& T, uint32_t t
     for (; e < g.tile_elems; e += nthreads) {
         uint32_t t, cw;
         ntt_store_source(g, e, t, cw);
-        ntt_store_element(p, g, T.get(t, cw), dst, tile, e, false, none);
+        ntt_store_element(p, g, T.get(t, cw), dst, tile, e, false, none, batch);
     }
 }
 template <class SH = NttDyn>

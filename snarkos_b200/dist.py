@@ -246,6 +246,15 @@ class PeerExchange:
         self._opened, self._own = [], []
 
 
+def ntt_rows_exchange(rows: torch.Tensor, dst_ptrs, world: int, rank: int, r_local: int, log_len: int, log_n: int, direction: int,
+                      twiddle: bool, row_base: int = 0) -> None:
+    """row transforms + exchange in one launch set: rows = this rank's [r_local, 2^log_len] slab (left unchanged); the last
+    pass of the transforms stores every output where `exchange_transpose` would put it (b200_ntt_rows_exchange_device)"""
+    _lib.check(_lib.lib().b200_ntt_rows_exchange_device(
+        ctypes.c_void_p(rows.data_ptr()), dst_ptrs, world, rank, r_local, log_len, log_n, direction, 1 if twiddle else 0, row_base,
+        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
 def exchange_transpose(src: torch.Tensor, dst_ptrs, world: int, rank: int, r_local: int, c: int, log_n: int, direction: int,
                        twiddle: bool, row_base: int = 0) -> None:
     """one fused exchange: src = this rank's [r_local, c] slab; dst_ptrs[d] = rank d's [c / world, r_local * world] slab"""
@@ -354,9 +363,11 @@ def ntt_distributed_overlapped(block: torch.Tensor, log_n: int, fabric: PeerExch
 
 
 def ntt_distributed_fused(block: torch.Tensor, log_n: int, fabric: PeerExchange, direction: int = 0, coset: int = 0,
-                          natural_out: bool = True, log_n1: Optional[int] = None) -> torch.Tensor:
+                          natural_out: bool = True, log_n1: Optional[int] = None, fuse_transforms: bool = True) -> torch.Tensor:
     """`ntt_distributed` with the exchanges fused into peer-memory stores.  Returns a VIEW of one of the fabric's
-    slabs (valid until the next call on the same fabric): natural-order block, or the k1 slab if not natural_out."""
+    slabs (valid until the next call on the same fabric): natural-order block, or the k1 slab if not natural_out.
+    fuse_transforms: the second and third exchange are the LAST PASS of the row transforms before them (one launch set:
+    butterflies, twiddle and peer stores; no local slab written and read again); False keeps them as separate kernels."""
     ops = CudaOps()
     world, rank = fabric.world, fabric.rank
     n = 1 << log_n
@@ -378,13 +389,20 @@ def ntt_distributed_fused(block: torch.Tensor, log_n: int, fabric: PeerExchange,
     fabric.barrier()                                               # every rank is done with the slabs of the previous call
     exchange_transpose(block, fabric.dst_array(0), world, rank, n1 // world, n2, log_n, direction, False)
     fabric.barrier()                                               # B = [N2/world, N1]: my columns j2, all j1
-    ops.ntt_rows(B.view(n2 // world, n1, FR_LIMBS), n1_log, direction)
-    exchange_transpose(B, fabric.dst_array(1), world, rank, n2 // world, n1, log_n, direction, True, rank * (n2 // world))
+    if fuse_transforms:
+        ntt_rows_exchange(B, fabric.dst_array(1), world, rank, n2 // world, n1_log, log_n, direction, True, rank * (n2 // world))
+    else:
+        ops.ntt_rows(B.view(n2 // world, n1, FR_LIMBS), n1_log, direction)
+        exchange_transpose(B, fabric.dst_array(1), world, rank, n2 // world, n1, log_n, direction, True, rank * (n2 // world))
     fabric.barrier()                                               # C = [N1/world, N2]: my k1, all j2, twiddled
-    ops.ntt_rows(C.view(n1 // world, n2, FR_LIMBS), n2_log, direction)
     if not natural_out:
+        ops.ntt_rows(C.view(n1 // world, n2, FR_LIMBS), n2_log, direction)
         return C.view(n1 // world, n2, FR_LIMBS)
-    exchange_transpose(C, fabric.dst_array(0), world, rank, n1 // world, n2, log_n, direction, False)
+    if fuse_transforms:
+        ntt_rows_exchange(C, fabric.dst_array(0), world, rank, n1 // world, n2_log, log_n, direction, False)
+    else:
+        ops.ntt_rows(C.view(n1 // world, n2, FR_LIMBS), n2_log, direction)
+        exchange_transpose(C, fabric.dst_array(0), world, rank, n1 // world, n2, log_n, direction, False)
     fabric.barrier()                                               # B = [N2/world, N1]: my k2 range = natural block
     out = B.view(per, FR_LIMBS)
     if coset and direction == 1:

@@ -217,3 +217,76 @@ extern "C" int host_ntt_variant(uint32_t* data, uint32_t log_n, uint32_t batch, 
     }
     return 0;
 }
+
+// Host emulation of b200_ntt_rows_exchange_device (ntt_run_device_x with an exchange descriptor): `rows` rows of
+// 2^log_len elements are transformed with the generic phases and the LAST pass stores into `world` destination slabs
+// (dsts[d], each c_local x (rows * world) elements) exactly as the kernel does.
+extern "C" int host_ntt_rows_exchange(const uint32_t* data, uint64_t rows, uint32_t log_len, uint32_t world, uint32_t rank,
+                                      uint32_t log_n_total, int direction, int twiddle, uint64_t row_base, uint32_t** dsts,
+                                      uint32_t nthreads) {
+    NttPlan plan;
+    const uint32_t tile_log = (log_len + 8) / 9 < (log_len + 7) / 8 ? 11 : 10;
+    if (!ntt_make_plan(log_len, &plan, tile_log)) return -1;
+    {
+        const uint32_t ll = plan.log_len[plan.npasses - 1];
+        uint32_t cw = ll >= 10 ? 0 : 10 - ll;
+        if (cw > 4) cw = 4;
+        while (cw && (rows & ((1u << cw) - 1))) cw--;
+        plan.log_cw[plan.npasses - 1] = cw;
+    }
+    const uint32_t* root = direction ? FR_TWO_ADIC_ROOT_INV : FR_TWO_ADIC_ROOT;
+    const uint32_t lo_count = 1u << NTT_POW_LO_LOG;
+    auto hi_count = [&](uint32_t lg) { return lg > NTT_POW_LO_LOG ? (1u << (lg - NTT_POW_LO_LOG)) : 1u; };
+    auto tile_tw = pow_table(root, FR_TWO_ADICITY - NTT_TILE_TW_LOG, 1u << (NTT_TILE_TW_LOG - 1), 0);
+    auto pow_lo = pow_table(root, FR_TWO_ADICITY - log_len, lo_count, 0);
+    auto pow_hi = pow_table(root, FR_TWO_ADICITY - log_len, hi_count(log_len), NTT_POW_LO_LOG);
+    auto xpow_lo = pow_table(root, FR_TWO_ADICITY - log_n_total, lo_count, 0);
+    auto xpow_hi = pow_table(root, FR_TWO_ADICITY - log_n_total, hi_count(log_n_total), NTT_POW_LO_LOG);
+    fr_t nn = fp_zero<FrP>();
+    nn.v[log_len >> 5] = 1u << (log_len & 31);
+    const fr_t size_inv = fp_inv(fp_to_mont(nn));
+    const size_t n = (size_t)1 << log_len;
+    std::vector<uint4> scratch(2 * rows * n);
+    const uint4* d = reinterpret_cast<const uint4*>(data);
+    for (uint32_t i = 0; i < plan.npasses; i++) {
+        NttPassParams p;
+        memset(&p, 0, sizeof(p));
+        const bool first = (i == 0), last = (i + 1 == plan.npasses);
+        p.src = first ? d : scratch.data();
+        p.dst = scratch.data();
+        p.tile_tw = tile_tw.data();
+        p.pow_lo = pow_lo.data(); p.pow_hi = pow_hi.data();
+        p.size_inv = size_inv;
+        p.batch_stride = n;
+        p.log_n = log_len; p.pass = i; p.npasses = plan.npasses;
+        for (int k = 0; k < NTT_MAX_PASSES; k++) p.log_len[k] = plan.log_len[k];
+        p.log_cw = plan.log_cw[i];
+        p.scale_post = (last && direction == 1);
+        p.radix4 = 1;
+        uint32_t ntiles = 1u << (log_len - plan.log_len[i] - plan.log_cw[i]);
+        uint32_t nbatch = (uint32_t)rows;
+        if (last) {
+            p.xchg = 1; p.x_world = world; p.x_rank = rank; p.x_twiddle = twiddle ? 1 : 0; p.x_log_n = log_n_total;
+            p.x_r_total = rows; p.x_row_base = row_base;
+            p.x_pow_lo = xpow_lo.data(); p.x_pow_hi = xpow_hi.data();
+            for (uint32_t w = 0; w < world; w++) p.x_dst[w] = reinterpret_cast<uint4*>(dsts[w]);
+            ntiles = 1u << (log_len - plan.log_len[i]);
+            nbatch = (uint32_t)(rows >> plan.log_cw[i]);
+        }
+        std::vector<uint4> sm(2 * ((size_t)1 << (plan.log_len[i] + plan.log_cw[i])));
+        std::vector<uint4> smtw((size_t)1 << plan.log_len[i]);
+        for (uint32_t b = 0; b < nbatch; b++)
+            for (uint32_t tile = 0; tile < ntiles; tile++) {
+                for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_load(p, sm.data(), tile, b, tid, nthreads);
+                for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage_twiddles(p, smtw.data(), tid, nthreads);
+                const NttTwiddles twd = ntt_shared_twiddles(smtw.data(), plan.log_len[i]);
+                uint32_t s = 0;
+                for (; s + 1 < plan.log_len[i]; s += 2)
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage2(p, sm.data(), twd, s, tid, nthreads);
+                for (; s < plan.log_len[i]; s++)
+                    for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_stage(p, sm.data(), twd, s, tid, nthreads);
+                for (uint32_t tid = 0; tid < nthreads; tid++) ntt_phase_store(p, sm.data(), tile, b, tid, nthreads);
+            }
+    }
+    return 0;
+}

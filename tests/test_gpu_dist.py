@@ -124,3 +124,47 @@ def test_peer_exchange_single_rank():
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy().view(np.uint64), C.ntt(x, log_n, direction=direction, coset=coset))
     fab.close()
+
+
+@pytest.mark.parametrize("log_n,world", [(10, 2), (12, 4), (13, 2), (16, 8), (20, 4), (22, 8)])
+@pytest.mark.parametrize("direction", [0, 1])
+def test_transforms_fused_with_exchange_virtual_world(log_n, world, direction):
+    """b200_ntt_rows_exchange_device: the row transforms' last pass IS the exchange (butterflies, twiddle and the stores
+    into the destination ranks' slabs in one launch set).  `world` virtual ranks on one GPU, full four-step schedule
+    with both fused steps == the oracle's transform (and == the schedule with separate exchange kernels)."""
+    import ctypes
+    import torch
+    from snarkos_b200 import dist as D
+    n = 1 << log_n
+    n1_log = log_n // 2
+    n2_log = log_n - n1_log
+    n1, n2, per = 1 << n1_log, 1 << n2_log, n // world
+    x = H.random_fr_mont_np(np.random.default_rng(11 * log_n + direction), (n,))
+    blocks = [torch.from_numpy(x[r * per:(r + 1) * per].view(np.int64)).cuda() for r in range(world)]
+    B = [torch.zeros((per, 4), dtype=torch.int64, device="cuda") for _ in range(world)]
+    Cb = [torch.zeros((per, 4), dtype=torch.int64, device="cuda") for _ in range(world)]
+    dst_b = (ctypes.c_void_p * world)(*[t.data_ptr() for t in B])
+    dst_c = (ctypes.c_void_p * world)(*[t.data_ptr() for t in Cb])
+    rb, rc = n2 // world, n1 // world
+    for r in range(world):
+        D.exchange_transpose(blocks[r], dst_b, world, r, rc, n2, log_n, direction, False)
+    torch.cuda.synchronize()
+    keep_b = [t.clone() for t in B]
+    for r in range(world):                                  # transforms of B's rows + twiddle + exchange into every C
+        D.ntt_rows_exchange(B[r], dst_c, world, r, rb, n1_log, log_n, direction, True, r * rb)
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert torch.equal(B[r], keep_b[r])                 # the source slab is left unchanged
+    for r in range(world):                                  # transforms of C's rows + exchange into every B (natural order)
+        D.ntt_rows_exchange(Cb[r], dst_b, world, r, rc, n2_log, log_n, direction, False)
+    torch.cuda.synchronize()
+    got = torch.cat(B).cpu().numpy().view(np.uint64)
+    if log_n <= 16:
+        assert np.array_equal(got, C.ntt(x, log_n, direction=direction))
+    else:
+        import snarkos_b200 as S
+        t = torch.from_numpy(x.view(np.int64)).cuda()
+        d = S.EvaluationDomain(n)
+        want = d.ifft_in_place(t) if direction else d.fft_in_place(t)
+        torch.cuda.synchronize()
+        assert np.array_equal(got, want.cpu().numpy().view(np.uint64))

@@ -138,3 +138,41 @@ def test_shape_specialised_7_3_and_6_4_match_oracle(hostlib, log_n, lens, cws, d
     data = H.random_fr_mont_np(rng, (n,))
     got = run(hostlib, data, log_n, 1, n, direction, coset, lens, cws, nthreads=16, variant=3)
     assert np.array_equal(got, C.ntt(data, log_n, direction=direction, coset=coset))
+
+
+@pytest.mark.parametrize("log_len,rows,world,log_n_total", [(4, 8, 2, 7), (8, 16, 4, 12), (11, 32, 2, 16), (13, 16, 8, 17), (13, 48, 4, 19), (6, 5, 1, 9)])
+@pytest.mark.parametrize("direction,twiddle", [(0, 1), (1, 1), (0, 0)])
+def test_rows_transform_with_fused_exchange(hostlib, log_len, rows, world, log_n_total, direction, twiddle):
+    """b200_ntt_rows_exchange_device emulated on the host: the last pass of a batch of row transforms stores every output
+    (row, col) -- twiddled by w_N^((row_base + row) * col) -- into the transposed slab of the rank that owns the column.
+    Checked against the oracle's row transforms + big-int twiddles + an explicit transposition (single pass, two passes,
+    odd row counts that shrink the row tile, world = 1)."""
+    n = 1 << log_len
+    rank, row_base = world - 1, 3 * rows
+    rng = np.random.default_rng(9000 + log_len + rows + direction)
+    data = H.random_fr_mont_np(rng, (rows * n,))
+    c_local, R = n // world, rows * world
+    dsts = [np.zeros((c_local * R, 4), dtype=np.uint64) for _ in range(world)]
+    ptrs = (ctypes.c_void_p * world)(*[d.ctypes.data_as(ctypes.c_void_p).value for d in dsts])
+    rc = hostlib.host_ntt_rows_exchange(data.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(rows), ctypes.c_uint32(log_len),
+                                        ctypes.c_uint32(world), ctypes.c_uint32(rank), ctypes.c_uint32(log_n_total), ctypes.c_int(direction),
+                                        ctypes.c_int(twiddle), ctypes.c_uint64(row_base), ptrs, ctypes.c_uint32(24))
+    assert rc == 0
+    dom = O.EvaluationDomain(1 << log_n_total)
+    w = dom.group_gen_inv if direction else dom.group_gen
+    N = 1 << log_n_total
+    for r in range(rows):
+        out = C.ntt(data[r * n:(r + 1) * n], log_len, direction=direction)
+        vals = H.fr_from_mont_array(out)
+        if twiddle:
+            vals = [v * pow(w, ((row_base + r) * col) % N, O.R_MOD) % O.R_MOD for col, v in enumerate(vals)]
+        want = H.fr_mont_array(vals)
+        for col in range(0, n, max(1, n // 64)):            # a sample of the columns, every destination rank
+            d, cl = col // c_local, col % c_local
+            assert np.array_equal(dsts[d][cl * R + rank * rows + r], want[col]), (r, col)
+    # every slot written by this rank is its own: rows of other ranks stay zero
+    for d in range(world):
+        view = dsts[d].reshape(c_local, world, rows, 4)
+        for other in range(world):
+            if other != rank:
+                assert not view[:, other].any()
