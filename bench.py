@@ -375,8 +375,7 @@ def run_b200(args):
     if not args.no_strong:
         L26 = args.strong_log_n
         per = (1 << L26) // world
-        S.release_scratch()                                         # the 2^24 steps' cached temporaries: this call has another shape
-        torch.cuda.empty_cache()
+        torch.cuda.empty_cache()                                    # (the library's scratch cache evicts the 2^24 steps' blocks itself)
         Ks = min(K, 3)
         b26 = S.synthetic_bases(per, seed=26000 + rank)            # rank r holds points [r * per, (r + 1) * per)
         s26 = rand_limbs(per)
@@ -438,9 +437,11 @@ def run_b200(args):
                   "ntt_ms": {k_: v for k_, v in zip(keys, vals[1:])},
                   "ntt_gelem_s": (1 << L26) / (best_ntt * 1e-3) / 1e9,
                   "ntt_exchange": ("none (one GPU: the plain multi-pass transform)" if world == 1 else
-                                   "fused_*: ONE kernel per exchange storing transposed + twiddled tiles into peer HBM over "
-                                   "NVLink (CUDA IPC); nccl_*: re-tile + ncclAllToAll + re-tile; *_natural = 3 exchanges "
-                                   "(natural order out), *_slab = 2 (k1-slab out for a following pointwise stage)")}
+                                   "fused_*: the exchanges after a local transform ARE that transform's last pass (butterflies, "
+                                   "twiddle and peer stores over NVLink in one launch set, CUDA IPC); fused_separate_kernels_*: ONE "
+                                   "kernel per exchange storing transposed + twiddled tiles into peer HBM; nccl_*: re-tile + "
+                                   "ncclAllToAll + re-tile; *_natural = 3 exchanges (natural order out), *_slab = 2 (k1-slab out for "
+                                   "a following pointwise stage)")}
 
     if rank != 0:
         if world > 1:

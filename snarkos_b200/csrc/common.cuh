@@ -80,6 +80,8 @@ extern B200Counters g_counters;
 cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream);
 void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream);
 void b200_scratch_release_all();     // b200_shutdown
+void b200_scratch_register_stream(cudaStream_t s);   // a stream the library created (alive until it says otherwise)
+void b200_scratch_forget_stream(cudaStream_t s);     // ... is about to be destroyed
 
 // stream-ordered scratch buffer (freed on the same stream when it goes out of scope)
 struct DevBuf {

@@ -69,7 +69,10 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // one batch: pack into pinned staging, one H2D, one segmented MSM, one D2H
 static b200_error_t queue_run_batch(std::vector<std::shared_ptr<QueueJob>>& batch) {
     B200_TRY(b200_require_device());
-    if (!g_q.stream) CUDA_TRY(cudaStreamCreateWithFlags(&g_q.stream, cudaStreamNonBlocking));
+    if (!g_q.stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_q.stream, cudaStreamNonBlocking));
+        b200_scratch_register_stream(g_q.stream);
+    }
     const size_t nmsm = batch.size(), stride = batch[0]->stride;
     size_t npts = 0;
     for (auto& j : batch) npts += j->n;
@@ -203,7 +206,10 @@ void b200_queue_shutdown() {
     if (worker.joinable()) worker.join();
     if (g_q.h_stage) cudaFreeHost(g_q.h_stage);
     if (g_q.d_stage) cudaFree(g_q.d_stage);
-    if (g_q.stream) cudaStreamDestroy(g_q.stream);
+    if (g_q.stream) {
+        b200_scratch_forget_stream(g_q.stream);             // its cached scratch goes back while the stream still exists
+        cudaStreamDestroy(g_q.stream);
+    }
     g_q.h_stage = g_q.d_stage = nullptr;
     g_q.h_cap = g_q.d_cap = 0;
     g_q.stream = nullptr;
