@@ -718,7 +718,11 @@ static b200_error_t ntt_run_device_x(void* d_inout, uint32_t log_n, size_t batch
             // one tile = one sub-problem of 2^cw adjacent rows; generic kernels (run-time flags), 8 elements per thread
             grid = dim3(1u << (log_n - plan.log_len[i]), (unsigned)(batch >> plan.log_cw[i]));
             const size_t xsmem = (size_t)tile_elems * 32 + ((size_t)1 << plan.log_len[i]) * 16;
-            if (tile_elems == 1024) ntt_pass_kernel_128<<<grid, 128, xsmem, stream>>>(p);
+            const bool xshaped = b200_config().ntt_variant == 0 && b200_config().ntt_radix4;
+            if (xshaped && plan.log_len[i] == 6 && plan.log_cw[i] == 4) ntt_launch_shaped<6, 4>(0, grid, xsmem, stream, p);
+            else if (xshaped && plan.log_len[i] == 7 && plan.log_cw[i] == 3) ntt_launch_shaped<7, 3>(0, grid, xsmem, stream, p);
+            else if (xshaped && plan.log_len[i] == 8 && plan.log_cw[i] == 2) ntt_launch_shaped<8, 2>(0, grid, xsmem, stream, p);
+            else if (tile_elems == 1024) ntt_pass_kernel_128<<<grid, 128, xsmem, stream>>>(p);
             else ntt_pass_kernel<<<grid, threads, xsmem, stream>>>(p);
             KERNEL_CHECK();
             continue;
