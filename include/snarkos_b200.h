@@ -61,7 +61,7 @@ enum { B200_NTT_FORWARD = 0, B200_NTT_INVERSE = 1 };
  * tables.  Idempotent.  b200_shutdown releases every cached table and registered base set. */
 b200_error_t b200_init(int device);
 void b200_shutdown(void);
-/* Hands every cached scratch block (per-stream caches of the calls' temporaries, up to 40 GiB in total) back to the
+/* Hands every cached scratch block (per-stream caches of the calls' temporaries, up to half the device memory in total) back to the
  * driver's stream-ordered memory pool of the device: for a long-running node between proving bursts, or before calls of
  * a very different shape.  The pool keeps the memory mapped (cudaMemPoolTrimTo on the device's default pool returns it
  * to the OS; the next large call then pays for mapping it again).  Blocks cached on the library's own streams go back in

@@ -114,7 +114,12 @@ B200Counters g_counters;
 // size classes: powers of two up to 64 MiB, eighths of an octave above (<= 12.5 % over-allocation on the GB-sized lists
 // of a large MSM); one budget for everything the caches of all threads hold
 #define SCRATCH_POW2_LIMIT ((size_t)64 << 20)
-#define SCRATCH_GLOBAL_BUDGET ((size_t)40 << 30)
+// Budget: half of the device's memory, fixed at b200_init (a B200: 89 GiB).  One 2^24-point MSM works in ~25 GB of scratch
+// on the stream it runs on, and a process that calls through the device API on its own stream, through the host API
+// (two library streams) and against resident sets keeps three such working sets alive: with 40 GiB every call of that
+// mix went back to the driver's allocator (+12 ms per 2^24 call).  An allocation failure still empties every cache.
+static std::atomic<size_t> g_scratch_budget{(size_t)40 << 30};
+#define SCRATCH_GLOBAL_BUDGET (g_scratch_budget.load(std::memory_order_relaxed))
 static std::atomic<size_t> g_scratch_cached{0};
 // One cache per STREAM (not per thread): a caller thread that exits hands its stream to the next thread, and the
 // scratch cached on that stream goes with it -- a new thread's first call finds the blocks of the same shape already
@@ -125,7 +130,6 @@ struct ScratchCache {
     cudaStream_t stream = nullptr;
     struct Block { void* p; uint64_t tick; };
     std::map<size_t, std::vector<Block>> free_blocks;       // rounded size -> blocks
-    uint64_t tick = 0;                                      // last-use order, for eviction
 };
 struct ScratchRegistry {
     std::mutex mu;                                          // the map itself; never held together with a cache mutex except by try_lock
@@ -173,19 +177,61 @@ static size_t scratch_round(size_t bytes) {
     const size_t step = top >> 3;
     return (bytes + step - 1) / step * step;
 }
-// least recently used block of one cache back to the driver; false when the cache is empty (cache mutex held)
-static bool scratch_evict_one_locked(ScratchCache& c) {
-    std::map<size_t, std::vector<ScratchCache::Block>>::iterator oldest = c.free_blocks.end();
+// least recently used block of one cache (cache mutex held); nullptr-like end() when the cache is empty
+static bool scratch_oldest_locked(ScratchCache& c, std::map<size_t, std::vector<ScratchCache::Block>>::iterator* which, size_t* index) {
+    auto oldest = c.free_blocks.end();
     size_t oldest_i = 0;
     for (auto it = c.free_blocks.begin(); it != c.free_blocks.end(); ++it)
         for (size_t i = 0; i < it->second.size(); i++)
             if (oldest == c.free_blocks.end() || it->second[i].tick < oldest->second[oldest_i].tick) { oldest = it; oldest_i = i; }
     if (oldest == c.free_blocks.end()) return false;
-    cudaFreeAsync(oldest->second[oldest_i].p, c.stream);
-    g_scratch_cached.fetch_sub(oldest->first);
-    oldest->second.erase(oldest->second.begin() + oldest_i);
-    if (oldest->second.empty()) c.free_blocks.erase(oldest);
+    *which = oldest;
+    *index = oldest_i;
     return true;
+}
+static void scratch_evict_locked(ScratchCache& c, std::map<size_t, std::vector<ScratchCache::Block>>::iterator which, size_t index) {
+    cudaFreeAsync(which->second[index].p, c.stream);
+    g_scratch_cached.fetch_sub(which->first);
+    which->second.erase(which->second.begin() + index);
+    if (which->second.empty()) c.free_blocks.erase(which);
+}
+// least recently used block of one cache back to the driver; false when the cache is empty (cache mutex held)
+static bool scratch_evict_one_locked(ScratchCache& c) {
+    std::map<size_t, std::vector<ScratchCache::Block>>::iterator which;
+    size_t index;
+    if (!scratch_oldest_locked(c, &which, &index)) return false;
+    scratch_evict_locked(c, which, index);
+    return true;
+}
+// Over budget: the least recently used blocks of ALL caches that may be touched from here go first -- the calling
+// stream's own and those of the library's live streams (a stream-ordered free is ordered behind the last use of a cached
+// block by construction).  A call that works on two streams (the streamed MSM) would otherwise evict its own working
+// set from the stream it frees on while the other stream's cache keeps blocks of shapes long gone (measured: every call
+// back at the driver's allocator, 100 .. 2900 ms instead of 90).  Ticks are global for that.  No cache mutex is held on
+// entry; registry mutex first, cache mutexes by try_lock (same order as b200_scratch_release_all).
+static std::atomic<uint64_t> g_scratch_tick{0};
+static void scratch_evict_global(cudaStream_t own) {
+    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    while (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET) {
+        ScratchCache* best = nullptr;
+        uint64_t best_tick = 0;
+        for (auto& kv : g_scratch.caches) {
+            if (kv.first != own && !g_scratch.lib_streams.count(kv.first)) continue;
+            ScratchCache* c = kv.second;
+            if (!c->mu.try_lock()) continue;
+            std::map<size_t, std::vector<ScratchCache::Block>>::iterator which;
+            size_t index;
+            if (scratch_oldest_locked(*c, &which, &index) && (!best || which->second[index].tick < best_tick)) {
+                best = c;
+                best_tick = which->second[index].tick;
+            }
+            c->mu.unlock();
+        }
+        if (!best || !best->mu.try_lock()) return;
+        const bool done = !scratch_evict_one_locked(*best);
+        best->mu.unlock();
+        if (done) return;
+    }
 }
 cudaError_t b200_scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
     const size_t rounded = scratch_round(bytes);
@@ -217,16 +263,10 @@ void b200_scratch_free(void* p, size_t bytes, cudaStream_t stream) {
     ScratchCache* c = scratch_cache_of(stream);
     {
         std::lock_guard<std::mutex> lock(c->mu);
-        c->free_blocks[rounded].push_back(ScratchCache::Block{p, ++c->tick});
+        c->free_blocks[rounded].push_back(ScratchCache::Block{p, ++g_scratch_tick});
         g_scratch_cached.fetch_add(rounded);
-        // over budget: this stream's least recently used blocks go first (a call of another shape left them behind)
-        while (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET && c->free_blocks.size() > 1)
-            if (!scratch_evict_one_locked(*c)) break;
-        // still over budget (other streams' caches hold the rest): this block is not cached either.  Other streams are
-        // never touched from here -- their owners may have destroyed them, and a stream-ordered free on a destroyed
-        // stream crashes inside the driver; b200_release_scratch / an allocation failure empty every cache safely.
-        if (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET) scratch_evict_one_locked(*c);
     }
+    if (g_scratch_cached.load() > SCRATCH_GLOBAL_BUDGET) scratch_evict_global(stream);
 }
 // streams of the library's own (per-thread streams, the queue's dispatcher stream) are known to be alive until the library
 // destroys them: their caches can be emptied in their own stream order, which keeps the driver pool's reuse cheap
@@ -289,6 +329,8 @@ static void config_from_env(B200Config& c) {
     c.msm_chunk = env_int("B200_MSM_CHUNK", 0);
     c.msm_host_pipeline = !getenv("B200_MSM_NO_HOST_PIPELINE");
     c.msm_host_first_log = env_int("B200_MSM_HOST_FIRST_LOG", 20);
+    c.msm_host_chunk_log = env_int("B200_MSM_HOST_CHUNK_LOG", 23);
+    c.msm_stream_two = !getenv("B200_MSM_NO_STREAM_TWO");
     c.msm_auto_table = !getenv("B200_MSM_NO_AUTO_TABLE");
     c.msm_queue_threshold = env_int("B200_MSM_QUEUE_THRESHOLD", 0);
     if (const char* e = getenv("B200_NTT_PLAN")) { strncpy(c.ntt_plan, e, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
@@ -319,6 +361,8 @@ extern "C" b200_error_t b200_set_option(const char* key, const char* value) {
     else if (k == "msm_chunk") c.msm_chunk = v;
     else if (k == "msm_host_pipeline") c.msm_host_pipeline = v != 0;
     else if (k == "msm_host_first_log") c.msm_host_first_log = v;
+    else if (k == "msm_host_chunk_log") c.msm_host_chunk_log = v;
+    else if (k == "msm_stream_two") c.msm_stream_two = v != 0;
     else if (k == "msm_auto_table") c.msm_auto_table = v != 0;
     else if (k == "msm_list_budget_bytes") c.msm_list_budget = strtoull(value, nullptr, 0);
     else if (k == "msm_queue_threshold") c.msm_queue_threshold = v;
@@ -398,6 +442,11 @@ extern "C" b200_error_t b200_init(int device) {
         uint64_t threshold = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) g_scratch_budget.store(total_b / 2);
+        else (void)cudaGetLastError();
+    }
     const B200Config& cfg = b200_config();
     if (cfg.l2_fetch_granularity) {
         size_t before = 0, after = 0;
@@ -458,36 +507,36 @@ NvtxRange::~NvtxRange() { nvtxRangePop(); }
 struct StageRec { const char* name; cudaEvent_t start; cudaEvent_t stop; };
 static thread_local bool t_prof_on = false;
 static thread_local std::vector<StageRec> t_prof;
-static thread_local bool t_prof_open = false;
+// the open stage of every stream a call works on (a call may fork onto the thread's helper stream: stages are per stream)
+static thread_local std::map<cudaStream_t, size_t> t_prof_open;
 
 bool& StageTimer::enabled() { return t_prof_on; }
-void StageTimer::mark(const char* name, cudaStream_t stream) {
+static cudaEvent_t stage_event(cudaStream_t stream) {
     cudaEvent_t e = nullptr;
     if (cudaEventCreate(&e) != cudaSuccess || cudaEventRecord(e, stream) != cudaSuccess) {
         (void)cudaGetLastError();                  // profiling is best effort: a stage without events reports 0 ms
         if (e) cudaEventDestroy(e);
         e = nullptr;
     }
-    if (t_prof_open) t_prof.back().stop = e;
-    cudaEvent_t e2 = e;
-    t_prof.push_back(StageRec{name, e2, nullptr});
-    t_prof_open = true;
+    return e;
+}
+void StageTimer::mark(const char* name, cudaStream_t stream) {
+    cudaEvent_t e = stage_event(stream);
+    auto it = t_prof_open.find(stream);
+    if (it != t_prof_open.end()) t_prof[it->second].stop = e;
+    t_prof.push_back(StageRec{name, e, nullptr});
+    t_prof_open[stream] = t_prof.size() - 1;
 }
 void StageTimer::finish(cudaStream_t stream) {
-    if (!t_prof_open) return;
-    cudaEvent_t e = nullptr;
-    if (cudaEventCreate(&e) != cudaSuccess || cudaEventRecord(e, stream) != cudaSuccess) {
-        (void)cudaGetLastError();
-        if (e) cudaEventDestroy(e);
-        e = nullptr;
-    }
-    t_prof.back().stop = e;
-    t_prof_open = false;
+    auto it = t_prof_open.find(stream);
+    if (it == t_prof_open.end()) return;
+    t_prof[it->second].stop = stage_event(stream);
+    t_prof_open.erase(it);
 }
 
 extern "C" void b200_profile_begin(void) {
     t_prof.clear();
-    t_prof_open = false;
+    t_prof_open.clear();
     t_prof_on = true;
 }
 // Writes "name=ms;name=ms;..." (one entry per recorded stage, in order) and stops profiling.
@@ -536,7 +585,9 @@ cudaStream_t b200_thread_copy_stream() { return thread_stream_get(t_copy_stream,
 static thread_local ThreadStream t_copy_stream2;
 cudaStream_t b200_thread_copy_stream2() { return thread_stream_get(t_copy_stream2, false); }
 
-#define MSM_HOST_CHUNK_LOG 23
+#define MSM_HOST_STAGING_BUFFERS 3
+#define MSM_HOST_CHUNK_LOG_MIN 10
+#define MSM_HOST_CHUNK_LOG_MAX 26
 
 extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, size_t n, const void* scalars,
                                               size_t stride) {
@@ -551,7 +602,10 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     }
     cudaStream_t s = b200_thread_stream();
     if (!s) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
-    const size_t chunk = (size_t)1 << MSM_HOST_CHUNK_LOG;
+    uint32_t chunk_log = (uint32_t)b200_config().msm_host_chunk_log;
+    if (chunk_log < MSM_HOST_CHUNK_LOG_MIN) chunk_log = MSM_HOST_CHUNK_LOG_MIN;
+    if (chunk_log > MSM_HOST_CHUNK_LOG_MAX) chunk_log = MSM_HOST_CHUNK_LOG_MAX;
+    const size_t chunk = (size_t)1 << chunk_log;
     if (n < chunk || !b200_config().msm_host_pipeline) {
         DevBuf d_pts, d_sc, d_out;
         CUDA_TRY(d_pts.alloc(n * stride, s));
@@ -567,14 +621,17 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         return b200_ok();
     }
     // Large call: the MSM is a sum over point ranges, so the ranges are streamed -- range i+1 crosses PCIe while the
-    // buckets of range i are being accumulated (double-buffered staging); all ranges add into ONE bucket array, which
-    // is reduced and folded once at the end.
+    // buckets of range i are being accumulated; the ranges are independent until the finish (msm.cu:
+    // msm_stream_*), so they alternate between the thread's two compute streams: the latency-bound inversion chains of
+    // one range run under the multiplier-bound additions of the other.
     cudaStream_t cs = b200_thread_copy_stream();
     if (!cs) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
+    cudaStream_t s2 = b200_config().msm_stream_two ? b200_thread_aux_stream() : s;
+    if (!s2) return b200_err(B200_ERR_NO_DEVICE, "could not create a CUDA stream");
     std::vector<size_t> range_off, range_cnt;
     uint32_t first_log = (uint32_t)b200_config().msm_host_first_log;
-    if (first_log < 16) first_log = 16;
-    if (first_log > MSM_HOST_CHUNK_LOG) first_log = MSM_HOST_CHUNK_LOG;
+    if (first_log < 16 && first_log < chunk_log) first_log = chunk_log < 16 ? chunk_log : 16;
+    if (first_log > chunk_log) first_log = chunk_log;
     for (size_t done = 0, cur = (size_t)1 << first_log; done < n;) {
         const size_t cnt = n - done < cur ? n - done : cur;
         range_off.push_back(done);
@@ -583,8 +640,13 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         if (range_off.size() > 1 && cur < chunk) cur <<= 1;
     }
     const size_t nchunks = range_off.size();
-    DevBuf d_pts[2], d_sc[2], d_out;
-    for (int b = 0; b < 2; b++) {
+    // THREE staging buffers: with two, the copy of range i + 1 can only start when range i - 1 is done, i.e. together with
+    // the work on range i -- and a range twice as long takes longer to cross PCIe (2.7 ms per 2^20 points) than its
+    // predecessor takes to compute (4.9 ms per 2^20): the GPU waited ~10 % of the growth phase.  With three the copies
+    // run back to back from the start of the call.
+    const int NBUF = MSM_HOST_STAGING_BUFFERS;
+    DevBuf d_pts[MSM_HOST_STAGING_BUFFERS], d_sc[MSM_HOST_STAGING_BUFFERS], d_out;
+    for (int b = 0; b < NBUF; b++) {
         CUDA_TRY(d_pts[b].alloc(chunk * stride, s));
         CUDA_TRY(d_sc[b].alloc(chunk * 32, s));
     }
@@ -605,26 +667,33 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
     if (rc.code == 0) {
         cudaError_t e = cudaEventRecord(ready, s);                 // staging buffers exist from here on in stream order
         if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ready, 0);
+        if (e == cudaSuccess && s2 != s) e = cudaStreamWaitEvent(s2, ready, 0);
         if (e != cudaSuccess) rc = b200_cuda_err(e);
     }
     for (size_t i = 0; i < nchunks && rc.code == 0; i++) {
-        const int b = (int)(i & 1);
+        const int b = (int)(i % NBUF);
         const size_t off = range_off[i], cnt = range_cnt[i];
         cudaError_t e = cudaSuccess;
-        if (i >= 2) e = cudaStreamWaitEvent(cs, computed[i - 2], 0);        // staging buffer b is free again
+        if (i >= (size_t)NBUF) e = cudaStreamWaitEvent(cs, computed[i - NBUF], 0);        // staging buffer b is free again
         if (e == cudaSuccess) {
             rc = b200_h2d(d_pts[b].p, (const uint8_t*)points + off * stride, cnt * stride, cs);
             if (rc.code == 0) rc = b200_h2d(d_sc[b].p, (const uint8_t*)scalars + off * 32, cnt * 32, cs);
             if (rc.code != 0) break;
         }
+        cudaStream_t si = (i & 1) ? s2 : s;
         if (e == cudaSuccess) e = cudaEventRecord(copied[i], cs);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, copied[i], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(si, copied[i], 0);
         if (e != cudaSuccess) { rc = b200_cuda_err(e); break; }
-        rc = msm_stream_add(session, d_pts[b].p, cnt, d_sc[b].p, stride, s);
+        rc = msm_stream_add(session, d_pts[b].p, cnt, d_sc[b].p, stride, si);
         if (rc.code == 0) {
-            e = cudaEventRecord(computed[i], s);
+            e = cudaEventRecord(computed[i], si);
             if (e != cudaSuccess) rc = b200_cuda_err(e);
         }
+    }
+    if (rc.code == 0 && s2 != s && nchunks >= 2) {                  // the finish reads what the last range on s2 left
+        const size_t last2 = (nchunks - 1) & 1 ? nchunks - 1 : nchunks - 2;
+        cudaError_t e = cudaStreamWaitEvent(s, computed[last2], 0);
+        if (e != cudaSuccess) rc = b200_cuda_err(e);
     }
     if (rc.code == 0) rc = msm_stream_finish(session, d_out.p, s);
     else msm_stream_abort(session);
@@ -633,6 +702,7 @@ extern "C" b200_error_t b200_msm_g1_bls12_377(void* out, const void* points, siz
         if (e != cudaSuccess) rc = b200_cuda_err(e);
     }
     cudaStreamSynchronize(cs);
+    if (s2 != s) cudaStreamSynchronize(s2);
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (rc.code == 0 && e2 != cudaSuccess) rc = b200_cuda_err(e2);
     if (ready) cudaEventDestroy(ready);

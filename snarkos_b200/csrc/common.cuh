@@ -44,6 +44,9 @@ struct B200Config {
     int msm_chunk = 0;               // msm_chunk                B200_MSM_CHUNK         0 = automatic
     bool msm_host_pipeline = true;   // msm_host_pipeline        B200_MSM_NO_HOST_PIPELINE
     int msm_host_first_log = 20;     // msm_host_first_log       B200_MSM_HOST_FIRST_LOG
+    int msm_host_chunk_log = 23;     // msm_host_chunk_log       B200_MSM_HOST_CHUNK_LOG  host calls of >= 2^this points are streamed
+                                     //                          in ranges of at most 2^this points (tests lower it)
+    bool msm_stream_two = true;      // msm_stream_two           B200_MSM_NO_STREAM_TWO    streamed ranges alternate between two compute streams
     bool msm_auto_table = true;      // msm_auto_table           B200_MSM_NO_AUTO_TABLE
     unsigned long long msm_list_budget = 0;   // msm_list_budget_bytes: cap on the pair-round scratch of ONE call
                                      //                          (0 = whatever cudaMallocAsync grants); above it the call
@@ -70,7 +73,7 @@ struct B200Counters {
 extern B200Counters g_counters;
 
 // Stream-ordered scratch (api.cu): blocks are recycled through a per-thread, per-stream cache -- size classes are powers
-// of two up to 64 MiB and eighths of an octave above, one 40 GiB budget for all caches together, everything handed back
+// of two up to 64 MiB and eighths of an octave above, one budget (half the device memory) for all caches together, everything handed back
 // to the driver when an allocation fails -- so a call in steady state makes no allocator call at all.  Reuse on the
 // SAME stream needs no synchronisation, and -- unlike the driver's pool -- a block freed by one caller thread is never
 // handed to another stream: with hundreds of caller threads the driver pool's cross-stream reuse put milliseconds of

@@ -11,7 +11,9 @@
 //   fold      : Horner over the windows with c doublings each -> Jacobian result
 // HBM layout: packed bases n * 128 B | entries n * nwin * 4 B | offsets (nwin * 2^(c-1) + 1) * 4 B |
 //             buckets nwin * 2^(c-1) * 192 B (XYZZ) | segment sums | window sums.
+#include <algorithm>
 #include <cstdlib>
+#include <memory>
 
 #include "common.cuh"
 #include "msm_core.cuh"
@@ -813,7 +815,7 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
                               const unsigned long long* d_seg_off, cudaStream_t stream) {
     const MsmShape& sh = pl.sh;
     const size_t K = pl.K;
-    DevBuf packed, halves, counts, offsets, cursor, entries, heads, tails, head_bucket, tail_bucket, max_heads;
+    DevBuf packed, halves;
     const uint4* pts = reinterpret_cast<const uint4*>(d_packed);
     const uint32_t glv = pl.glv ? 1u : 0u;
     if (glv) {
@@ -834,6 +836,7 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
         B200_TRY(msm_pack_bases_device(packed.p, d_points, n, stride, stream));
         pts = packed.as<uint4>();
     }
+    DevBuf counts, offsets, cursor, entries, heads, tails, head_bucket, tail_bucket, max_heads;
     CUDA_TRY(counts.alloc((K + 1) * 4, stream));
     CUDA_TRY(offsets.alloc((K + 1) * 4, stream));
     CUDA_TRY(cursor.alloc((K + 1) * 4, stream));
@@ -1070,61 +1073,83 @@ b200_error_t msm_run_batch_device(void* d_out, const void* d_points, size_t n, c
     return msm_back(pl, d_out, buckets.as<g1_xyzz_mem_t>(), stream);
 }
 
-// Streaming form for the host-buffer path: a session fixes the window width for n_total points; every range adds
-// its buckets into the session's bucket array; finish reduces once.
+// Streaming form for the host-buffer path: a session fixes the window width for n_total points; every range is
+// accumulated into a bucket array of its own, on whatever stream the caller gives it, and added to THAT stream's running
+// total (streams are independent until the finish: the caller alternates two, so that the latency-bound chains of one
+// range run under the multiplier-bound additions of the other); finish adds the totals up and reduces once.
+// (Tried and dropped: keeping every range's half-reduced point lists, concatenating them bucket by bucket at the finish
+// and running the last pair rounds + the XYZZ walk once -- 3.0 instead of 9.8 ms of XYZZ walks and no merges, but the
+// serial tail of concatenation + rounds and the extra inversion chains cost as much: 93.3 against 90.3 ms at 2^24.)
 struct MsmStream {
     MsmPlan plan;
-    DevBuf total, part;
-    bool first = true;
+    cudaStream_t main = nullptr;
+    std::vector<cudaStream_t> others;                          // streams other than `main` that ranges ran on
+    std::vector<std::pair<cudaStream_t, std::unique_ptr<DevBuf>>> totals;      // per stream: the sum of its ranges' bucket arrays
+    ~MsmStream() {
+        // blocks allocated on another stream go back to THAT stream's cache: its later work must not reuse them before
+        // the finish (enqueued on `main`) has read them
+        if (!main || others.empty()) return;
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaStreamSynchronize(main); return; }
+        cudaEventRecord(ev, main);
+        for (cudaStream_t o : others) cudaStreamWaitEvent(o, ev, 0);
+        cudaEventDestroy(ev);
+    }
 };
 
 b200_error_t msm_stream_begin(void** session, size_t n_total, cudaStream_t stream) {
     MsmStream* st = new MsmStream();
+    st->main = stream;
     // one window narrower than the single-shot choice: every range pays one group addition per touched bucket when it
     // is merged, so fewer, fuller buckets win (2^24 in 2^22 ranges: c = 19)
     const bool glv = msm_use_glv(nullptr, 0);
     uint32_t c = glv ? msm_glv_window_bits(2 * n_total) : b200_msm_window_bits(n_total);
     if (!glv && !(b200_config().msm_c >= 2 && b200_config().msm_c <= 22) && c > 6) c -= 1;
     b200_error_t r = msm_make_plan(&st->plan, n_total, 1, 0, c, glv);
-    if (r.code == 0) {
-        cudaError_t e = st->total.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);
-        if (e == cudaSuccess) e = st->part.alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream);
-        if (e != cudaSuccess) r = b200_cuda_err(e);
-    }
     if (r.code != 0) { delete st; return r; }
     *session = st;
     return b200_ok();
 }
 
-b200_error_t msm_stream_add(void* session, const void* d_points, size_t n, const void* d_scalars, size_t stride,
-                            cudaStream_t stream) {
-    MsmStream* st = reinterpret_cast<MsmStream*>(session);
-    if (n == 0) return b200_ok();
-    if (st->first) {
-        B200_TRY(msm_front(st->plan, st->total.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
-        st->first = false;
-        return b200_ok();
-    }
-    B200_TRY(msm_front(st->plan, st->part.as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
+static b200_error_t msm_stream_merge(const MsmPlan& pl, g1_xyzz_mem_t* total, const g1_xyzz_mem_t* part, cudaStream_t stream) {
     STAGE("msm_merge", stream);
-    const uint32_t K = (uint32_t)st->plan.K;
-    msm_merge_buckets_kernel<<<(K + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS, MSM_ACC_THREADS, 0, stream>>>(
-        st->total.as<g1_xyzz_mem_t>(), st->part.as<g1_xyzz_mem_t>(), K);
+    const uint32_t K = (uint32_t)pl.K;
+    msm_merge_buckets_kernel<<<(K + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS, MSM_ACC_THREADS, 0, stream>>>(total, part, K);
     KERNEL_CHECK();
     return b200_ok();
 }
 
-b200_error_t msm_stream_finish(void* session, void* d_out, cudaStream_t stream) {
+// `stream` may differ from range to range; the caller orders msm_stream_finish behind all of them
+b200_error_t msm_stream_add(void* session, const void* d_points, size_t n, const void* d_scalars, size_t stride,
+                            cudaStream_t stream) {
     MsmStream* st = reinterpret_cast<MsmStream*>(session);
-    b200_error_t r = b200_ok();
-    if (st->first) {
+    if (n == 0) return b200_ok();
+    if (stream != st->main && std::find(st->others.begin(), st->others.end(), stream) == st->others.end()) st->others.push_back(stream);
+    std::unique_ptr<DevBuf> buckets(new DevBuf());
+    CUDA_TRY(buckets->alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream));
+    B200_TRY(msm_front(st->plan, buckets->as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
+    for (auto& t : st->totals)
+        if (t.first == stream) {                              // this stream's running total: no cross-stream dependency
+            B200_TRY(msm_stream_merge(st->plan, t.second->as<g1_xyzz_mem_t>(), buckets->as<g1_xyzz_mem_t>(), stream));
+            STAGE_END(stream);                                // stages are per stream: the next one here may be a range away
+            return b200_ok();
+        }
+    STAGE_END(stream);
+    st->totals.emplace_back(stream, std::move(buckets));
+    return b200_ok();
+}
+
+b200_error_t msm_stream_finish(void* session, void* d_out, cudaStream_t stream) {
+    std::unique_ptr<MsmStream> st(reinterpret_cast<MsmStream*>(session));      // stream-ordered frees on every path
+    if (st->totals.empty()) {
         msm_write_infinity_kernel<<<1, 64, 0, stream>>>(reinterpret_cast<uint4*>(d_out), 1);
-        B200_LAUNCH_COUNT();
-    } else {
-        r = msm_back(st->plan, d_out, st->total.as<g1_xyzz_mem_t>(), stream);
+        KERNEL_CHECK();
+        return b200_ok();
     }
-    delete st;          // stream-ordered frees
-    return r;
+    g1_xyzz_mem_t* total = st->totals[0].second->as<g1_xyzz_mem_t>();
+    for (size_t i = 1; i < st->totals.size(); i++)
+        B200_TRY(msm_stream_merge(st->plan, total, st->totals[i].second->as<g1_xyzz_mem_t>(), stream));
+    return msm_back(st->plan, d_out, total, stream);
 }
 
 

@@ -275,6 +275,46 @@ def test_host_buffer_streaming_path():
     assert H.jac_bytes_to_affine(got) == O.g1_mul(O.G1_GEN, H.dot_mod_r(sc, k))
 
 
+@pytest.mark.parametrize("two,rounds", [(1, -1), (1, 3), (0, -1)])
+@pytest.mark.parametrize("n,c,first_log,chunk_log", [(5000, 6, 10, 11), (3000, 4, 10, 10), (70000, 9, 12, 14)])
+def test_streamed_ranges_small(b200_opt, two, rounds, n, c, first_log, chunk_log):
+    """the streamed host path at sizes the oracle finishes: ranges 2^first, 2^first, ... <= 2^chunk through three staging
+    buffers, alternating between the thread's two compute streams (two = 1), one bucket array per range, added up at
+    the finish"""
+    b200_opt("msm_host_chunk_log", chunk_log)
+    b200_opt("msm_host_first_log", first_log)
+    b200_opt("msm_window_bits", c)
+    b200_opt("msm_stream_two", two)
+    b200_opt("msm_affine_rounds", rounds)
+    rng = O.SplitMix64(7700 + n + c)
+    pts = O.random_points(rng, 48)
+    pts[5] = None
+    pts = [pts[(i * 7) % len(pts)] for i in range(n)]           # repeated points: doublings inside and across ranges
+    sc = O.random_fr(rng, n)
+    sc[0], sc[1], sc[2] = 0, O.R_MOD - 1, 1
+    sc[100:140] = [sc[99]] * 40                                   # a run of equal scalars across pair boundaries
+    bases, scal = H.bases_array(pts), H.scalars_array(sc)
+    assert gpu_msm(bases, scal) == oracle_msm(bases, scal)
+
+
+def test_streamed_ranges_degenerate(b200_opt):
+    """all scalars equal: ONE bucket per window holds every point of every range; all points equal: every pair is a
+    doubling"""
+    b200_opt("msm_host_chunk_log", 11)
+    b200_opt("msm_host_first_log", 10)
+    b200_opt("msm_window_bits", 5)
+    rng = O.SplitMix64(99)
+    n = 6000
+    pts = O.random_points(rng, 32)
+    pts = [pts[i % 32] for i in range(n)]
+    s0 = O.random_fr(rng, 1)[0]
+    bases = H.bases_array(pts)
+    assert gpu_msm(bases, H.scalars_array([s0] * n)) == oracle_msm(bases, H.scalars_array([s0] * n))
+    sc = O.random_fr(rng, n)
+    assert gpu_msm(H.bases_array([pts[0]] * n), H.scalars_array(sc)) == O.g1_mul(pts[0], sum(sc) % O.R_MOD)
+    assert gpu_msm(bases, H.scalars_array([0] * n)) is None
+
+
 # ---------------------------------------------------------------------------------------------
 # batched-affine pair rounds (msm_affine.cuh), forced on at small sizes through the msm_affine_rounds option
 # ---------------------------------------------------------------------------------------------
