@@ -333,6 +333,7 @@ static void config_from_env(B200Config& c) {
     c.msm_stream_two = !getenv("B200_MSM_NO_STREAM_TWO");
     c.msm_auto_table = !getenv("B200_MSM_NO_AUTO_TABLE");
     c.msm_queue_threshold = env_int("B200_MSM_QUEUE_THRESHOLD", 0);
+    c.msm_queue_linger_us = env_int("B200_MSM_QUEUE_LINGER_US", 100);
     if (const char* e = getenv("B200_NTT_PLAN")) { strncpy(c.ntt_plan, e, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
     c.ntt_tile_log = env_int("B200_NTT_TILE_LOG", 0);
     c.ntt_radix4 = !getenv("B200_NTT_RADIX2");
@@ -366,6 +367,7 @@ extern "C" b200_error_t b200_set_option(const char* key, const char* value) {
     else if (k == "msm_auto_table") c.msm_auto_table = v != 0;
     else if (k == "msm_list_budget_bytes") c.msm_list_budget = strtoull(value, nullptr, 0);
     else if (k == "msm_queue_threshold") c.msm_queue_threshold = v;
+    else if (k == "msm_queue_linger_us") c.msm_queue_linger_us = v;
     else if (k == "ntt_plan") { strncpy(c.ntt_plan, value, sizeof(c.ntt_plan) - 1); c.ntt_plan[sizeof(c.ntt_plan) - 1] = 0; }
     else if (k == "ntt_tile_log") c.ntt_tile_log = v;
     else if (k == "ntt_radix4") c.ntt_radix4 = v != 0;

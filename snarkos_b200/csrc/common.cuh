@@ -53,6 +53,8 @@ struct B200Config {
                                      //                          runs the XYZZ-only path, exactly as on an allocation failure
     int msm_queue_threshold = 0;     // msm_queue_threshold      B200_MSM_QUEUE_THRESHOLD  host MSMs of <= this many points go
                                      //                          through the coalescing queue (queue.cu); 0 = off
+    int msm_queue_linger_us = 100;   // msm_queue_linger_us      B200_MSM_QUEUE_LINGER_US  the dispatcher waits this long for further submissions
+                                     //                          before it launches a batch (at most 4 x; 0 = launch at once)
     char ntt_plan[32] = {0};         // ntt_plan "a,b,c"         B200_NTT_PLAN
     int ntt_tile_log = 0;            // ntt_tile_log             B200_NTT_TILE_LOG
     bool ntt_radix4 = true;          // ntt_radix4               B200_NTT_RADIX2

@@ -14,6 +14,7 @@
 //
 // The Rust call sites stay unchanged: with option `msm_queue_threshold` = T (B200_MSM_QUEUE_THRESHOLD), every
 // b200_msm_g1_bls12_377 call of <= T points goes through submit + wait internally.
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -122,6 +123,19 @@ static void queue_worker() {
             if (g_q.pending.empty()) {
                 if (g_q.stop) return;
                 continue;
+            }
+            // Linger: a launch set costs ~2 ms however few MSMs it carries, and the callers of a burst (the transactions
+            // of one block) arrive within a fraction of that -- so wait while submissions keep coming (no arrival for
+            // `linger` microseconds ends it, four times that is the cap).  A lone caller pays `linger` once.
+            const int linger = b200_config().msm_queue_linger_us;
+            if (linger > 0 && !g_q.stop) {
+                const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(4 * linger);
+                for (;;) {
+                    const size_t seen = g_q.pending.size();
+                    if (seen >= QUEUE_MAX_MSMS_PER_BATCH) break;
+                    g_q.cv.wait_for(lock, std::chrono::microseconds(linger), [&] { return g_q.stop || g_q.pending.size() != seen; });
+                    if (g_q.stop || g_q.pending.size() == seen || std::chrono::steady_clock::now() >= t_end) break;
+                }
             }
             // everything pending with the stride of the first job, up to the batch limits
             const size_t stride = g_q.pending.front()->stride;
