@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <memory>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "msm_core.cuh"
 #include "msm_affine.cuh"
@@ -348,14 +350,10 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
 }
 
 // one pairwise round over the heads of every spanning bucket: heads[j] += heads[j + stride], j = 0 mod 2*stride
-__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_heads_kernel(g1_xyzz_mem_t* __restrict__ heads,
-                                                                           const uint32_t* __restrict__ head_bucket,
-                                                                           const uint32_t* __restrict__ offsets,
-                                                                           const uint32_t* __restrict__ max_heads,
-                                                                           uint32_t nthreads_total, uint32_t chunk,
-                                                                           uint32_t stride) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads_total || stride >= *max_heads) return;          // no bucket has that many heads: whole round is a no-op
+__device__ __forceinline__ void msm_combine_heads_step(g1_xyzz_mem_t* __restrict__ heads, const uint32_t* __restrict__ head_bucket,
+                                                       const uint32_t* __restrict__ offsets, uint32_t t, uint32_t nthreads_total,
+                                                       uint32_t chunk, uint32_t stride) {
+    if (t >= nthreads_total) return;
     const uint32_t k = head_bucket[t];
     if (k == MSM_NONE) return;
     const uint32_t ta = offsets[k] / chunk, tb = (offsets[k + 1] - 1) / chunk;
@@ -366,14 +364,10 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_heads_kernel(g1_x
     g1_add(a, b);
     g1_xyzz_store(heads + t, a);
 }
-
 // bucket = tail of the thread where it starts + the (already summed) heads of the following threads
-__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_tails_kernel(g1_xyzz_mem_t* __restrict__ buckets,
-                                                                           const g1_xyzz_mem_t* __restrict__ heads,
-                                                                           const g1_xyzz_mem_t* __restrict__ tails,
-                                                                           const uint32_t* __restrict__ tail_bucket,
-                                                                           uint32_t nthreads_total) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void msm_combine_tails_step(g1_xyzz_mem_t* __restrict__ buckets, const g1_xyzz_mem_t* __restrict__ heads,
+                                                       const g1_xyzz_mem_t* __restrict__ tails, const uint32_t* __restrict__ tail_bucket,
+                                                       uint32_t t, uint32_t nthreads_total) {
     if (t >= nthreads_total) return;
     const uint32_t k = tail_bucket[t];
     if (k == MSM_NONE) return;
@@ -381,6 +375,45 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_tails_kernel(g1_x
     g1_xyzz_t b = g1_xyzz_load(heads + t + 1);
     g1_add(a, b);
     g1_xyzz_store(buckets + k, a);
+}
+
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_heads_kernel(g1_xyzz_mem_t* __restrict__ heads,
+                                                                           const uint32_t* __restrict__ head_bucket,
+                                                                           const uint32_t* __restrict__ offsets,
+                                                                           const uint32_t* __restrict__ max_heads,
+                                                                           uint32_t nthreads_total, uint32_t chunk,
+                                                                           uint32_t stride) {
+    if (stride >= *max_heads) return;                          // no bucket has that many heads: whole round is a no-op
+    msm_combine_heads_step(heads, head_bucket, offsets, blockIdx.x * blockDim.x + threadIdx.x, nthreads_total, chunk, stride);
+}
+
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_tails_kernel(g1_xyzz_mem_t* __restrict__ buckets,
+                                                                           const g1_xyzz_mem_t* __restrict__ heads,
+                                                                           const g1_xyzz_mem_t* __restrict__ tails,
+                                                                           const uint32_t* __restrict__ tail_bucket,
+                                                                           uint32_t nthreads_total) {
+    msm_combine_tails_step(buckets, heads, tails, tail_bucket, blockIdx.x * blockDim.x + threadIdx.x, nthreads_total);
+}
+
+// All rounds and the tails in ONE cooperative launch, for grids that are resident as a whole (small calls): the number
+// of rounds is known on the device only (max_heads), so the launcher above issues log2(longest possible span) launches
+// of which all but the first one or two return at once -- 16 launches, 0.12 ms of a 1.2 ms commit at 2^16.
+__global__ void __launch_bounds__(MSM_ACC_THREADS) msm_combine_coop_kernel(g1_xyzz_mem_t* __restrict__ buckets,
+                                                                          g1_xyzz_mem_t* __restrict__ heads,
+                                                                          const g1_xyzz_mem_t* __restrict__ tails,
+                                                                          const uint32_t* __restrict__ head_bucket,
+                                                                          const uint32_t* __restrict__ tail_bucket,
+                                                                          const uint32_t* __restrict__ offsets,
+                                                                          const uint32_t* __restrict__ max_heads,
+                                                                          uint32_t nthreads_total, uint32_t chunk) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t mh = *max_heads;                            // final: the accumulation kernel has completed
+    for (uint32_t stride = 1; stride < mh; stride <<= 1) {
+        msm_combine_heads_step(heads, head_bucket, offsets, t, nthreads_total, chunk, stride);
+        grid.sync();
+    }
+    msm_combine_tails_step(buckets, heads, tails, tail_bucket, t, nthreads_total);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -534,6 +567,37 @@ __global__ void __launch_bounds__(MSM_TREE_THREADS) msm_window_sum_kernel(g1_xyz
         __syncthreads();
     }
     if (tid == 0) out[(size_t)w * gridDim.y + blockIdx.y] = sh[0];
+}
+
+// The same sums for calls with so few inputs that the tree is one dependent chain on a mostly idle chip (a 2^16-point
+// commit: 4096 segment sums, 0.29 ms of its 1.29 ms in the two levels above -- ncu, profiles/r02_ncu_commit_2p16.txt):
+// a QUAD of lanes per running sum (ec_coop.cuh: 4 product latencies per addition instead of 14), 32 quads per block,
+// short slices (the launcher uses 128 inputs per block: 4 serial additions + 5 tree levels).
+__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_window_sum_quad_kernel(g1_xyzz_mem_t* __restrict__ out,
+                                                                              const g1_xyzz_mem_t* __restrict__ in,
+                                                                              uint32_t count, uint32_t per_block) {
+    __shared__ g1_xyzz_mem_t sh[MSM_TREE_THREADS / 4];
+    const Quad Q = quad_here();
+    const uint32_t w = blockIdx.x, qid = threadIdx.x >> 2, nquads = MSM_TREE_THREADS / 4;
+    const uint32_t lo = blockIdx.y * per_block;
+    const uint32_t hi = lo + per_block < count ? lo + per_block : count;
+    g1_xyzz_t acc = g1_xyzz_infinity();
+    for (uint32_t s = lo + qid; s < hi; s += nquads) {           // trip count is quad-uniform
+        const g1_xyzz_t v = g1_xyzz_load(in + (size_t)w * count + s);
+        g1_add_quad(Q, acc, v);
+    }
+    if (Q.q == 0) g1_xyzz_store(&sh[qid], acc);
+    __syncthreads();
+    for (uint32_t d = nquads / 2; d >= 1; d >>= 1) {
+        if (qid < d) {
+            g1_xyzz_t a = g1_xyzz_load(&sh[qid]);
+            const g1_xyzz_t b = g1_xyzz_load(&sh[qid + d]);
+            g1_add_quad(Q, a, b);
+            if (Q.q == 0) g1_xyzz_store(&sh[qid], a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)w * gridDim.y + blockIdx.y] = sh[0];
 }
 
 __device__ __forceinline__ void store_jacobian(uint4* out, const g1_xyzz_t& p) {
@@ -755,6 +819,8 @@ static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n
     if ((size_t)n * pl->sh.nwin >= ((size_t)1 << 32)) return b200_err(B200_ERR_TOO_LARGE, "msm: n * windows overflows 32-bit offsets");
     // segment length of the running-sum reduction: short segments when there are few buckets (latency), long
     // ones when there are many (each segment pays a ~c-step double-and-add for its offset)
+    // (up to 2^15 buckets -- a commit against <= 2^16 powers -- the reduction is ONE dependent chain per quad of lanes:
+    // 4-bucket segments make it 8 additions + a 13-step offset instead of 16 + 12)
     uint32_t seg_len = 8;
     while (seg_len < 64 && pl->K / seg_len > 65536) seg_len <<= 1;
     if (seg_len > pl->sh.nbuckets) seg_len = pl->sh.nbuckets;
@@ -807,6 +873,23 @@ extern "C" void b200_msm_describe(size_t n, uint32_t* out4) {
     out4[1] = sh.nwin;
     out4[2] = msm_affine_rounds(n_eff * sh.nwin, (size_t)sh.nwin * sh.nbuckets);
     out4[3] = glv ? 1u : 0u;
+}
+
+// blocks of msm_combine_coop_kernel that are resident at once on the current device (0: cooperative launch unsupported)
+static unsigned msm_combine_coop_capacity() {
+    static std::atomic<int> cached{-1};
+    int v = cached.load(std::memory_order_relaxed);
+    if (v >= 0) return (unsigned)v;
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_combine_coop_kernel, MSM_ACC_THREADS, 0) == cudaSuccess)
+        v = sms * per_sm;
+    else
+        (void)cudaGetLastError();
+    cached.store(v, std::memory_order_relaxed);
+    return (unsigned)v;
 }
 
 // bucket array (K x XYZZ) of one range of points; d_buckets is overwritten
@@ -978,6 +1061,20 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     // window of every point lands in ONE bucket set, so "at most n" does not hold: n * nwin equal digits are possible).
     // Rounds above the device-side maximum return at once, so the extra launches of the bound are cheap.
     const size_t max_span = (acc_E + chunk - 1) / chunk + 1;
+    if (tblocks <= msm_combine_coop_capacity()) {
+        g1_xyzz_mem_t* a_buckets = d_buckets;
+        g1_xyzz_mem_t* a_heads = heads.as<g1_xyzz_mem_t>();
+        const g1_xyzz_mem_t* a_tails = tails.as<g1_xyzz_mem_t>();
+        const uint32_t* a_hb = head_bucket.as<uint32_t>();
+        const uint32_t* a_tb = tail_bucket.as<uint32_t>();
+        const uint32_t* a_off = acc_off;
+        const uint32_t* a_mh = max_heads.as<uint32_t>();
+        uint32_t a_tmax = (uint32_t)t_max, a_chunk = chunk;
+        void* args[] = {&a_buckets, &a_heads, &a_tails, &a_hb, &a_tb, &a_off, &a_mh, &a_tmax, &a_chunk};
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void*)msm_combine_coop_kernel, dim3(tblocks), dim3(MSM_ACC_THREADS), args, 0, stream));
+        B200_LAUNCH_COUNT();
+        return b200_ok();
+    }
     for (uint32_t stride2 = 1; stride2 < max_span; stride2 <<= 1) {
         msm_combine_heads_kernel<<<tblocks, MSM_ACC_THREADS, 0, stream>>>(heads.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
                                                                          acc_off, max_heads.as<uint32_t>(), (uint32_t)t_max, chunk, stride2);
@@ -1017,7 +1114,25 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
             segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
     KERNEL_CHECK();
     STAGE("msm_window_sum", stream);
-    {
+    if (nseg_threads <= 8192 && pl.segs_per_win > 1) {
+        // latency-bound: quads, 128 inputs per block, then the (<= 64) slice sums of each window
+        const uint32_t per_block = 128;
+        const uint32_t slices = (pl.segs_per_win + per_block - 1) / per_block;
+        if (slices > 1) {
+            DevBuf slice_sums;
+            CUDA_TRY(slice_sums.alloc((size_t)slices * vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
+            msm_window_sum_quad_kernel<<<dim3(vsh.nwin, slices), MSM_TREE_THREADS, 0, stream>>>(
+                slice_sums.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), pl.segs_per_win, per_block);
+            KERNEL_CHECK();
+            msm_window_sum_quad_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
+                wsum.as<g1_xyzz_mem_t>(), slice_sums.as<g1_xyzz_mem_t>(), slices, slices);
+            KERNEL_CHECK();
+        } else {
+            msm_window_sum_quad_kernel<<<dim3(vsh.nwin, 1), MSM_TREE_THREADS, 0, stream>>>(
+                wsum.as<g1_xyzz_mem_t>(), segs.as<g1_xyzz_mem_t>(), pl.segs_per_win, pl.segs_per_win);
+            KERNEL_CHECK();
+        }
+    } else {
         // level 1: slices of >= 4 * MSM_TREE_THREADS segment results per block; level 2: the slice sums of each window
         const uint32_t per_block = 4 * MSM_TREE_THREADS;
         const uint32_t slices = (pl.segs_per_win + per_block - 1) / per_block;
