@@ -12,6 +12,16 @@ from . import _lib
 
 FR_TWO_ADICITY = 47
 FR_BYTES = 32
+# BLS12-377 scalar field: r, the multiplicative generator snarkVM uses, and its 2^47-th root of unity
+FR_MODULUS = 0x12AB655E9A2CA55660B44D1E5C37B00159AA76FED00000010A11800000000001
+FR_GENERATOR = 22
+FR_TWO_ADIC_ROOT_OF_UNITY = pow(FR_GENERATOR, (FR_MODULUS - 1) >> FR_TWO_ADICITY, FR_MODULUS)
+
+
+def fr_to_mont_limbs(x: int) -> np.ndarray:
+    """canonical integer -> snarkVM's in-memory Fr: 4 x u64 little-endian limbs of x * 2^256 mod r"""
+    v = (x % FR_MODULUS) * (1 << 256) % FR_MODULUS
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
 MAX_LOG_SIZE = 28            # library limit (2^28 elements = 8 GiB); snarkVM's own limit is the 2-adicity, 47
 
 try:
@@ -36,6 +46,43 @@ class EvaluationDomain:
             raise ValueError("EvaluationDomain::new: domain larger than 2^47 (snarkVM returns None)")
         self.size = size
         self.log_size_of_group = log
+        # the remaining fields of snarkVM's struct, as canonical integers (fr_to_mont_limbs gives the in-memory form);
+        # the CUDA library derives the same values for its twiddle tables (ntt.cu: get_tables)
+        self.size_as_field_element = size % FR_MODULUS
+        self.size_inv = pow(size, -1, FR_MODULUS)
+        self.group_gen = pow(FR_TWO_ADIC_ROOT_OF_UNITY, 1 << (FR_TWO_ADICITY - log), FR_MODULUS)
+        self.group_gen_inv = pow(self.group_gen, -1, FR_MODULUS)
+        self.generator_inv = pow(FR_GENERATOR, -1, FR_MODULUS)
+
+    def elements(self):
+        """`EvaluationDomain::elements()`: 1, g, g^2, ... (canonical integers)"""
+        x = 1
+        for _ in range(self.size):
+            yield x
+            x = x * self.group_gen % FR_MODULUS
+
+    def evaluate_vanishing_polynomial(self, tau: int) -> int:
+        """Z_H(tau) = tau^size - 1"""
+        return (pow(tau, self.size, FR_MODULUS) - 1) % FR_MODULUS
+
+    # out-of-place forms (`fft`, `ifft`, `coset_fft`, `coset_ifft`): the input is left alone
+    def fft(self, coeffs):
+        return self._run(self._copy(coeffs), 0, 0)
+
+    def ifft(self, evals):
+        return self._run(self._copy(evals), 1, 0)
+
+    def coset_fft(self, coeffs):
+        return self._run(self._copy(coeffs), 0, 1)
+
+    def coset_ifft(self, evals):
+        return self._run(self._copy(evals), 1, 1)
+
+    @staticmethod
+    def _copy(x):
+        if torch is not None and isinstance(x, torch.Tensor):
+            return x.clone()
+        return np.array(x, copy=True)
 
     @classmethod
     def new(cls, num_coeffs: int) -> "EvaluationDomain":
