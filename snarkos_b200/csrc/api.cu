@@ -327,6 +327,8 @@ static void config_from_env(B200Config& c) {
     c.msm_affine_rounds = env_int("B200_MSM_AFFINE_ROUNDS", -1);
     c.msm_slices = env_int("B200_MSM_SLICES", 1);
     c.msm_chunk = env_int("B200_MSM_CHUNK", 0);
+    c.msm_seg_len = env_int("B200_MSM_SEG_LEN", 0);
+    c.msm_reduce_quad_max = env_int("B200_MSM_REDUCE_QUAD_MAX", 8192);
     c.msm_host_pipeline = !getenv("B200_MSM_NO_HOST_PIPELINE");
     c.msm_host_first_log = env_int("B200_MSM_HOST_FIRST_LOG", 20);
     c.msm_host_chunk_log = env_int("B200_MSM_HOST_CHUNK_LOG", 23);
@@ -360,6 +362,8 @@ extern "C" b200_error_t b200_set_option(const char* key, const char* value) {
     else if (k == "msm_affine_rounds") c.msm_affine_rounds = v;
     else if (k == "msm_slices") c.msm_slices = v;
     else if (k == "msm_chunk") c.msm_chunk = v;
+    else if (k == "msm_seg_len") c.msm_seg_len = v;
+    else if (k == "msm_reduce_quad_max") c.msm_reduce_quad_max = v;
     else if (k == "msm_host_pipeline") c.msm_host_pipeline = v != 0;
     else if (k == "msm_host_first_log") c.msm_host_first_log = v;
     else if (k == "msm_host_chunk_log") c.msm_host_chunk_log = v;

@@ -42,6 +42,8 @@ struct B200Config {
     int msm_affine_rounds = -1;      // msm_affine_rounds        B200_MSM_AFFINE_ROUNDS -1 = automatic
     int msm_slices = 1;              // msm_slices               B200_MSM_SLICES
     int msm_chunk = 0;               // msm_chunk                B200_MSM_CHUNK         0 = automatic
+    int msm_seg_len = 0;             // msm_seg_len              B200_MSM_SEG_LEN       buckets per running-sum segment of the reduction, 0 = automatic
+    int msm_reduce_quad_max = 8192;  // msm_reduce_quad_max      B200_MSM_REDUCE_QUAD_MAX  up to this many segments: four lanes per segment (ec_coop.cuh)
     bool msm_host_pipeline = true;   // msm_host_pipeline        B200_MSM_NO_HOST_PIPELINE
     int msm_host_first_log = 20;     // msm_host_first_log       B200_MSM_HOST_FIRST_LOG
     int msm_host_chunk_log = 23;     // msm_host_chunk_log       B200_MSM_HOST_CHUNK_LOG  host calls of >= 2^this points are streamed

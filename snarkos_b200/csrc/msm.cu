@@ -823,6 +823,7 @@ static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n
     // 4-bucket segments make it 8 additions + a 13-step offset instead of 16 + 12)
     uint32_t seg_len = 8;
     while (seg_len < 64 && pl->K / seg_len > 65536) seg_len <<= 1;
+    if (b200_config().msm_seg_len > 0) seg_len = (uint32_t)b200_config().msm_seg_len;
     if (seg_len > pl->sh.nbuckets) seg_len = pl->sh.nbuckets;
     pl->seg_len = seg_len;
     pl->segs_per_win = (pl->sh.nbuckets + seg_len - 1) / seg_len;
@@ -1106,7 +1107,8 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
     CUDA_TRY(wsum.alloc((size_t)vsh.nwin * sizeof(g1_xyzz_mem_t), stream));
     STAGE("msm_reduce_segments", stream);
     const uint32_t nseg_threads = pl.segs_per_win * vsh.nwin;
-    if (nseg_threads <= 8192)          // latency-bound: four lanes per segment
+    const bool quads = nseg_threads <= (uint32_t)b200_config().msm_reduce_quad_max;
+    if (quads)                         // latency-bound: four lanes per segment
         msm_reduce_segments_quad_kernel<<<(4 * nseg_threads + MSM_RED_THREADS - 1) / MSM_RED_THREADS, MSM_RED_THREADS, 0, stream>>>(
             segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
     else
@@ -1114,7 +1116,7 @@ static b200_error_t msm_back(const MsmPlan& pl, void* d_out, const g1_xyzz_mem_t
             segs.as<g1_xyzz_mem_t>(), d_buckets, vsh, pl.seg_len, pl.segs_per_win);
     KERNEL_CHECK();
     STAGE("msm_window_sum", stream);
-    if (nseg_threads <= 8192 && pl.segs_per_win > 1) {
+    if (quads && pl.segs_per_win > 1) {
         // latency-bound: quads, 128 inputs per block, then the (<= 64) slice sums of each window
         const uint32_t per_block = 128;
         const uint32_t slices = (pl.segs_per_win + per_block - 1) / per_block;
