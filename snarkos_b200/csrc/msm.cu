@@ -802,6 +802,20 @@ static uint32_t msm_glv_window_bits(size_t n_eff) {
     return (uint32_t)c;
 }
 
+// threads of msm_reduce_segments_kernel resident on the device at once (queried once per process)
+static size_t msm_reduce_wave_threads() {
+    static std::once_flag once;
+    static size_t wave = 148 * 256;
+    std::call_once(once, [] {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_reduce_segments_kernel, MSM_RED_THREADS, 0) == cudaSuccess &&
+            sms > 0 && per_sm > 0)
+            wave = (size_t)sms * per_sm * MSM_RED_THREADS;
+    });
+    return wave;
+}
+
 static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n_reg, uint32_t c_force, bool glv = false) {
     pl->glv = glv;
     if (glv) {
@@ -821,8 +835,17 @@ static b200_error_t msm_make_plan(MsmPlan* pl, size_t n, uint32_t nmsm, size_t n
     // ones when there are many (each segment pays a ~c-step double-and-add for its offset)
     // (up to 2^15 buckets -- a commit against <= 2^16 powers -- the reduction is ONE dependent chain per quad of lanes:
     // 4-bucket segments make it 8 additions + a 13-step offset instead of 16 + 12)
+    // Above one wave of the reduction kernel (255 registers: 4 blocks of 64 threads per SM, 37888 threads on a B200)
+    // the segments grow so that the grid stays ONE wave: the kernel is a dependent chain per thread at 8 warps per SM,
+    // so a second wave costs a whole chain (2 * seg_len additions + the offset) while longer segments cost 2 additions
+    // per bucket.  2^24 points (7 x 2^18 buckets): 49 buckets per segment 2.8 ms, 32 (1.5 waves) 4.3 ms, 64 3.4 ms
+    // (tools/reduce_sweep.py, profiles/r02_reduce_sweep.jsonl).
     uint32_t seg_len = 8;
-    while (seg_len < 64 && pl->K / seg_len > 65536) seg_len <<= 1;
+    const size_t wave = msm_reduce_wave_threads();
+    if (pl->K / seg_len > wave) {
+        seg_len = (uint32_t)((pl->K + wave - 1) / wave);
+        while ((size_t)pl->vsh.nwin * ((pl->sh.nbuckets + seg_len - 1) / seg_len) > wave && seg_len < pl->sh.nbuckets) seg_len++;
+    }
     if (b200_config().msm_seg_len > 0) seg_len = (uint32_t)b200_config().msm_seg_len;
     if (seg_len > pl->sh.nbuckets) seg_len = pl->sh.nbuckets;
     pl->seg_len = seg_len;
