@@ -74,7 +74,7 @@ b200_error_t b200_release_scratch(void);
 uint32_t b200_abi_version(void);
 /* Tuning knobs.  The B200_* environment variables are read once, on first use; this call changes a knob afterwards
  * (sweep tools, tests, the -sys crate's init).  Keys: msm_window_bits, msm_glv, msm_affine_rounds, msm_slices,
- * msm_chunk, msm_host_pipeline, msm_host_first_log, msm_host_chunk_log, msm_stream_two, msm_auto_table, msm_list_budget_bytes,
+ * msm_chunk, msm_seg_len, msm_reduce_quad_max, msm_host_pipeline, msm_host_first_log, msm_host_chunk_log, msm_stream_two, msm_auto_table, msm_list_budget_bytes,
  * msm_queue_threshold, msm_queue_linger_us, ntt_plan ("a,b,c"), ntt_tile_log, ntt_radix4, ntt_boundary_tables, ntt_host_pipeline, ntt_variant,
  * staged_copies.  Unknown key -> B200_ERR_INVALID_ARG. */
 b200_error_t b200_set_option(const char* key, const char* value);

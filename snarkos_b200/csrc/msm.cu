@@ -282,7 +282,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 #define MSM_NONE 0xffffffffu
 
 // DIRECT: the entry stream IS the point list (output of the batched-affine rounds), no index / sign indirection.
-template <bool DIRECT>
+// ADD: `buckets` holds the sums of earlier point ranges (streamed host path) and this range is added to them: a bucket's
+// walk starts from its stored sum instead of infinity -- the merge costs no product at all (a separate pass over the
+// bucket arrays is one general XYZZ addition, 14 products, per bucket and range); buckets without entries stay as they are.
+template <bool DIRECT, bool ADD>
 __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_xyzz_mem_t* __restrict__ buckets,
                                                                         g1_xyzz_mem_t* __restrict__ heads,
                                                                         g1_xyzz_mem_t* __restrict__ tails,
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
     uint32_t bucket_end = offsets[k + 1];
     bool from_start = (offsets[k] == e);
     g1_xyzz_t acc = g1_xyzz_infinity();
+    if (ADD && from_start) acc = g1_xyzz_load(buckets + k);
     uint32_t cur_id = DIRECT ? e : entries[e];
     g1_packed_t cur = DIRECT ? g1_load_planes(pts + 3 * (size_t)cur_id, pts_y + 3 * (size_t)cur_id) : g1_load_packed(pts + (size_t)(cur_id & 0x7fffffffu) * G1_BASE_U4);
     for (;;) {
@@ -342,7 +346,8 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, 3) msm_accumulate_kernel(g1_x
             do { ++k; } while (offsets[k + 1] == e);          // next non-empty bucket starts exactly at e
             bucket_end = offsets[k + 1];
             from_start = true;
-            acc = g1_xyzz_infinity();
+            if (ADD) acc = g1_xyzz_load(buckets + k);
+            else acc = g1_xyzz_infinity();
         }
         cur = nxt;
         cur_id = nxt_id;
@@ -919,7 +924,7 @@ static unsigned msm_combine_coop_capacity() {
 // bucket array (K x XYZZ) of one range of points; d_buckets is overwritten
 static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const void* d_points, size_t n,
                               const void* d_scalars, size_t stride, const void* d_packed,
-                              const unsigned long long* d_seg_off, cudaStream_t stream) {
+                              const unsigned long long* d_seg_off, cudaStream_t stream, bool add_to = false) {
     const MsmShape& sh = pl.sh;
     const size_t K = pl.K;
     DevBuf packed, halves;
@@ -1069,16 +1074,18 @@ static b200_error_t msm_front(const MsmPlan& pl, g1_xyzz_mem_t* d_buckets, const
     CUDA_TRY(cudaMemsetAsync(max_heads.p, 0, 16, stream));
     CUDA_TRY(cudaMemsetAsync(head_bucket.p, 0xff, (t_max + 1) * 4, stream));
     CUDA_TRY(cudaMemsetAsync(tail_bucket.p, 0xff, t_max * 4, stream));
-    CUDA_TRY(cudaMemsetAsync(d_buckets, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
+    if (!add_to) CUDA_TRY(cudaMemsetAsync(d_buckets, 0, K * sizeof(g1_xyzz_mem_t), stream));      // ZZ = 0: empty buckets are infinity
     const unsigned tblocks = (unsigned)((t_max + MSM_ACC_THREADS - 1) / MSM_ACC_THREADS);
-    if (direct)
-        msm_accumulate_kernel<true><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
-            d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-            tail_bucket.as<uint32_t>(), acc_pts, acc_pts_y, nullptr, acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
-    else
-        msm_accumulate_kernel<false><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(
-            d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(),
-            tail_bucket.as<uint32_t>(), pts, nullptr, entries.as<uint32_t>(), acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk);
+#define MSM_ACC_ARGS_DIRECT d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(), \
+                            tail_bucket.as<uint32_t>(), acc_pts, acc_pts_y, nullptr, acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk
+#define MSM_ACC_ARGS_INDEXED d_buckets, heads.as<g1_xyzz_mem_t>(), tails.as<g1_xyzz_mem_t>(), head_bucket.as<uint32_t>(), \
+                             tail_bucket.as<uint32_t>(), pts, nullptr, entries.as<uint32_t>(), acc_off, max_heads.as<uint32_t>(), (uint32_t)K, chunk
+    if (direct && add_to) msm_accumulate_kernel<true, true><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(MSM_ACC_ARGS_DIRECT);
+    else if (direct) msm_accumulate_kernel<true, false><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(MSM_ACC_ARGS_DIRECT);
+    else if (add_to) msm_accumulate_kernel<false, true><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(MSM_ACC_ARGS_INDEXED);
+    else msm_accumulate_kernel<false, false><<<tblocks, MSM_ACC_THREADS, 0, stream>>>(MSM_ACC_ARGS_INDEXED);
+#undef MSM_ACC_ARGS_DIRECT
+#undef MSM_ACC_ARGS_INDEXED
     KERNEL_CHECK();
     STAGE("msm_combine", stream);
     // longest possible run of heads: a bucket holds at most all acc_E entries of the stream (with tabulated bases every
@@ -1265,15 +1272,17 @@ b200_error_t msm_stream_add(void* session, const void* d_points, size_t n, const
     MsmStream* st = reinterpret_cast<MsmStream*>(session);
     if (n == 0) return b200_ok();
     if (stream != st->main && std::find(st->others.begin(), st->others.end(), stream) == st->others.end()) st->others.push_back(stream);
-    std::unique_ptr<DevBuf> buckets(new DevBuf());
-    CUDA_TRY(buckets->alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream));
-    B200_TRY(msm_front(st->plan, buckets->as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
     for (auto& t : st->totals)
-        if (t.first == stream) {                              // this stream's running total: no cross-stream dependency
-            B200_TRY(msm_stream_merge(st->plan, t.second->as<g1_xyzz_mem_t>(), buckets->as<g1_xyzz_mem_t>(), stream));
+        if (t.first == stream) {
+            // this stream's running total (no cross-stream dependency): the range's XYZZ walk starts every bucket from
+            // the sum so far (msm_accumulate_kernel<.., ADD>), so there is no bucket array of its own and no merge pass
+            B200_TRY(msm_front(st->plan, t.second->as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream, true));
             STAGE_END(stream);                                // stages are per stream: the next one here may be a range away
             return b200_ok();
         }
+    std::unique_ptr<DevBuf> buckets(new DevBuf());
+    CUDA_TRY(buckets->alloc(st->plan.K * sizeof(g1_xyzz_mem_t), stream));
+    B200_TRY(msm_front(st->plan, buckets->as<g1_xyzz_mem_t>(), d_points, n, d_scalars, stride, nullptr, nullptr, stream));
     STAGE_END(stream);
     st->totals.emplace_back(stream, std::move(buckets));
     return b200_ok();
