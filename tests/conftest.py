@@ -32,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
 # run-time tuning knobs of the library (b200_set_option); the B200_* environment is only read on first use, so tests
 # change knobs through this fixture, which restores the defaults afterwards
 _OPTION_DEFAULTS = {
-    "msm_window_bits": 0, "msm_glv": 1, "msm_affine_rounds": -1, "msm_slices": 1, "msm_chunk": 0, "msm_host_pipeline": 1,
+    "msm_window_bits": 0, "msm_glv": 1, "msm_affine_rounds": -1, "msm_slices": 1, "msm_chunk": 0, "msm_seg_len": 0, "msm_reduce_quad_max": 8192, "msm_host_pipeline": 1,
     "msm_host_first_log": 20, "msm_host_chunk_log": 23, "msm_stream_two": 1, "msm_auto_table": 1, "msm_list_budget_bytes": 0, "msm_queue_threshold": 0, "msm_queue_linger_us": 100,
     "ntt_plan": "", "ntt_tile_log": 0, "ntt_radix4": 1, "ntt_boundary_tables": 1, "ntt_host_pipeline": 1, "ntt_variant": 0,
     "staged_copies": 1,

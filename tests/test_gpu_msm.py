@@ -297,6 +297,23 @@ def test_streamed_ranges_small(b200_opt, two, rounds, n, c, first_log, chunk_log
     assert gpu_msm(bases, scal) == oracle_msm(bases, scal)
 
 
+@pytest.mark.parametrize("seg_len,quad_max", [(1, 0), (3, 0), (7, 1 << 30), (49, 0), (49, 1 << 30), (100000, 0)])
+def test_bucket_reduction_segment_lengths(b200_opt, seg_len, quad_max):
+    """the running-sum reduction for segment lengths that do not divide the bucket count (the one-wave rule picks
+    ceil(K / resident threads), 49 at 2^24), with one lane and with a quad of lanes per segment"""
+    b200_opt("msm_seg_len", seg_len)
+    b200_opt("msm_reduce_quad_max", quad_max)
+    b200_opt("msm_window_bits", 9)
+    rng = O.SplitMix64(4242 + seg_len)
+    n = 3000
+    pts = O.random_points(rng, 40)
+    pts = [pts[(i * 11) % len(pts)] for i in range(n)]
+    sc = O.random_fr(rng, n)
+    sc[0], sc[1] = 0, O.R_MOD - 1
+    bases, scal = H.bases_array(pts), H.scalars_array(sc)
+    assert gpu_msm(bases, scal) == oracle_msm(bases, scal)
+
+
 def test_streamed_ranges_degenerate(b200_opt):
     """all scalars equal: ONE bucket per window holds every point of every range; all points equal: every pair is a
     doubling"""
