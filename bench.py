@@ -16,6 +16,7 @@ A "step" is one pass of the hot path over one batch of synthetic input: one Vari
 toolchain exists in the image, so there is no oracle/_ref to run).
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -67,7 +68,11 @@ def measured_peaks():
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi -lms 100 on THIS rank's GPU only, started before the warm-up steps (on an 8-GPU box nvidia-smi needs
+    several hundred ms to come up, longer than a short timed region) and filtered by its own timestamps to the timed
+    region [mark_begin, mark_end]; if no sample fell inside, the samples of the warm-up steps (the same workload) are
+    reported and `window` says so."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -75,13 +80,20 @@ class ClockSampler:
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.p is None:
@@ -95,23 +107,27 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in rows:
             try:
-                if int(r[0]) != self.gpu:
+                if int(r[1]) != self.gpu:
                     continue
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(names, r[5:9]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                parsed.append((ts, float(r[2]), float(r[3]), {n for n, v in zip(names, r[6:10]) if v.strip().lower().startswith("active")}))
             except Exception:
                 continue
-        if not sm:
+        if not parsed:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [x for x in parsed if self.t0 is not None and self.t1 is not None and self.t0 - 0.05 <= x[0] <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            inside, window = parsed, "warm-up + timed steps (no sample fell inside the timed region)"
+        sm = [x[1] for x in inside]
+        reasons = set().union(*[x[3] for x in inside])
         busy = [x for x in sm if x > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(x[2] for x in inside), "reasons": sorted(reasons),
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -240,17 +256,18 @@ def run_b200(args):
     def step_ntt():
         dom.fft_in_place(ntt_data)
 
+    sampler = ClockSampler(local)
+    sampler.start()                                        # comes up during the warm-up; samples are filtered by timestamp
     for _ in range(W):
         step_msm()
         step_ntt()
     barrier()
 
     # ---- timed region: exactly K steps ---------------------------------------------------------------------------
-    sampler = ClockSampler(local)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     launches0 = S.kernel_launch_count()
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     with S.profile() as prof:
         for i in range(K):
             ev[i][0].record()
@@ -259,6 +276,7 @@ def run_b200(args):
             step_ntt()
             ev[i][2].record()
         torch.cuda.synchronize()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop()
     launches = S.kernel_launch_count() - launches0
