@@ -107,6 +107,9 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
+        return self.summarise(rows)
+
+    def summarise(self, rows):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         parsed = []
         for r in rows:
