@@ -279,8 +279,8 @@ def test_host_buffer_streaming_path():
 @pytest.mark.parametrize("n,c,first_log,chunk_log", [(5000, 6, 10, 11), (3000, 4, 10, 10), (70000, 9, 12, 14)])
 def test_streamed_ranges_small(b200_opt, two, rounds, n, c, first_log, chunk_log):
     """the streamed host path at sizes the oracle finishes: ranges 2^first, 2^first, ... <= 2^chunk through three staging
-    buffers, alternating between the thread's two compute streams (two = 1), one bucket array per range, added up at
-    the finish"""
+    buffers, alternating between the thread's two compute streams (two = 1); the first range of a stream fills a bucket
+    array, later ranges are accumulated into it (msm_accumulate_kernel<.., ADD>), the two streams' arrays are added at the finish"""
     b200_opt("msm_host_chunk_log", chunk_log)
     b200_opt("msm_host_first_log", first_log)
     b200_opt("msm_window_bits", c)
